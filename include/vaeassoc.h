@@ -1,0 +1,179 @@
+/* libvaeassoc -- C-ABI of the B200-native associated-VAE train step.
+ *
+ * Drop-in boundary: the reference has no FFI layer; its model class funnels every
+ * arithmetic op through ONE TensorFlow entry point, `self.sess.run(fetches, feed_dict)`
+ * (/root/reference/vae_assoc.py:383,389,399,402,417,423).  Each function below replaces one of those
+ * sess.run call sites (cited per function).  The Python class `vae_assoc_b200.vae_assoc.
+ * AssocVariationalAutoEncoder` binds them with ctypes and keeps the reference's surface.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; `vaeassoc_last_error(h)` gives the text
+ *     (pass NULL for errors of vaeassoc_create).  No C++ exception crosses the ABI.
+ *   - a handle is bound to one CUDA device and one compute stream; calls on one handle are serialised by an
+ *     internal mutex (the reference's callers drive the model from a Qt worker thread,
+ *     baxter_vae_assoc_writer.py:654-674).
+ *   - all tensors are fp32, row-major.  `*_dev` pointers are device pointers, `*_host` host pointers.
+ *     The caller owns every I/O buffer; the library owns parameters, gradients, Adam slots, activations and
+ *     workspaces.
+ *   - there is NO CPU fallback: without a usable sm_100 device `vaeassoc_create` fails.
+ */
+#ifndef VAEASSOC_H_
+#define VAEASSOC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VAEASSOC_MAX_MODALITIES 4
+#define VAEASSOC_ABI_VERSION 1
+
+typedef struct vaeassoc_ctx* vaeassoc_handle;
+
+enum { VAEASSOC_RELU = 0, VAEASSOC_SOFTPLUS = 1 };                 /* transfer_fct, vae_assoc.py:26,502   */
+enum { VAEASSOC_FP32 = 0, VAEASSOC_TF32 = 1 };                     /* SIMT FFMA  |  tcgen05 kind::tf32    */
+enum { VAEASSOC_PARAMS = 0, VAEASSOC_GRADS = 1, VAEASSOC_ADAM_M = 2, VAEASSOC_ADAM_V = 3 };
+
+/* one entry of `network_architectures` (vae_assoc.py:73-76) plus its `binary` / `weights` items (:31-41) */
+typedef struct {
+  int32_t n_input;
+  int32_t n_hidden_recog_1, n_hidden_recog_2;
+  int32_t n_hidden_gener_1, n_hidden_gener_2;   /* used by the conv variant only (vae_assoc.py:252,264,269,274) */
+  int32_t hidden_conv;
+  int32_t binary;
+  float weight;
+} vaeassoc_modality;
+
+/* constructor arguments of AssocVariationalAutoEncoder (vae_assoc.py:26-27) */
+typedef struct {
+  int32_t abi_version;          /* VAEASSOC_ABI_VERSION */
+  int32_t n_modalities;
+  int32_t batch_size;           /* rows THIS handle processes per step (static, vae_assoc.py:90) */
+  int32_t n_z;
+  int32_t transfer_fct;
+  int32_t precision;
+  int32_t device;               /* CUDA ordinal */
+  int32_t use_graph;            /* replay the step as one CUDA graph */
+  float assoc_lambda;
+  float learning_rate;
+  float beta1, beta2, adam_epsilon;   /* tf.train.AdamOptimizer defaults: 0.9, 0.999, 1e-8 */
+  int64_t global_batch;         /* divisor of the batch-mean loss terms; 0 -> batch_size (single process) */
+  int64_t global_row0;          /* first global sample index of this shard (Philox counters) */
+  uint32_t eps_seed;
+  uint32_t reserved;
+  vaeassoc_modality mod[VAEASSOC_MAX_MODALITIES];
+} vaeassoc_config;
+
+/* logical tensor i (reference tf.Variable creation order) -> where it lives in the flat buffers */
+typedef struct {
+  char name[48];        /* TF-style variable name, e.g. "image/Variable_2", "image_1/Variable" */
+  char role[16];        /* "W1","b1",...,"Vo","co" (oracle/vae_assoc_oracle.py header) */
+  int32_t modality;
+  int32_t ndim;         /* 1, 2 or 4 */
+  int32_t shape[4];     /* logical shape, reference layout */
+  int64_t offset;       /* float offset of element [0,0] in every flat buffer */
+  int64_t rows, cols;   /* 2-D view: rows x cols (4-D conv filters: rows = kh*kw*d2, cols = d3) */
+  int64_t ld;           /* physical row stride (floats) */
+} vaeassoc_tensor_info;
+
+/* ---- lifetime ------------------------------------------------------------------------------------------ */
+/* replaces AssocVariationalAutoEncoder.__init__'s graph build + tf.InteractiveSession (vae_assoc.py:54-67) */
+int vaeassoc_create(const vaeassoc_config* cfg, vaeassoc_handle* out);
+int vaeassoc_destroy(vaeassoc_handle h);
+const char* vaeassoc_last_error(vaeassoc_handle h);
+int vaeassoc_abi_version(void);
+/* run the handle's work on an existing stream (e.g. torch's current stream); NULL -> the handle's own */
+int vaeassoc_set_stream(vaeassoc_handle h, void* cuda_stream);
+int vaeassoc_stream_sync(vaeassoc_handle h);
+int vaeassoc_set_precision(vaeassoc_handle h, int precision);
+int vaeassoc_set_learning_rate(vaeassoc_handle h, float lr);
+
+/* ---- parameters / optimiser state (replaces tf.Variable access; tf.train.Saver, vae_assoc.py:70) --------- */
+int vaeassoc_num_tensors(vaeassoc_handle h);
+int vaeassoc_layout_query(vaeassoc_handle h, int i, vaeassoc_tensor_info* out);
+int64_t vaeassoc_flat_size(vaeassoc_handle h);                       /* floats per flat buffer (padded)  */
+void* vaeassoc_flat_ptr(vaeassoc_handle h, int which);               /* device pointer of a flat buffer  */
+int vaeassoc_tensor_set(vaeassoc_handle h, int which, int i, const float* src_host);   /* dense, logical */
+int vaeassoc_tensor_get(vaeassoc_handle h, int which, int i, float* dst_host);
+int vaeassoc_step_get(vaeassoc_handle h, int64_t* step);             /* Adam step count t                */
+int vaeassoc_step_set(vaeassoc_handle h, int64_t step);
+
+/* ---- the hot path ------------------------------------------------------------------------------------------
+ * vaeassoc_train_step  replaces  sess.run((self.optimizer, self.cost), feed_dict)   vae_assoc.py:383-384
+ *   x_dev[m]  : [batch_size, n_input_m] device rows with leading dimension ld[m] (floats; NULL -> n_input_m)
+ *   eps_dev   : [batch_size, n_z] injected reparameterisation noise, or NULL -> Philox4x32-10
+ *               (key (eps_seed, 1), counter (global row, block, step)) replacing tf.random_normal :90
+ * The step is asynchronous; the scalar cost of step t lands in a device-side history ring and is fetched with
+ * vaeassoc_cost_read (which synchronises), so a training loop need not sync every step as the reference does.
+ * vaeassoc_grad_step = the same without the Adam update (gradients stay readable through VAEASSOC_GRADS). */
+int vaeassoc_train_step(vaeassoc_handle h, const float* const* x_dev, const int64_t* ld, const float* eps_dev);
+int vaeassoc_grad_step(vaeassoc_handle h, const float* const* x_dev, const int64_t* ld, const float* eps_dev);
+int vaeassoc_adam_step(vaeassoc_handle h);                            /* ApplyAdam on the current gradients */
+int vaeassoc_cost_read(vaeassoc_handle h, float* cost_host);          /* cost of the most recent step       */
+int vaeassoc_cost_history(vaeassoc_handle h, int64_t first_step, int64_t n, float* dst_host);
+/* host-buffer form of partial_fit (vae_assoc.py:378-386): H2D copy of X, one step, D2H of the cost.
+ * x_host[m] dense [batch_size, n_input_m]; eps_host may be NULL. */
+int vaeassoc_partial_fit_host(vaeassoc_handle h, const float* const* x_host, const float* eps_host,
+                              float* cost_host);
+/* pipelined host form used by train(): uploads batch k+1 on a copy stream while step k computes.
+ * `vaeassoc_submit_host` returns as soon as the batch is queued; costs are read back with
+ * vaeassoc_cost_history / vaeassoc_cost_read. */
+int vaeassoc_submit_host(vaeassoc_handle h, const float* const* x_host, const float* eps_host);
+
+/* evaluate_cost (vae_assoc.py:388-391): forward + loss, no gradients, no update */
+int vaeassoc_eval_cost(vaeassoc_handle h, const float* const* x_dev, const int64_t* ld, const float* eps_dev,
+                       float* cost_host);
+/* transform (vae_assoc.py:393-403): z_mean (and log sigma^2) of one modality; outputs dense [B, n_z] device */
+int vaeassoc_encode(vaeassoc_handle h, int modality, const float* x_dev, int64_t ld, float* mu_dev,
+                    float* logvar_dev);
+/* generate (vae_assoc.py:405-419): feeds z directly; xhat_dev dense [B, n_input_m] device */
+int vaeassoc_decode(vaeassoc_handle h, int modality, const float* z_dev, float* xhat_dev);
+/* reconstruct (vae_assoc.py:421-425): encode + sample + decode of ONE modality */
+int vaeassoc_reconstruct(vaeassoc_handle h, int modality, const float* x_dev, int64_t ld, const float* eps_dev,
+                         float* xhat_dev);
+
+/* the probe points of vae_assoc.py:545-571 after the most recent step.  kind: */
+enum {
+  VAEASSOC_PROBE_Z_MEAN = 0,        /* [B, n_z]  per modality          vae_assoc.py:114 */
+  VAEASSOC_PROBE_Z_LOG_SIGMA_SQ,    /* [B, n_z]                        :115 */
+  VAEASSOC_PROBE_Z,                 /* [B, n_z]                        :116 */
+  VAEASSOC_PROBE_X_RECONSTR_MEAN,   /* [B, n_input_m]                  :117 */
+  VAEASSOC_PROBE_RECONSTR_LOSS,     /* [B] (binary) or [1] (Gaussian)  :338 */
+  VAEASSOC_PROBE_LATENT_LOSS,       /* [B]                             :339 */
+  VAEASSOC_PROBE_VAE_COST,          /* [1]                             :340 */
+  VAEASSOC_PROBE_ASSOC_COST,        /* [1]  sum over modality pairs    :344-366 (modality ignored) */
+  VAEASSOC_PROBE_D_Z_MEAN,          /* [B, n_z]  d cost / d z_mean     (autodiff of :373-374) */
+  VAEASSOC_PROBE_D_Z_LOG_SIGMA_SQ,  /* [B, n_z] */
+  VAEASSOC_PROBE_EPS                /* [B, n_z]  the noise the step used (modality ignored) */
+};
+int vaeassoc_probe_get(vaeassoc_handle h, int kind, int modality, float* dst_host, int64_t capacity_floats,
+                       int64_t* n_written);
+
+/* ---- synthetic paired batches: replaces dataset.py:22-43 next_batch + utils.py:142-195 ------------------- */
+/* rows [row0, row0 + n_rows) of the global stream; x_dev[m] dense [n_rows, n_input_m] device */
+int vaeassoc_synth_batch(vaeassoc_handle h, uint32_t data_seed, uint32_t proj_seed, int64_t row0, int64_t n_rows,
+                         float* const* x_dev);
+/* Philox N(0,1) rows, exposed for tests and for generate(z_mu=None) (vae_assoc.py:414) */
+int vaeassoc_philox_normal(vaeassoc_handle h, uint32_t seed, uint32_t tag, int64_t row0, int64_t n_rows,
+                           int32_t n_cols, uint32_t step, float* dst_dev);
+
+/* ---- data parallelism (new; the reference is single process) ------------------------------------------------
+ * One NCCL all-reduce(SUM) per gradient bucket on a communication stream, overlapped with the rest of the
+ * backward pass; the scalar cost rides in a spare slot of the flat gradient buffer. */
+int vaeassoc_comm_unique_id(const char* nccl_lib_path, void* id128);           /* rank 0: ncclGetUniqueId   */
+int vaeassoc_comm_init(vaeassoc_handle h, const char* nccl_lib_path, const void* id128, int rank, int world);
+int vaeassoc_comm_destroy(vaeassoc_handle h);
+
+/* ---- introspection for benchmarks --------------------------------------------------------------------------- */
+/* number of kernels this library launched on the handle since creation (bench.py's gpu_launches) */
+int64_t vaeassoc_launch_count(vaeassoc_handle h);
+/* per-op timing of one eager (non-graph) step with CUDA events: names[i] (<=32 chars) and ms[i]; returns the
+ * number of ops written (<= capacity) or a negative error */
+int vaeassoc_profile_step(vaeassoc_handle h, const float* const* x_dev, const int64_t* ld, const float* eps_dev,
+                          char* names, float* ms, double* flops, double* bytes, int capacity);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VAEASSOC_H_ */

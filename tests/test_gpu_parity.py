@@ -1,0 +1,269 @@
+"""Parity of the CUDA path (through the C-ABI) against the fp64 oracle.  Needs a B200: `pytest -m gpu`.
+
+Tolerances (BASELINE.json north_star): relative 1e-4 on the fp32 path, 2e-3 on the TF32 tensor-core path, where
+"relative" is max|a-b| / max|b| per tensor (element-wise ratios are meaningless for entries near zero).
+PARITY UNPINNED by the reference (no TensorFlow here, no reference fixtures): the oracle is the CPU restatement
+in oracle/, itself checked by tests/test_oracle.py.
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import make_golden, philox, synth          # noqa: E402  (test infrastructure)
+from oracle import vae_assoc_oracle as vo              # noqa: E402
+
+TOL = {"fp32": 1e-4, "tf32": 2e-3}
+
+
+def rel(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.fixture(scope="module")
+def va():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    from vae_assoc_b200 import build, vae_assoc
+    build.build(verbose=False)
+    return vae_assoc
+
+
+def make_pair(va, archs, batch, f, precision, seed=0, lam=8.0, weights=(50.0, 1.0), binary=(True, False), **kw):
+    model = va.AssocVariationalAutoEncoder(archs, list(binary), transfer_fct=f, weights=list(weights), assoc_lambda=lam,
+                                           learning_rate=1e-3, batch_size=batch, precision=precision, seed=seed, **kw)
+    params = model.get_params()
+    per_mod, k = [], 0
+    for na in archs:
+        n = len(vo.param_names(na))
+        per_mod.append([p.astype(np.float64) for p in params[k:k + n]]); k += n
+    # non-zero biases so that every bias path is exercised
+    rng = np.random.RandomState(seed + 100)
+    per_mod = [[p if p.ndim > 1 else rng.normal(size=p.shape) * 0.05 for p in ps] for ps in per_mod]
+    model.set_params(per_mod)
+    per_mod = [[p.astype(np.float32).astype(np.float64) for p in ps] for ps in per_mod]
+    oracle = vo.OracleAssocVAE(archs, list(binary), f, list(weights), lam, 1e-3, batch, params=per_mod)
+    return model, oracle
+
+
+def inputs(archs, batch, seed, binary=(True, False)):
+    X = synth.synth_batch(archs, list(binary), data_seed=seed, proj_seed=1, row0=0, n_rows=batch)
+    X = [x.astype(np.float32) for x in X]
+    eps = philox.eps_rows(seed, 0, 0, batch, archs[0]["n_z"]).astype(np.float32)
+    return X, eps
+
+
+# ---------------------------------------------------------------------------------------------------------
+def test_philox_and_generator_match_oracle(va):
+    archs = vo.reference_archs(4)
+    model = va.AssocVariationalAutoEncoder(archs, [True, False], transfer_fct="relu", batch_size=8, precision="fp32")
+    got = model.philox_normal(7, philox.TAG_EPS, 5, 64, 6, step=3).cpu().numpy()
+    want = philox.normal_rows(7, philox.TAG_EPS, 5, 64, 6, step=3)
+    assert np.abs(got - want).max() < 2e-5
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "oracle_golden.npz"))
+    assert np.abs(model.philox_normal(7, 1, 5, 4, 6, step=3).cpu().numpy() - g["philox/eps_seed7_step3_row5"]).max() < 2e-5
+    xs = model.synth_batch(1000, 512)
+    ref = synth.synth_batch(archs, [True, False], 0, 1, 1000, 512)
+    img, jnt = xs[0].cpu().numpy(), xs[1].cpu().numpy()
+    # thresholded pixels can flip when sigmoid(logit) and u1 agree to the last ulp: allow a vanishing fraction
+    lit_mismatch = ((img > 0) != (ref[0] > 0)).mean()
+    assert lit_mismatch < 1e-4
+    same = (img > 0) == (ref[0] > 0)
+    assert np.abs(img - ref[0])[same].max() < 1e-6
+    assert np.abs(jnt - ref[1]).max() < 2e-5
+    assert img.min() == 0.0 and 0.1 < (img > 0).mean() < 0.35 and img[img > 0].min() >= 0.5
+    # a shard of the stream equals the same rows of the global stream
+    a = model.synth_batch(0, 64)[1].cpu().numpy()
+    b = model.synth_batch(32, 32)[1].cpu().numpy()
+    assert np.array_equal(a[32:], b)
+
+
+@pytest.mark.parametrize("f", ["relu", "softplus"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("batch", [1, 64, 100])
+def test_gradient_step_reference_config(va, f, precision, batch):
+    archs = vo.reference_archs(4)
+    model, oracle = make_pair(va, archs, batch, f, precision, seed=batch)
+    X, eps = inputs(archs, batch, seed=batch)
+    cost = model.compute_gradients(X, eps)
+    c_ref, g_ref, pr = oracle.loss_and_grads(X, eps)
+    tol = TOL[precision]
+    assert abs(cost - c_ref) <= tol * abs(c_ref), (cost, c_ref)
+    for m in range(2):
+        assert rel(model.z_means[m], pr["z_means"][m]) < tol
+        assert rel(model.z_log_sigma_sqs[m], pr["z_log_sigma_sqs"][m]) < tol
+        assert rel(model.z_array[m], pr["z_array"][m]) < tol
+        assert rel(model.x_reconstr_means[m], pr["x_reconstr_means"][m]) < tol
+        assert rel(model.vae_latent_losses[m], pr["vae_latent_losses"][m]) < tol
+        assert rel(model.vae_reconstr_losses[m], pr["vae_reconstr_losses"][m]) < tol
+        assert rel(model.vae_costs[m], pr["vae_costs"][m]) < tol
+        assert rel(model.d_z_means[m], pr["d_z_means"][m]) < tol
+        assert rel(model.d_z_log_sigma_sqs[m], pr["d_z_log_sigma_sqs"][m]) < tol
+    assert rel(model.assoc_costs[0], pr["assoc_costs"][0]) < max(tol, 1e-4)
+    grads = model.get_grads()
+    flat_ref = [g for gs in g_ref for g in gs]
+    names = model.variable_roles()
+    for g, r, n in zip(grads, flat_ref, names):
+        assert g.shape == r.shape
+        assert rel(g, r) < tol, (n, rel(g, r))
+    model.close()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_training_steps_match_oracle(va, precision):
+    """cost, gradients-through-Adam and the updated parameters / Adam slots over several steps."""
+    archs = vo.reference_archs(4)
+    batch = 100
+    model, oracle = make_pair(va, archs, batch, "relu", precision, seed=3)
+    tol = TOL[precision]
+    for t in range(5):
+        X = [x.astype(np.float32) for x in synth.synth_batch(archs, [True, False], 0, 1, t * batch, batch)]
+        eps = philox.eps_rows(3, t, 0, batch, 4).astype(np.float32)
+        c = model.partial_fit(X, eps)
+        c_ref = oracle.partial_fit(X, eps)
+        assert abs(c - c_ref) <= tol * abs(c_ref), (t, c, c_ref)
+    params = model.get_params()
+    m, v, step = model.get_adam_state()
+    assert step == 5
+    flat = [p for ps in oracle.params for p in ps]
+    flat_m = [p for ps in oracle.m for p in ps]
+    flat_v = [p for ps in oracle.v for p in ps]
+    for i, n in enumerate(model.variable_roles()):
+        assert rel(params[i], flat[i]) < tol, (n, rel(params[i], flat[i]))
+        assert rel(m[i], flat_m[i]) < 5 * tol, (n, "m", rel(m[i], flat_m[i]))
+        assert rel(v[i], flat_v[i]) < 5 * tol, (n, "v", rel(v[i], flat_v[i]))
+    model.close()
+
+
+def test_large_batch_fp32(va):
+    """B = 8192 (BASELINE configs[1]) against the oracle: cost and every gradient tensor."""
+    archs = vo.reference_archs(4)
+    batch = 8192
+    model, oracle = make_pair(va, archs, batch, "relu", "fp32", seed=5)
+    xs = model.synth_batch(0, batch)
+    X = [x.cpu().numpy() for x in xs]
+    eps = philox.eps_rows(5, 0, 0, batch, 4).astype(np.float32)
+    cost = model.compute_gradients(xs, eps)
+    c_ref, g_ref, _ = oracle.loss_and_grads(X, eps)
+    assert abs(cost - c_ref) <= 1e-4 * abs(c_ref)
+    for g, r, n in zip(model.get_grads(), [g for gs in g_ref for g in gs], model.variable_roles()):
+        assert rel(g, r) < 1e-4, (n, rel(g, r))
+    model.close()
+
+
+def test_odd_shapes_and_three_modalities(va):
+    """ragged sizes (nothing a multiple of 4), n_z = 3, three modalities with all-pairs association (:346)."""
+    archs = make_golden.tiny_archs(3) + [dict(scope="third", hidden_conv=False, n_hidden_recog_1=9, n_hidden_recog_2=5,
+                                              n_hidden_gener_1=9, n_hidden_gener_2=5, n_input=13, n_z=3)]
+    binary, weights = (True, False, False), (2.0, 1.0, 0.5)
+    batch = 7
+    model, oracle = make_pair(va, archs, batch, "softplus", "fp32", seed=9, lam=0.7, weights=weights, binary=binary)
+    X, eps = inputs(archs, batch, 9, binary)
+    cost = model.compute_gradients(X, eps)
+    c_ref, g_ref, pr = oracle.loss_and_grads(X, eps)
+    assert abs(cost - c_ref) <= 1e-4 * abs(c_ref)
+    assert rel(model.assoc_costs[0], sum(pr["assoc_costs"])) < 1e-4
+    for g, r, n in zip(model.get_grads(), [g for gs in g_ref for g in gs], model.variable_roles()):
+        assert rel(g, r) < 1e-4, (n, rel(g, r))
+    model.close()
+
+
+def test_inference_surface(va):
+    """evaluate_cost / transform / generate / reconstruct (vae_assoc.py:388-425) against the oracle."""
+    archs = vo.reference_archs(4)
+    batch = 64
+    model, oracle = make_pair(va, archs, batch, "relu", "fp32", seed=2)
+    X, eps = inputs(archs, batch, 2)
+    assert abs(model.evaluate_cost(X, eps) - oracle.evaluate_cost(X, eps)) <= 1e-4 * abs(oracle.evaluate_cost(X, eps))
+    zt, zo = model.transform(X), oracle.transform(X)
+    for a, b in zip(zt, zo):
+        assert a.shape == (batch, 4) and rel(a, b) < 1e-4
+    assert rel(model.transform(X[0], sens_idx=0), zo[0]) < 1e-4
+    z_mu = np.zeros((batch, 4), np.float32); z_mu[0] = [0.5, -1.0, 2.0, 0.1]     # viewer pattern: row 0 only
+    go, gr = model.generate(z_mu=z_mu), oracle.generate(z_mu)
+    for a, b in zip(go, gr):
+        assert rel(a, b) < 1e-4
+    assert [g.shape for g in model.generate()] == [(batch, 784), (batch, 147)]
+    ro, rr = model.reconstruct(X, eps=eps), oracle.reconstruct(X, eps=eps)
+    for a, b in zip(ro, rr):
+        assert rel(a, b) < 1e-4
+    model.close()
+
+
+def test_host_path_device_path_graph_and_eager_agree(va):
+    import torch
+    archs = vo.reference_archs(4)
+    batch = 100
+    X, eps = inputs(archs, batch, 4)
+    outs = []
+    for use_graph, on_device in [(True, False), (True, True), (False, True)]:
+        model, _ = make_pair(va, archs, batch, "relu", "fp32", seed=4, use_graph=use_graph)
+        Xi = [torch.as_tensor(x).cuda() for x in X] if on_device else X
+        costs = [float(model.partial_fit(Xi, eps)) for _ in range(3)]
+        outs.append((costs, model.get_params()))
+        model.close()
+    for costs, params in outs[1:]:
+        np.testing.assert_allclose(costs, outs[0][0], rtol=2e-6)
+        for a, b in zip(params, outs[0][1]):
+            assert rel(a, b) < 1e-5
+
+
+def test_philox_eps_and_async_history(va):
+    """eps=None draws Philox noise addressed by (global row, step); the async path records every step's cost."""
+    archs = vo.reference_archs(4)
+    batch = 32
+    model, oracle = make_pair(va, archs, batch, "relu", "fp32", seed=6, eps_seed=77, global_row0=1000)
+    X, _ = inputs(archs, batch, 6)
+    costs_ref = []
+    for t in range(4):
+        model.partial_fit_async(X)
+        e = philox.eps_rows(77, t, 1000, batch, 4)
+        assert np.abs(model.last_eps - e).max() < 2e-5
+        costs_ref.append(oracle.partial_fit(X, model.last_eps.astype(np.float64)))
+    hist = model.cost_history(0, 4)
+    np.testing.assert_allclose(hist, costs_ref, rtol=1e-4)
+    model.close()
+
+
+def test_checkpoint_roundtrip_and_restore_semantics(va, tmp_path, capsys):
+    archs = vo.reference_archs(4)
+    batch = 16
+    model, _ = make_pair(va, archs, batch, "relu", "fp32", seed=8)
+    X, eps = inputs(archs, batch, 8)
+    model.partial_fit(X, eps)
+    path = tmp_path / "model_a.ckpt"
+    model.save_model(str(path))
+    assert path.exists()
+    want = model.partial_fit(X, eps)
+    other, _ = make_pair(va, archs, batch, "relu", "fp32", seed=99)
+    other.restore_model(str(tmp_path))                      # fname=None -> last *.ckpt in the folder (:446-451)
+    got = other.partial_fit(X, eps)
+    assert abs(got - want) <= 1e-6 * abs(want)
+    other.restore_model(str(tmp_path / "nope"))             # prints, does not raise (:461-462)
+    other.restore_model(str(tmp_path), "missing.ckpt")
+    out = capsys.readouterr().out
+    assert "Invalid or non-exist model folder." in out and "Invalid or non-exist model file." in out
+    model.close(); other.close()
+
+
+def test_train_loop_matches_reference_semantics(va):
+    """train() (vae_assoc.py:498-583): running average bookkeeping and return value."""
+    from vae_assoc_b200 import dataset
+    archs = vo.reference_archs(4)
+    np.random.seed(0)
+    Xs = synth.synth_batch(archs, [True, False], 0, 1, 0, 330)
+    data = np.concatenate(Xs, axis=1).astype(np.float32)
+    ds = dataset.construct_datasets(data, validation_ratio=.1, test_ratio=.1)
+    model, hist = va.train(ds, archs, binary=[True, False], weights=[50, 1], assoc_lambda=8, learning_rate=1e-3,
+                           batch_size=64, training_epochs=3, display_step=1, precision="fp32")
+    n_train = ds.train._data.shape[0]
+    assert len(hist) == 3 * (n_train // 64)
+    assert hist[n_train // 64 - 1] > 0 and np.isfinite(hist).all()
+    # costs fall over three epochs on this easy synthetic set
+    per_epoch = [hist[(e + 1) * (n_train // 64) - 1] for e in range(3)]
+    assert per_epoch[2] < per_epoch[0]
+    model.close()

@@ -1,0 +1,1140 @@
+// libvaeassoc C-ABI implementation: flat parameter layout, op schedule of the train step, CUDA-graph replay,
+// NCCL data parallelism.  See include/vaeassoc.h for the contract and the reference call sites each entry
+// point replaces.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/vaeassoc.h"
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace vaeassoc;
+
+namespace {
+
+// -------------------------------------------------------------------------------------------------------
+// errors
+// -------------------------------------------------------------------------------------------------------
+thread_local std::string g_create_error;
+
+[[noreturn]] void fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  throw std::runtime_error(buf);
+}
+
+#define CUDA_OK(expr)                                                                         \
+  do {                                                                                        \
+    cudaError_t e__ = (expr);                                                                 \
+    if (e__ != cudaSuccess) fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+inline int64_t round_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+// -------------------------------------------------------------------------------------------------------
+// NCCL through dlopen (torch ships libnccl.so.2; nothing is linked at build time)
+// -------------------------------------------------------------------------------------------------------
+struct NcclId { char internal[128]; };
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(NcclId*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  void load(const char* path) {
+    if (lib) return;
+    lib = dlopen(path && path[0] ? path : "libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) fail("dlopen(%s) failed: %s", path ? path : "libnccl.so.2", dlerror());
+#define NCCL_SYM(field, name)                                    \
+    *reinterpret_cast<void**>(&field) = dlsym(lib, name);        \
+    if (!field) fail("dlsym(%s) failed", name);
+    NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+    NCCL_SYM(CommInitRank, "ncclCommInitRank")
+    NCCL_SYM(CommDestroy, "ncclCommDestroy")
+    NCCL_SYM(AllReduce, "ncclAllReduce")
+    NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef NCCL_SYM
+  }
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mutex;
+constexpr int kNcclFloat = 7, kNcclSum = 0;
+
+// -------------------------------------------------------------------------------------------------------
+// schedule
+// -------------------------------------------------------------------------------------------------------
+struct Op {
+  std::string name;
+  std::function<void(cudaStream_t)> run;
+  double flops = 0, bytes = 0;
+  int launches = 1;
+};
+
+struct Mod {               // one modality (dense variant)
+  vaeassoc_modality cfg;
+  int ni, nip, r1, r1p, r2, r2p, nz, nh, nhp;
+  // float offsets in the flat buffers
+  int64_t W1, b1, W2, b2, Wh, bh, V1, c1, V2, c2, Vo, co;
+  // activations / gradients (device)
+  float *xin[2] = {nullptr, nullptr};   // dense [B, ni] upload buffers (host API, double buffered)
+  float *xs = nullptr, *h1 = nullptr, *h2 = nullptr, *hd = nullptr, *z = nullptr, *g1 = nullptr, *g2 = nullptr,
+        *xh = nullptr, *da = nullptr, *dg2 = nullptr, *dg1 = nullptr, *dz = nullptr, *dhd = nullptr,
+        *dh2 = nullptr, *dh1 = nullptr, *gstat = nullptr, *lat_loss = nullptr, *rec_loss = nullptr,
+        *partials = nullptr;
+  int recon_blocks = 0;
+  // synthetic generator state
+  float *P = nullptr, *inv_std = nullptr;
+  uint32_t proj_seed_built = 0xFFFFFFFFu;
+};
+
+}  // namespace
+
+struct vaeassoc_ctx {
+  vaeassoc_config cfg;
+  std::mutex mu;
+  std::string err;
+  int device = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr, comm_stream = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+  cudaEvent_t ev_bucket = nullptr, ev_comm = nullptr;
+  int64_t submit_count = 0;
+  std::vector<void*> allocs;
+  std::vector<Mod> mods;
+  std::vector<vaeassoc_tensor_info> tensors;
+  int64_t n_flat = 0;          // floats in the parameter part (multiple of 32)
+  int64_t bucket_split = 0;    // [0, split) decoders, [split, n_flat) encoders
+  float *p = nullptr, *g = nullptr, *m = nullptr, *v = nullptr, *p_tf32 = nullptr;   // g has n_flat + 32 floats
+  bool shadow_dirty = true;
+  float *eps = nullptr, *eps_in[2] = {nullptr, nullptr}, *lat_partials = nullptr, *scalars = nullptr;
+  float *cost_hist = nullptr, *last_cost = nullptr;
+  int hist_cap = 1 << 16;
+  int64_t* step_dev = nullptr;
+  int lat_blocks = 0;
+  bool round_z = false;
+  int64_t launches = 0;
+  // schedules
+  std::vector<Op> ops_fwd_enc, ops_latent_fwd, ops_fwd_dec, ops_loss, ops_bwd_dec, ops_latent_bwd, ops_bwd_enc;
+  std::vector<std::vector<Op>> ops_enc_mod, ops_dec_mod;   // per-modality forward slices (encode / decode)
+  std::vector<TcPlan*> plans;
+  // graphs
+  cudaGraphExec_t graph_train = nullptr, graph_grad = nullptr, graph_a1 = nullptr, graph_a2 = nullptr,
+                  graph_adam = nullptr;
+  int graph_train_nodes = 0, graph_grad_nodes = 0, graph_a1_nodes = 0, graph_a2_nodes = 0, graph_adam_nodes = 0;
+  // comm
+  void* comm = nullptr;
+  int rank = 0, world = 1;
+
+  template <typename T>
+  T* dalloc(int64_t n, bool zero = true) {
+    void* ptr = nullptr;
+    CUDA_OK(cudaMalloc(&ptr, (size_t)std::max<int64_t>(n, 1) * sizeof(T)));
+    if (zero) CUDA_OK(cudaMemset(ptr, 0, (size_t)std::max<int64_t>(n, 1) * sizeof(T)));
+    allocs.push_back(ptr);
+    return reinterpret_cast<T*>(ptr);
+  }
+};
+
+namespace {
+
+using Ctx = vaeassoc_ctx;
+
+int64_t global_batch(const Ctx* c) { return c->cfg.global_batch > 0 ? c->cfg.global_batch : c->cfg.batch_size; }
+int fwd_act(const Ctx* c) { return c->cfg.transfer_fct == VAEASSOC_SOFTPLUS ? ACT_SOFTPLUS : ACT_RELU; }
+
+// ---- layout --------------------------------------------------------------------------------------------
+void add_tensor(Ctx* c, int m, const char* scope, int scope_entry, int var_idx, const char* role, int ndim,
+                std::initializer_list<int> shape, int64_t offset, int64_t rows, int64_t cols, int64_t ld) {
+  vaeassoc_tensor_info t;
+  memset(&t, 0, sizeof t);
+  char sc[40];
+  if (scope_entry == 0) snprintf(sc, sizeof sc, "%s", scope);
+  else snprintf(sc, sizeof sc, "%s_%d", scope, scope_entry);
+  if (var_idx == 0) snprintf(t.name, sizeof t.name, "%s/Variable", sc);
+  else snprintf(t.name, sizeof t.name, "%s/Variable_%d", sc, var_idx);
+  snprintf(t.role, sizeof t.role, "%s", role);
+  t.modality = m;
+  t.ndim = ndim;
+  int i = 0;
+  for (int s : shape) t.shape[i++] = s;
+  t.offset = offset; t.rows = rows; t.cols = cols; t.ld = ld;
+  c->tensors.push_back(t);
+}
+
+void build_layout(Ctx* c) {
+  const int M = c->cfg.n_modalities;
+  const int nz = c->cfg.n_z;
+  int64_t off = 0;
+  auto take = [&](int64_t rows, int64_t ld) { int64_t o = off; off = round_up(off + rows * ld, 32); return o; };
+  c->mods.resize(M);
+  for (int m = 0; m < M; ++m) {
+    Mod& d = c->mods[m];
+    d.cfg = c->cfg.mod[m];
+    if (d.cfg.hidden_conv) fail("modality %d: hidden_conv=True (conv/deconv variant) is not available in this build", m);
+    d.ni = d.cfg.n_input; d.nip = (int)round_up(d.ni, 4);
+    d.r1 = d.cfg.n_hidden_recog_1; d.r1p = (int)round_up(d.r1, 4);
+    d.r2 = d.cfg.n_hidden_recog_2; d.r2p = (int)round_up(d.r2, 4);
+    d.nz = nz; d.nh = 2 * nz; d.nhp = (int)round_up(d.nh, 4);
+    if (d.ni <= 0 || d.r1 <= 0 || d.r2 <= 0) fail("modality %d: layer sizes must be positive", m);
+  }
+  // bucket 0: decoders, in the order their gradients complete (output layer first)
+  for (int m = 0; m < M; ++m) {
+    Mod& d = c->mods[m];
+    d.Vo = take(d.r2, d.nip); d.co = take(1, d.nip);
+    d.V2 = take(d.r1, d.r2p); d.c2 = take(1, d.r2p);
+    d.V1 = take(d.nz, d.r1p); d.c1 = take(1, d.r1p);
+  }
+  c->bucket_split = off;
+  // bucket 1: encoders
+  for (int m = 0; m < M; ++m) {
+    Mod& d = c->mods[m];
+    d.Wh = take(d.r2, d.nhp); d.bh = take(1, d.nhp);
+    d.W2 = take(d.r1, d.r2p); d.b2 = take(1, d.r2p);
+    d.W1 = take(d.ni, d.r1p); d.b1 = take(1, d.r1p);
+  }
+  c->n_flat = off;
+  // logical tensors in the reference's tf.Variable creation order (vae_assoc.py:93-111: per modality
+  // recognition (8 variables, scope "<scope>") then generator (6 variables, name scope "<scope>_1"))
+  // default scope names follow the reference script (vae_assoc_ujichar_img_jnt.py:54,64)
+  static const char* default_scopes[4] = {"image", "joint", "modal2", "modal3"};
+  for (int m = 0; m < M; ++m) {
+    const Mod& d = c->mods[m];
+    const char* sc = default_scopes[m];
+    add_tensor(c, m, sc, 0, 0, "W1", 2, {d.ni, d.r1}, d.W1, d.ni, d.r1, d.r1p);
+    add_tensor(c, m, sc, 0, 1, "b1", 1, {d.r1}, d.b1, 1, d.r1, d.r1p);
+    add_tensor(c, m, sc, 0, 2, "W2", 2, {d.r1, d.r2}, d.W2, d.r1, d.r2, d.r2p);
+    add_tensor(c, m, sc, 0, 3, "b2", 1, {d.r2}, d.b2, 1, d.r2, d.r2p);
+    add_tensor(c, m, sc, 0, 4, "Wmu", 2, {d.r2, nz}, d.Wh, d.r2, nz, d.nhp);
+    add_tensor(c, m, sc, 0, 5, "bmu", 1, {nz}, d.bh, 1, nz, d.nhp);
+    add_tensor(c, m, sc, 0, 6, "Wls", 2, {d.r2, nz}, d.Wh + nz, d.r2, nz, d.nhp);
+    add_tensor(c, m, sc, 0, 7, "bls", 1, {nz}, d.bh + nz, 1, nz, d.nhp);
+    add_tensor(c, m, sc, 1, 0, "V1", 2, {nz, d.r1}, d.V1, nz, d.r1, d.r1p);
+    add_tensor(c, m, sc, 1, 1, "c1", 1, {d.r1}, d.c1, 1, d.r1, d.r1p);
+    add_tensor(c, m, sc, 1, 2, "V2", 2, {d.r1, d.r2}, d.V2, d.r1, d.r2, d.r2p);
+    add_tensor(c, m, sc, 1, 3, "c2", 1, {d.r2}, d.c2, 1, d.r2, d.r2p);
+    add_tensor(c, m, sc, 1, 4, "Vo", 2, {d.r2, d.ni}, d.Vo, d.r2, d.ni, d.nip);
+    add_tensor(c, m, sc, 1, 5, "co", 1, {d.ni}, d.co, 1, d.ni, d.nip);
+  }
+}
+
+void alloc_buffers(Ctx* c) {
+  const int64_t B = c->cfg.batch_size;
+  const int nz = c->cfg.n_z;
+  c->p = c->dalloc<float>(c->n_flat);
+  c->g = c->dalloc<float>(c->n_flat + 32);
+  c->m = c->dalloc<float>(c->n_flat);
+  c->v = c->dalloc<float>(c->n_flat);
+  c->p_tf32 = c->dalloc<float>(c->n_flat);
+  c->eps = c->dalloc<float>(B * nz);
+  c->eps_in[0] = c->dalloc<float>(B * nz);
+  c->eps_in[1] = c->dalloc<float>(B * nz);
+  c->lat_partials = c->dalloc<float>((int64_t)kMaxPartialBlocks * kCostSlots);
+  c->scalars = c->dalloc<float>(16);
+  c->cost_hist = c->dalloc<float>(c->hist_cap);
+  c->last_cost = c->dalloc<float>(1);
+  c->step_dev = c->dalloc<int64_t>(1);
+  for (Mod& d : c->mods) {
+    d.xin[0] = c->dalloc<float>(B * d.ni);
+    d.xin[1] = c->dalloc<float>(B * d.ni);
+    d.xs = c->dalloc<float>(B * d.nip);
+    d.h1 = c->dalloc<float>(B * d.r1p);  d.h2 = c->dalloc<float>(B * d.r2p);
+    d.hd = c->dalloc<float>(B * d.nh);   d.z = c->dalloc<float>(B * nz);
+    d.g1 = c->dalloc<float>(B * d.r1p);  d.g2 = c->dalloc<float>(B * d.r2p);
+    d.xh = c->dalloc<float>(B * d.nip);  d.da = c->dalloc<float>(B * d.nip);
+    d.dg2 = c->dalloc<float>(B * d.r2p); d.dg1 = c->dalloc<float>(B * d.r1p);
+    d.dz = c->dalloc<float>(B * nz);     d.dhd = c->dalloc<float>(B * d.nh);
+    d.dh2 = c->dalloc<float>(B * d.r2p); d.dh1 = c->dalloc<float>(B * d.r1p);
+    d.gstat = c->dalloc<float>(B * d.nh);
+    d.lat_loss = c->dalloc<float>(B);    d.rec_loss = c->dalloc<float>(B);
+    d.partials = c->dalloc<float>((int64_t)kMaxPartialBlocks * kCostSlots);
+    d.P = c->dalloc<float>(4 * d.ni);    d.inv_std = c->dalloc<float>(d.ni);
+  }
+}
+
+// ---- op construction -------------------------------------------------------------------------------------
+enum { KIND_NN = 0, KIND_NT = 1, KIND_TN = 2 };
+
+// w_off >= 0: operand B is the weight at that flat offset (master fp32 for SIMT, tf32-rounded shadow for tcgen05)
+// round_out: the stored result feeds a tcgen05 kind::tf32 GEMM and is rounded (RNA) by this producer
+Op make_gemm(Ctx* c, const char* name, int m, int kind, GemmArgs a, int64_t w_off, bool round_out) {
+  Op op;
+  op.name = std::string(name) + "." + std::to_string(m);
+  const bool tf32 = c->cfg.precision == VAEASSOC_TF32;
+  a.round_out = (tf32 && round_out) ? 1 : 0;
+  op.flops = 2.0 * a.M * a.N * a.K;
+  op.bytes = 4.0 * ((double)a.M * a.K + (double)a.K * a.N + (double)a.M * a.N * (kind == KIND_NT && a.aux ? 2 : 1));
+  if (w_off >= 0) a.B = c->p_tf32 + w_off;
+  if (tf32 && tc_supported(kind, a)) {
+    char err[256] = {0};
+    TcPlan* plan = tc_plan_create(kind, a, err, sizeof err);
+    if (!plan) fail("tcgen05 plan for %s failed: %s", op.name.c_str(), err);
+    c->plans.push_back(plan);
+    op.name += ".tc";
+    op.run = [plan](cudaStream_t s) { launch_gemm_tc(plan, s); };
+    return op;
+  }
+  if (w_off >= 0) a.B = c->p + w_off;
+  switch (kind) {
+    case KIND_NN: op.run = [a](cudaStream_t s) { launch_gemm_nn_simt(a, s); }; break;
+    case KIND_NT: op.run = [a](cudaStream_t s) { launch_gemm_nt_simt(a, s); }; break;
+    default: op.run = [a](cudaStream_t s) { launch_gemm_tn_simt(a, s); }; break;
+  }
+  return op;
+}
+
+GemmArgs gemm_fwd(int B, int N, int K, const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
+                  float* C, int64_t ldc, int act) {
+  GemmArgs a;
+  a.M = B; a.N = N; a.K = K; a.A = A; a.lda = lda; a.B = W; a.ldb = ldw; a.C = C; a.ldc = ldc; a.bias = bias; a.act = act;
+  return a;
+}
+// dX[B,K] = (dY[B,N] . W[K,N]^T) (*) act'(H[B,K])
+GemmArgs gemm_dgrad(int B, int K, int N, const float* dY, int64_t lddy, const float* W, int64_t ldw, float* dX,
+                    int64_t lddx, const float* H, int64_t ldh, int act) {
+  GemmArgs a;
+  a.M = B; a.N = K; a.K = N; a.A = dY; a.lda = lddy; a.B = W; a.ldb = ldw; a.C = dX; a.ldc = lddx;
+  a.aux = H; a.ldaux = ldh; a.act = H ? act : ACT_NONE;
+  return a;
+}
+// dW[K,N] += X[B,K]^T . dY[B,N] ; db[N] += colsum(dY)
+GemmArgs gemm_wgrad(int B, int K, int N, const float* X, int64_t ldx, const float* dY, int64_t lddy, float* dW,
+                    int64_t lddw, float* db) {
+  GemmArgs a;
+  a.M = K; a.N = N; a.K = B; a.A = X; a.lda = ldx; a.B = dY; a.ldb = lddy; a.C = dW; a.ldc = lddw; a.bias_grad = db;
+  return a;
+}
+
+void destroy_graphs(Ctx* c) {
+  for (cudaGraphExec_t* g : {&c->graph_train, &c->graph_grad, &c->graph_a1, &c->graph_a2, &c->graph_adam}) {
+    if (*g) cudaGraphExecDestroy(*g);
+    *g = nullptr;
+  }
+}
+
+void build_ops(Ctx* c) {
+  destroy_graphs(c);
+  for (TcPlan* p : c->plans) tc_plan_destroy(p);
+  c->plans.clear();
+  c->ops_fwd_enc.clear(); c->ops_latent_fwd.clear(); c->ops_fwd_dec.clear(); c->ops_loss.clear();
+  c->ops_bwd_dec.clear(); c->ops_latent_bwd.clear(); c->ops_bwd_enc.clear();
+  const int M = c->cfg.n_modalities;
+  c->ops_enc_mod.assign(M, {}); c->ops_dec_mod.assign(M, {});
+  const int B = c->cfg.batch_size, nz = c->cfg.n_z;
+  const int f = fwd_act(c);
+  const bool tf32 = c->cfg.precision == VAEASSOC_TF32;
+  const float inv_bg = 1.0f / (float)global_batch(c);
+  float* P = c->p;   // biases are always read from the fp32 master
+  bool round_z = false, round_dheads = false;
+
+  for (int m = 0; m < M; ++m) {
+    Mod& d = c->mods[m];
+    // argument sets of every dense contraction of this modality
+    GemmArgs f_e1 = gemm_fwd(B, d.r1, d.ni, d.xs, d.nip, nullptr, d.r1p, P + d.b1, d.h1, d.r1p, f);
+    GemmArgs f_e2 = gemm_fwd(B, d.r2, d.r1, d.h1, d.r1p, nullptr, d.r2p, P + d.b2, d.h2, d.r2p, f);
+    GemmArgs f_hd = gemm_fwd(B, d.nh, d.r2, d.h2, d.r2p, nullptr, d.nhp, P + d.bh, d.hd, d.nh, ACT_NONE);
+    GemmArgs f_d1 = gemm_fwd(B, d.r1, nz, d.z, nz, nullptr, d.r1p, P + d.c1, d.g1, d.r1p, f);
+    GemmArgs f_d2 = gemm_fwd(B, d.r2, d.r1, d.g1, d.r1p, nullptr, d.r2p, P + d.c2, d.g2, d.r2p, f);
+    GemmArgs f_o = gemm_fwd(B, d.ni, d.r2, d.g2, d.r2p, nullptr, d.nip, P + d.co, d.xh, d.nip, d.cfg.binary ? ACT_SIGMOID : ACT_NONE);
+    GemmArgs w_o = gemm_wgrad(B, d.r2, d.ni, d.g2, d.r2p, d.da, d.nip, c->g + d.Vo, d.nip, c->g + d.co);
+    GemmArgs d_o = gemm_dgrad(B, d.r2, d.ni, d.da, d.nip, nullptr, d.nip, d.dg2, d.r2p, d.g2, d.r2p, f);
+    GemmArgs w_d2 = gemm_wgrad(B, d.r1, d.r2, d.g1, d.r1p, d.dg2, d.r2p, c->g + d.V2, d.r2p, c->g + d.c2);
+    GemmArgs d_d2 = gemm_dgrad(B, d.r1, d.r2, d.dg2, d.r2p, nullptr, d.r2p, d.dg1, d.r1p, d.g1, d.r1p, f);
+    GemmArgs w_d1 = gemm_wgrad(B, nz, d.r1, d.z, nz, d.dg1, d.r1p, c->g + d.V1, d.r1p, c->g + d.c1);
+    GemmArgs d_d1 = gemm_dgrad(B, nz, d.r1, d.dg1, d.r1p, nullptr, d.r1p, d.dz, nz, nullptr, 0, ACT_NONE);
+    GemmArgs w_hd = gemm_wgrad(B, d.r2, d.nh, d.h2, d.r2p, d.dhd, d.nh, c->g + d.Wh, d.nhp, c->g + d.bh);
+    GemmArgs d_hd = gemm_dgrad(B, d.r2, d.nh, d.dhd, d.nh, nullptr, d.nhp, d.dh2, d.r2p, d.h2, d.r2p, f);
+    GemmArgs w_e2 = gemm_wgrad(B, d.r1, d.r2, d.h1, d.r1p, d.dh2, d.r2p, c->g + d.W2, d.r2p, c->g + d.b2);
+    GemmArgs d_e2 = gemm_dgrad(B, d.r1, d.r2, d.dh2, d.r2p, nullptr, d.r2p, d.dh1, d.r1p, d.h1, d.r1p, f);
+    GemmArgs w_e1 = gemm_wgrad(B, d.ni, d.r1, d.xs, d.nip, d.dh1, d.r1p, c->g + d.W1, d.r1p, c->g + d.b1);
+    // an output is rounded to tf32 by its producer iff one of its consumers runs on the tensor cores
+    auto tc = [&](int kind, GemmArgs a, int64_t w_off) {
+      if (w_off >= 0) a.B = c->p_tf32 + w_off;
+      return tf32 && tc_supported(kind, a);
+    };
+    const bool r_h1 = tc(KIND_NN, f_e2, d.W2) || tc(KIND_TN, w_e2, -1);
+    const bool r_h2 = tc(KIND_NN, f_hd, d.Wh) || tc(KIND_TN, w_hd, -1);
+    const bool r_g1 = tc(KIND_NN, f_d2, d.V2) || tc(KIND_TN, w_d2, -1);
+    const bool r_g2 = tc(KIND_NN, f_o, d.Vo) || tc(KIND_TN, w_o, -1);
+    const bool r_dg2 = tc(KIND_TN, w_d2, -1) || tc(KIND_NT, d_d2, d.V2);
+    const bool r_dg1 = tc(KIND_TN, w_d1, -1) || tc(KIND_NT, d_d1, d.V1);
+    const bool r_dh2 = tc(KIND_TN, w_e2, -1) || tc(KIND_NT, d_e2, d.W2);
+    const bool r_dh1 = tc(KIND_TN, w_e1, -1);
+    round_z = round_z || tc(KIND_NN, f_d1, d.V1) || tc(KIND_TN, w_d1, -1);
+    round_dheads = round_dheads || tc(KIND_TN, w_hd, -1) || tc(KIND_NT, d_hd, d.Wh);
+
+    auto& enc = c->ops_enc_mod[m];
+    enc.push_back(make_gemm(c, "fwd_enc1", m, KIND_NN, f_e1, d.W1, r_h1));
+    enc.push_back(make_gemm(c, "fwd_enc2", m, KIND_NN, f_e2, d.W2, r_h2));
+    enc.push_back(make_gemm(c, "fwd_heads", m, KIND_NN, f_hd, d.Wh, false));
+    auto& dec = c->ops_dec_mod[m];
+    dec.push_back(make_gemm(c, "fwd_dec1", m, KIND_NN, f_d1, d.V1, r_g1));
+    dec.push_back(make_gemm(c, "fwd_dec2", m, KIND_NN, f_d2, d.V2, r_g2));
+    dec.push_back(make_gemm(c, "fwd_out", m, KIND_NN, f_o, d.Vo, false));
+    for (auto& op : enc) c->ops_fwd_enc.push_back(op);
+    for (auto& op : dec) c->ops_fwd_dec.push_back(op);
+
+    auto& bd = c->ops_bwd_dec;
+    bd.push_back(make_gemm(c, "wgrad_out", m, KIND_TN, w_o, -1, false));
+    bd.push_back(make_gemm(c, "dgrad_out", m, KIND_NT, d_o, d.Vo, r_dg2));
+    bd.push_back(make_gemm(c, "wgrad_dec2", m, KIND_TN, w_d2, -1, false));
+    bd.push_back(make_gemm(c, "dgrad_dec2", m, KIND_NT, d_d2, d.V2, r_dg1));
+    bd.push_back(make_gemm(c, "wgrad_dec1", m, KIND_TN, w_d1, -1, false));
+    bd.push_back(make_gemm(c, "dgrad_dec1", m, KIND_NT, d_d1, d.V1, false));
+    auto& be = c->ops_bwd_enc;
+    be.push_back(make_gemm(c, "wgrad_heads", m, KIND_TN, w_hd, -1, false));
+    be.push_back(make_gemm(c, "dgrad_heads", m, KIND_NT, d_hd, d.Wh, r_dh2));
+    be.push_back(make_gemm(c, "wgrad_enc2", m, KIND_TN, w_e2, -1, false));
+    be.push_back(make_gemm(c, "dgrad_enc2", m, KIND_NT, d_e2, d.W2, r_dh1));
+    be.push_back(make_gemm(c, "wgrad_enc1", m, KIND_TN, w_e1, -1, false));
+
+    Op op; op.name = "recon_loss." + std::to_string(m);
+    ReconArgs a;
+    a.batch = B; a.n_input = d.ni; a.binary = d.cfg.binary; a.slot = 2 * m;
+    a.scale = d.cfg.binary ? d.cfg.weight * inv_bg : d.cfg.weight;
+    a.x = d.xs; a.ldx = d.nip; a.xhat = d.xh; a.ldxh = d.nip; a.da = d.da; a.ldda = d.nip;
+    a.row_loss = d.rec_loss; a.partials = d.partials;
+    a.round_tf32 = (tc(KIND_TN, w_o, -1) || tc(KIND_NT, d_o, d.Vo)) ? 1 : 0;
+    d.recon_blocks = (int)std::min<int64_t>(std::max<int64_t>((B + 7) / 8, 1), kMaxPartialBlocks);
+    op.bytes = 4.0 * 3 * B * d.ni;
+    op.run = [a](cudaStream_t s) { launch_recon_loss(a, s); };
+    c->ops_loss.push_back(op);
+  }
+  {
+    Op op; op.name = "latent_fwd";
+    LatentArgs a;
+    a.n_mod = M; a.batch = B; a.n_z = nz; a.inv_global_batch = inv_bg; a.lambda = c->cfg.assoc_lambda;
+    for (int m = 0; m < M; ++m) {
+      Mod& d = c->mods[m];
+      a.weight[m] = d.cfg.weight; a.heads[m] = d.hd; a.z[m] = d.z; a.gstat[m] = d.gstat; a.latent_loss[m] = d.lat_loss;
+    }
+    a.eps = c->eps; a.partials = c->lat_partials; a.with_grad = 1; a.round_z = round_z ? 1 : 0;
+    c->lat_blocks = (int)std::min<int64_t>(std::max<int64_t>((B + 255) / 256, 1), kMaxPartialBlocks);
+    c->round_z = round_z;
+    op.bytes = 4.0 * B * nz * (1 + M * 5);
+    op.run = [a](cudaStream_t s) { launch_latent_fwd(a, s); };
+    c->ops_latent_fwd.push_back(op);
+  }
+  {
+    Op op; op.name = "latent_bwd";
+    LatentBwdArgs a;
+    a.n_mod = M; a.batch = B; a.n_z = nz; a.eps = c->eps; a.round_out = round_dheads ? 1 : 0;
+    for (int m = 0; m < M; ++m) {
+      Mod& d = c->mods[m];
+      a.heads[m] = d.hd; a.gstat[m] = d.gstat; a.dz[m] = d.dz; a.dheads[m] = d.dhd;
+    }
+    op.bytes = 4.0 * B * nz * (1 + M * 6);
+    op.run = [a](cudaStream_t s) { launch_latent_bwd(a, s); };
+    c->ops_latent_bwd.push_back(op);
+  }
+}
+
+void run_ops(Ctx* c, std::vector<Op>& ops, cudaStream_t s) {
+  for (Op& op : ops) {
+    op.run(s);
+    c->launches += op.launches;
+  }
+}
+
+FinalizeArgs finalize_args(Ctx* c, int advance) {
+  FinalizeArgs a;
+  a.n_mod = c->cfg.n_modalities;
+  for (int m = 0; m < a.n_mod; ++m) {
+    a.binary[m] = c->mods[m].cfg.binary; a.weight[m] = c->mods[m].cfg.weight;
+    a.partials_recon[m] = c->mods[m].partials; a.blocks_recon[m] = c->mods[m].recon_blocks;
+  }
+  a.inv_global_batch = 1.0f / (float)global_batch(c); a.lambda = c->cfg.assoc_lambda;
+  a.partials_latent = c->lat_partials; a.blocks_latent = c->lat_blocks;
+  a.scalars = c->scalars; a.cost_slot = c->g + c->n_flat; a.step_dev = c->step_dev; a.advance = advance;
+  return a;
+}
+
+AdamArgs adam_args(Ctx* c) {
+  AdamArgs a;
+  a.p = c->p; a.g = c->g; a.m = c->m; a.v = c->v;
+  a.p_tf32 = c->cfg.precision == VAEASSOC_TF32 ? c->p_tf32 : nullptr;
+  a.n = c->n_flat; a.lr = c->cfg.learning_rate; a.beta1 = c->cfg.beta1; a.beta2 = c->cfg.beta2; a.eps = c->cfg.adam_epsilon;
+  a.step_dev = c->step_dev; a.cost_slot = c->g + c->n_flat; a.cost_hist = c->cost_hist; a.hist_cap = c->hist_cap;
+  a.last_cost = c->last_cost;
+  return a;
+}
+
+// segment A1: zero grads, forward, losses, decoder backward   (gradient bucket 0 complete at its end)
+void enqueue_a1(Ctx* c, cudaStream_t s) {
+  CUDA_OK(cudaMemsetAsync(c->g, 0, (size_t)(c->n_flat + 32) * sizeof(float), s));
+  run_ops(c, c->ops_fwd_enc, s);
+  run_ops(c, c->ops_latent_fwd, s);
+  run_ops(c, c->ops_fwd_dec, s);
+  run_ops(c, c->ops_loss, s);
+  run_ops(c, c->ops_bwd_dec, s);
+}
+// segment A2: latent + encoder backward, cost finalize (bucket 1 + cost slot complete at its end)
+void enqueue_a2(Ctx* c, cudaStream_t s, int advance) {
+  run_ops(c, c->ops_latent_bwd, s);
+  run_ops(c, c->ops_bwd_enc, s);
+  launch_finalize(finalize_args(c, advance), s);
+  c->launches += 1;
+}
+void enqueue_adam(Ctx* c, cudaStream_t s) {
+  launch_adam(adam_args(c), s);
+  c->launches += 1;
+}
+void enqueue_forward_loss(Ctx* c, cudaStream_t s) {   // evaluate_cost: no gradients
+  run_ops(c, c->ops_fwd_enc, s);
+  {
+    // latent forward without the gradient stash
+    LatentArgs a;
+    const int M = c->cfg.n_modalities;
+    a.n_mod = M; a.batch = c->cfg.batch_size; a.n_z = c->cfg.n_z;
+    a.inv_global_batch = 1.0f / (float)global_batch(c); a.lambda = c->cfg.assoc_lambda;
+    for (int m = 0; m < M; ++m) {
+      Mod& d = c->mods[m];
+      a.weight[m] = d.cfg.weight; a.heads[m] = d.hd; a.z[m] = d.z; a.gstat[m] = d.gstat; a.latent_loss[m] = d.lat_loss;
+    }
+    a.eps = c->eps; a.partials = c->lat_partials; a.with_grad = 0; a.round_z = c->round_z ? 1 : 0;
+    launch_latent_fwd(a, s);
+    c->launches += 1;
+  }
+  run_ops(c, c->ops_fwd_dec, s);
+  run_ops(c, c->ops_loss, s);   // also writes d cost/d a (harmless; gradients are not consumed)
+  launch_finalize(finalize_args(c, 0), s);
+  launch_publish_cost(c->g + c->n_flat, c->last_cost, s);
+  c->launches += 2;
+}
+
+// capture `fn` into an executable graph; returns the number of kernel/memset nodes
+template <typename F>
+int capture(Ctx* c, cudaGraphExec_t* out, F&& fn) {
+  cudaStream_t s = c->own_stream;
+  const int64_t launches_before = c->launches;
+  CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+  try {
+    fn(s);
+  } catch (...) {
+    cudaGraph_t g = nullptr;
+    cudaStreamEndCapture(s, &g);
+    if (g) cudaGraphDestroy(g);
+    c->launches = launches_before;
+    throw;
+  }
+  cudaGraph_t g = nullptr;
+  CUDA_OK(cudaStreamEndCapture(s, &g));
+  const int n = (int)(c->launches - launches_before);
+  c->launches = launches_before;
+  cudaError_t e = cudaGraphInstantiate(out, g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess) fail("cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+  return n;
+}
+
+void ensure_graphs(Ctx* c) {
+  if (!c->cfg.use_graph || c->graph_a1) return;
+  c->graph_a1_nodes = capture(c, &c->graph_a1, [&](cudaStream_t s) { enqueue_a1(c, s); });
+  c->graph_a2_nodes = capture(c, &c->graph_a2, [&](cudaStream_t s) { enqueue_a2(c, s, 1); });
+  c->graph_adam_nodes = capture(c, &c->graph_adam, [&](cudaStream_t s) { enqueue_adam(c, s); });
+  c->graph_train_nodes = capture(c, &c->graph_train, [&](cudaStream_t s) {
+    enqueue_a1(c, s); enqueue_a2(c, s, 1); enqueue_adam(c, s);
+  });
+  c->graph_grad_nodes = capture(c, &c->graph_grad, [&](cudaStream_t s) {
+    enqueue_a1(c, s); enqueue_a2(c, s, 0);
+    launch_publish_cost(c->g + c->n_flat, c->last_cost, s); c->launches += 1;
+  });
+}
+
+void refresh_shadow(Ctx* c, cudaStream_t s) {
+  if (c->shadow_dirty && c->cfg.precision == VAEASSOC_TF32) {
+    launch_round_copy(c->p, c->p_tf32, c->n_flat, s);
+    c->launches += 1;
+  }
+  c->shadow_dirty = false;
+}
+
+void stage_inputs(Ctx* c, const float* const* x, const int64_t* ld, const float* eps, cudaStream_t s,
+                  int only_modality = -1, bool want_eps = true) {
+  StageArgs a;
+  a.n_mod = c->cfg.n_modalities; a.batch = c->cfg.batch_size;
+  for (int m = 0; m < a.n_mod; ++m) {
+    const Mod& d = c->mods[m];
+    const bool use = (only_modality < 0 || only_modality == m) && x && x[m];
+    a.src[m] = use ? x[m] : nullptr;
+    a.src_ld[m] = (ld && ld[m] > 0) ? ld[m] : d.ni;
+    a.dst[m] = d.xs; a.dst_ld[m] = d.nip; a.n_input[m] = d.ni;
+  }
+  a.round_tf32 = c->cfg.precision == VAEASSOC_TF32 ? 1 : 0;
+  a.eps_src = eps; a.eps_dst = want_eps ? c->eps : nullptr; a.n_z = c->cfg.n_z;
+  a.eps_seed = c->cfg.eps_seed; a.global_row0 = c->cfg.global_row0; a.step_dev = c->step_dev;
+  launch_stage(a, s);
+  c->launches += 1;
+}
+
+void allreduce(Ctx* c, float* buf, int64_t count, cudaStream_t s) {
+  const int r = g_nccl.AllReduce(buf, buf, (size_t)count, kNcclFloat, kNcclSum, c->comm, s);
+  if (r != 0) fail("ncclAllReduce failed: %s", g_nccl.GetErrorString(r));
+}
+
+// the train step proper (inputs already staged)
+void run_step(Ctx* c, bool with_adam) {
+  cudaStream_t s = c->stream;
+  refresh_shadow(c, s);
+  ensure_graphs(c);
+  const bool dp = c->comm != nullptr && c->world > 1;
+  if (!dp) {
+    if (c->cfg.use_graph) {
+      CUDA_OK(cudaGraphLaunch(with_adam ? c->graph_train : c->graph_grad, s));
+      c->launches += with_adam ? c->graph_train_nodes : c->graph_grad_nodes;
+    } else {
+      enqueue_a1(c, s);
+      enqueue_a2(c, s, with_adam ? 1 : 0);
+      if (with_adam) enqueue_adam(c, s);
+      else { launch_publish_cost(c->g + c->n_flat, c->last_cost, s); c->launches += 1; }
+    }
+    return;
+  }
+  // data parallel: bucket 0 (decoders) is all-reduced on the comm stream while the encoder backward runs
+  if (c->cfg.use_graph) { CUDA_OK(cudaGraphLaunch(c->graph_a1, s)); c->launches += c->graph_a1_nodes; }
+  else enqueue_a1(c, s);
+  CUDA_OK(cudaEventRecord(c->ev_bucket, s));
+  CUDA_OK(cudaStreamWaitEvent(c->comm_stream, c->ev_bucket, 0));
+  allreduce(c, c->g, c->bucket_split, c->comm_stream);
+  if (c->cfg.use_graph && with_adam) { CUDA_OK(cudaGraphLaunch(c->graph_a2, s)); c->launches += c->graph_a2_nodes; }
+  else enqueue_a2(c, s, with_adam ? 1 : 0);
+  CUDA_OK(cudaEventRecord(c->ev_bucket, s));
+  CUDA_OK(cudaStreamWaitEvent(c->comm_stream, c->ev_bucket, 0));
+  allreduce(c, c->g + c->bucket_split, c->n_flat + 32 - c->bucket_split, c->comm_stream);
+  CUDA_OK(cudaEventRecord(c->ev_comm, c->comm_stream));
+  CUDA_OK(cudaStreamWaitEvent(s, c->ev_comm, 0));
+  if (with_adam) {
+    if (c->cfg.use_graph) { CUDA_OK(cudaGraphLaunch(c->graph_adam, s)); c->launches += c->graph_adam_nodes; }
+    else enqueue_adam(c, s);
+  } else {
+    launch_publish_cost(c->g + c->n_flat, c->last_cost, s);
+    c->launches += 1;
+  }
+}
+
+void check_handle(vaeassoc_handle h) {
+  if (!h) fail("null handle");
+  CUDA_OK(cudaSetDevice(h->device));
+}
+
+void validate_config(const vaeassoc_config* cfg) {
+  if (!cfg) fail("null config");
+  if (cfg->abi_version != VAEASSOC_ABI_VERSION) fail("ABI version mismatch: caller %d, library %d", cfg->abi_version, VAEASSOC_ABI_VERSION);
+  if (cfg->n_modalities < 1 || cfg->n_modalities > VAEASSOC_MAX_MODALITIES) fail("n_modalities must be in [1,%d]", VAEASSOC_MAX_MODALITIES);
+  if (cfg->batch_size < 1) fail("batch_size must be >= 1");
+  if (cfg->n_z < 1 || cfg->n_z > 1024) fail("n_z must be in [1,1024]");
+  if (cfg->transfer_fct != VAEASSOC_RELU && cfg->transfer_fct != VAEASSOC_SOFTPLUS) fail("transfer_fct must be relu or softplus");
+  if (cfg->precision != VAEASSOC_FP32 && cfg->precision != VAEASSOC_TF32) fail("precision must be fp32 or tf32");
+  if (cfg->global_batch != 0 && cfg->global_batch < cfg->batch_size) fail("global_batch < batch_size");
+}
+
+}  // namespace
+
+// =======================================================================================================
+// C-ABI
+// =======================================================================================================
+#define API_BEGIN(h)                          \
+  try {                                       \
+    check_handle(h);                          \
+    std::lock_guard<std::mutex> lock__(h->mu);
+#define API_END(h)                            \
+    return 0;                                 \
+  } catch (const std::exception& e) {         \
+    if (h) h->err = e.what(); else g_create_error = e.what(); \
+    return 1;                                 \
+  }
+
+extern "C" {
+
+int vaeassoc_abi_version(void) { return VAEASSOC_ABI_VERSION; }
+
+const char* vaeassoc_last_error(vaeassoc_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int vaeassoc_create(const vaeassoc_config* cfg, vaeassoc_handle* out) {
+  Ctx* c = nullptr;
+  try {
+    if (!out) fail("null output handle");
+    *out = nullptr;
+    validate_config(cfg);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+      fail("no CUDA device available (%s); libvaeassoc has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev) fail("device %d out of range (have %d)", cfg->device, ndev);
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) fail("device %d is sm_%d%d; this library is built for sm_100a (B200) only", cfg->device, prop.major, prop.minor);
+    CUDA_OK(cudaSetDevice(cfg->device));
+    c = new Ctx();
+    c->cfg = *cfg;
+    c->device = cfg->device;
+    if (c->cfg.beta1 == 0.f) c->cfg.beta1 = 0.9f;
+    if (c->cfg.beta2 == 0.f) c->cfg.beta2 = 0.999f;
+    if (c->cfg.adam_epsilon == 0.f) c->cfg.adam_epsilon = 1e-8f;
+    CUDA_OK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    for (int i = 0; i < 2; ++i) {
+      CUDA_OK(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+      CUDA_OK(cudaEventCreateWithFlags(&c->ev_consumed[i], cudaEventDisableTiming));
+    }
+    CUDA_OK(cudaEventCreateWithFlags(&c->ev_bucket, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming));
+    build_layout(c);
+    alloc_buffers(c);
+    build_ops(c);
+    CUDA_OK(cudaDeviceSynchronize());
+    *out = c;
+    return 0;
+  } catch (const std::exception& e) {
+    g_create_error = e.what();
+    if (c) vaeassoc_destroy(c);
+    return 1;
+  }
+}
+
+int vaeassoc_destroy(vaeassoc_handle h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  if (h->comm) { g_nccl.CommDestroy(h->comm); h->comm = nullptr; }
+  destroy_graphs(h);
+  for (TcPlan* p : h->plans) tc_plan_destroy(p);
+  for (void* p : h->allocs) cudaFree(p);
+  for (int i = 0; i < 2; ++i) {
+    if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
+    if (h->ev_consumed[i]) cudaEventDestroy(h->ev_consumed[i]);
+  }
+  if (h->ev_bucket) cudaEventDestroy(h->ev_bucket);
+  if (h->ev_comm) cudaEventDestroy(h->ev_comm);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+  delete h;
+  return 0;
+}
+
+int vaeassoc_set_stream(vaeassoc_handle h, void* cuda_stream) {
+  API_BEGIN(h)
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  h->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+  API_END(h)
+}
+
+int vaeassoc_stream_sync(vaeassoc_handle h) {
+  API_BEGIN(h)
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  API_END(h)
+}
+
+int vaeassoc_set_precision(vaeassoc_handle h, int precision) {
+  API_BEGIN(h)
+  if (precision != VAEASSOC_FP32 && precision != VAEASSOC_TF32) fail("precision must be fp32 or tf32");
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  h->cfg.precision = precision;
+  h->shadow_dirty = true;
+  build_ops(h);
+  API_END(h)
+}
+
+int vaeassoc_set_learning_rate(vaeassoc_handle h, float lr) {
+  API_BEGIN(h)
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  h->cfg.learning_rate = lr;
+  destroy_graphs(h);
+  API_END(h)
+}
+
+int vaeassoc_num_tensors(vaeassoc_handle h) { return h ? (int)h->tensors.size() : -1; }
+
+int vaeassoc_layout_query(vaeassoc_handle h, int i, vaeassoc_tensor_info* out) {
+  API_BEGIN(h)
+  if (i < 0 || i >= (int)h->tensors.size() || !out) fail("tensor index %d out of range", i);
+  *out = h->tensors[i];
+  API_END(h)
+}
+
+int64_t vaeassoc_flat_size(vaeassoc_handle h) { return h ? h->n_flat : -1; }
+
+void* vaeassoc_flat_ptr(vaeassoc_handle h, int which) {
+  if (!h) return nullptr;
+  switch (which) {
+    case VAEASSOC_PARAMS: return h->p;
+    case VAEASSOC_GRADS: return h->g;
+    case VAEASSOC_ADAM_M: return h->m;
+    case VAEASSOC_ADAM_V: return h->v;
+    default: return nullptr;
+  }
+}
+
+int vaeassoc_tensor_set(vaeassoc_handle h, int which, int i, const float* src_host) {
+  API_BEGIN(h)
+  float* base = reinterpret_cast<float*>(vaeassoc_flat_ptr(h, which));
+  if (!base) fail("bad flat buffer id %d", which);
+  if (i < 0 || i >= (int)h->tensors.size() || !src_host) fail("tensor index %d out of range", i);
+  const vaeassoc_tensor_info& t = h->tensors[i];
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  CUDA_OK(cudaMemcpy2D(base + t.offset, (size_t)t.ld * 4, src_host, (size_t)t.cols * 4, (size_t)t.cols * 4, (size_t)t.rows,
+                       cudaMemcpyHostToDevice));
+  if (which == VAEASSOC_PARAMS) h->shadow_dirty = true;
+  API_END(h)
+}
+
+int vaeassoc_tensor_get(vaeassoc_handle h, int which, int i, float* dst_host) {
+  API_BEGIN(h)
+  float* base = reinterpret_cast<float*>(vaeassoc_flat_ptr(h, which));
+  if (!base) fail("bad flat buffer id %d", which);
+  if (i < 0 || i >= (int)h->tensors.size() || !dst_host) fail("tensor index %d out of range", i);
+  const vaeassoc_tensor_info& t = h->tensors[i];
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  CUDA_OK(cudaMemcpy2D(dst_host, (size_t)t.cols * 4, base + t.offset, (size_t)t.ld * 4, (size_t)t.cols * 4, (size_t)t.rows,
+                       cudaMemcpyDeviceToHost));
+  API_END(h)
+}
+
+int vaeassoc_step_get(vaeassoc_handle h, int64_t* step) {
+  API_BEGIN(h)
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  CUDA_OK(cudaMemcpy(step, h->step_dev, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  API_END(h)
+}
+
+int vaeassoc_step_set(vaeassoc_handle h, int64_t step) {
+  API_BEGIN(h)
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  CUDA_OK(cudaMemcpy(h->step_dev, &step, sizeof(int64_t), cudaMemcpyHostToDevice));
+  API_END(h)
+}
+
+int vaeassoc_train_step(vaeassoc_handle h, const float* const* x_dev, const int64_t* ld, const float* eps_dev) {
+  API_BEGIN(h)
+  if (!x_dev) fail("x_dev is null");
+  for (int m = 0; m < h->cfg.n_modalities; ++m) if (!x_dev[m]) fail("x_dev[%d] is null", m);
+  stage_inputs(h, x_dev, ld, eps_dev, h->stream);
+  run_step(h, true);
+  API_END(h)
+}
+
+int vaeassoc_grad_step(vaeassoc_handle h, const float* const* x_dev, const int64_t* ld, const float* eps_dev) {
+  API_BEGIN(h)
+  if (!x_dev) fail("x_dev is null");
+  for (int m = 0; m < h->cfg.n_modalities; ++m) if (!x_dev[m]) fail("x_dev[%d] is null", m);
+  stage_inputs(h, x_dev, ld, eps_dev, h->stream);
+  run_step(h, false);
+  API_END(h)
+}
+
+int vaeassoc_adam_step(vaeassoc_handle h) {
+  API_BEGIN(h)
+  // grad_step leaves t unchanged; ApplyAdam uses t+1
+  int64_t one = 0;
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  CUDA_OK(cudaMemcpy(&one, h->step_dev, sizeof one, cudaMemcpyDeviceToHost));
+  one += 1;
+  CUDA_OK(cudaMemcpy(h->step_dev, &one, sizeof one, cudaMemcpyHostToDevice));
+  enqueue_adam(h, h->stream);
+  API_END(h)
+}
+
+int vaeassoc_cost_read(vaeassoc_handle h, float* cost_host) {
+  API_BEGIN(h)
+  CUDA_OK(cudaMemcpyAsync(cost_host, h->last_cost, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  API_END(h)
+}
+
+int vaeassoc_cost_history(vaeassoc_handle h, int64_t first_step, int64_t n, float* dst_host) {
+  API_BEGIN(h)
+  if (n < 0 || n > h->hist_cap) fail("history window %lld exceeds the ring capacity %d", (long long)n, h->hist_cap);
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  for (int64_t i = 0; i < n;) {
+    const int64_t pos = (first_step + i) % h->hist_cap;
+    const int64_t run = std::min<int64_t>(n - i, h->hist_cap - pos);
+    CUDA_OK(cudaMemcpy(dst_host + i, h->cost_hist + pos, (size_t)run * 4, cudaMemcpyDeviceToHost));
+    i += run;
+  }
+  API_END(h)
+}
+
+static void upload_host(Ctx* h, const float* const* x_host, const float* eps_host, int slot, cudaStream_t s) {
+  for (int m = 0; m < h->cfg.n_modalities; ++m) {
+    if (!x_host[m]) fail("x_host[%d] is null", m);
+    const Mod& d = h->mods[m];
+    CUDA_OK(cudaMemcpyAsync(d.xin[slot], x_host[m], (size_t)h->cfg.batch_size * d.ni * 4, cudaMemcpyHostToDevice, s));
+  }
+  if (eps_host)
+    CUDA_OK(cudaMemcpyAsync(h->eps_in[slot], eps_host, (size_t)h->cfg.batch_size * h->cfg.n_z * 4, cudaMemcpyHostToDevice, s));
+}
+
+int vaeassoc_partial_fit_host(vaeassoc_handle h, const float* const* x_host, const float* eps_host, float* cost_host) {
+  API_BEGIN(h)
+  if (!x_host) fail("x_host is null");
+  upload_host(h, x_host, eps_host, 0, h->stream);
+  const float* xd[VAEASSOC_MAX_MODALITIES];
+  for (int m = 0; m < h->cfg.n_modalities; ++m) xd[m] = h->mods[m].xin[0];
+  stage_inputs(h, xd, nullptr, eps_host ? h->eps_in[0] : nullptr, h->stream);
+  run_step(h, true);
+  if (cost_host) CUDA_OK(cudaMemcpyAsync(cost_host, h->last_cost, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  API_END(h)
+}
+
+int vaeassoc_submit_host(vaeassoc_handle h, const float* const* x_host, const float* eps_host) {
+  API_BEGIN(h)
+  if (!x_host) fail("x_host is null");
+  const int slot = (int)(h->submit_count & 1);
+  // the upload of batch k+1 overlaps the compute of batch k; slot reuse waits for the stage kernel of batch k-1
+  if (h->submit_count >= 2) CUDA_OK(cudaStreamWaitEvent(h->copy_stream, h->ev_consumed[slot], 0));
+  upload_host(h, x_host, eps_host, slot, h->copy_stream);
+  CUDA_OK(cudaEventRecord(h->ev_copied[slot], h->copy_stream));
+  CUDA_OK(cudaStreamWaitEvent(h->stream, h->ev_copied[slot], 0));
+  const float* xd[VAEASSOC_MAX_MODALITIES];
+  for (int m = 0; m < h->cfg.n_modalities; ++m) xd[m] = h->mods[m].xin[slot];
+  stage_inputs(h, xd, nullptr, eps_host ? h->eps_in[slot] : nullptr, h->stream);
+  CUDA_OK(cudaEventRecord(h->ev_consumed[slot], h->stream));
+  run_step(h, true);
+  h->submit_count += 1;
+  API_END(h)
+}
+
+int vaeassoc_eval_cost(vaeassoc_handle h, const float* const* x_dev, const int64_t* ld, const float* eps_dev,
+                       float* cost_host) {
+  API_BEGIN(h)
+  if (!x_dev) fail("x_dev is null");
+  for (int m = 0; m < h->cfg.n_modalities; ++m) if (!x_dev[m]) fail("x_dev[%d] is null", m);
+  if (h->comm && h->world > 1) fail("evaluate_cost is a single-process call; use it on a handle without a communicator");
+  stage_inputs(h, x_dev, ld, eps_dev, h->stream);
+  refresh_shadow(h, h->stream);
+  enqueue_forward_loss(h, h->stream);
+  if (cost_host) CUDA_OK(cudaMemcpyAsync(cost_host, h->last_cost, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  API_END(h)
+}
+
+int vaeassoc_encode(vaeassoc_handle h, int modality, const float* x_dev, int64_t ld, float* mu_dev, float* logvar_dev) {
+  API_BEGIN(h)
+  if (modality < 0 || modality >= h->cfg.n_modalities) fail("modality %d out of range", modality);
+  if (!x_dev) fail("x_dev is null");
+  const float* xs[VAEASSOC_MAX_MODALITIES] = {nullptr, nullptr, nullptr, nullptr};
+  int64_t lds[VAEASSOC_MAX_MODALITIES] = {0, 0, 0, 0};
+  xs[modality] = x_dev; lds[modality] = ld;
+  stage_inputs(h, xs, lds, nullptr, h->stream, modality, /*want_eps=*/false);
+  refresh_shadow(h, h->stream);
+  run_ops(h, h->ops_enc_mod[modality], h->stream);
+  const Mod& d = h->mods[modality];
+  const size_t w = (size_t)d.nz * 4;
+  if (mu_dev) CUDA_OK(cudaMemcpy2DAsync(mu_dev, w, d.hd, (size_t)d.nh * 4, w, (size_t)h->cfg.batch_size, cudaMemcpyDeviceToDevice, h->stream));
+  if (logvar_dev) CUDA_OK(cudaMemcpy2DAsync(logvar_dev, w, d.hd + d.nz, (size_t)d.nh * 4, w, (size_t)h->cfg.batch_size, cudaMemcpyDeviceToDevice, h->stream));
+  API_END(h)
+}
+
+int vaeassoc_decode(vaeassoc_handle h, int modality, const float* z_dev, float* xhat_dev) {
+  API_BEGIN(h)
+  if (modality < 0 || modality >= h->cfg.n_modalities) fail("modality %d out of range", modality);
+  if (!z_dev || !xhat_dev) fail("null z_dev / xhat_dev");
+  const Mod& d = h->mods[modality];
+  const int64_t B = h->cfg.batch_size;
+  CUDA_OK(cudaMemcpyAsync(d.z, z_dev, (size_t)B * d.nz * 4, cudaMemcpyDeviceToDevice, h->stream));
+  refresh_shadow(h, h->stream);
+  run_ops(h, h->ops_dec_mod[modality], h->stream);
+  CUDA_OK(cudaMemcpy2DAsync(xhat_dev, (size_t)d.ni * 4, d.xh, (size_t)d.nip * 4, (size_t)d.ni * 4, (size_t)B, cudaMemcpyDeviceToDevice, h->stream));
+  API_END(h)
+}
+
+int vaeassoc_reconstruct(vaeassoc_handle h, int modality, const float* x_dev, int64_t ld, const float* eps_dev,
+                         float* xhat_dev) {
+  API_BEGIN(h)
+  if (modality < 0 || modality >= h->cfg.n_modalities) fail("modality %d out of range", modality);
+  if (!x_dev || !xhat_dev) fail("null x_dev / xhat_dev");
+  const float* xs[VAEASSOC_MAX_MODALITIES] = {nullptr, nullptr, nullptr, nullptr};
+  int64_t lds[VAEASSOC_MAX_MODALITIES] = {0, 0, 0, 0};
+  xs[modality] = x_dev; lds[modality] = ld;
+  stage_inputs(h, xs, lds, eps_dev, h->stream, modality, /*want_eps=*/true);
+  refresh_shadow(h, h->stream);
+  run_ops(h, h->ops_enc_mod[modality], h->stream);
+  const Mod& d = h->mods[modality];
+  LatentArgs a;
+  a.n_mod = 1; a.batch = h->cfg.batch_size; a.n_z = h->cfg.n_z; a.inv_global_batch = 0.f; a.lambda = 0.f;
+  a.weight[0] = 0.f; a.heads[0] = d.hd; a.z[0] = d.z; a.gstat[0] = d.gstat; a.latent_loss[0] = nullptr;
+  a.eps = h->eps; a.partials = h->lat_partials; a.with_grad = 0; a.round_z = h->round_z ? 1 : 0;
+  launch_latent_fwd(a, h->stream);
+  h->launches += 1;
+  run_ops(h, h->ops_dec_mod[modality], h->stream);
+  CUDA_OK(cudaMemcpy2DAsync(xhat_dev, (size_t)d.ni * 4, d.xh, (size_t)d.nip * 4, (size_t)d.ni * 4, (size_t)h->cfg.batch_size,
+                            cudaMemcpyDeviceToDevice, h->stream));
+  API_END(h)
+}
+
+int vaeassoc_probe_get(vaeassoc_handle h, int kind, int modality, float* dst_host, int64_t capacity, int64_t* n_written) {
+  API_BEGIN(h)
+  if (!dst_host) fail("dst_host is null");
+  const bool needs_mod = !(kind == VAEASSOC_PROBE_ASSOC_COST || kind == VAEASSOC_PROBE_EPS);
+  if (needs_mod && (modality < 0 || modality >= h->cfg.n_modalities)) fail("modality %d out of range", modality);
+  const int64_t B = h->cfg.batch_size;
+  const int nz = h->cfg.n_z;
+  const Mod* d = needs_mod ? &h->mods[modality] : nullptr;
+  const float* src = nullptr;
+  int64_t rows = 1, cols = 1, ld = 1;
+  switch (kind) {
+    case VAEASSOC_PROBE_Z_MEAN: src = d->hd; rows = B; cols = nz; ld = d->nh; break;
+    case VAEASSOC_PROBE_Z_LOG_SIGMA_SQ: src = d->hd + nz; rows = B; cols = nz; ld = d->nh; break;
+    case VAEASSOC_PROBE_Z: src = d->z; rows = B; cols = nz; ld = nz; break;
+    case VAEASSOC_PROBE_X_RECONSTR_MEAN: src = d->xh; rows = B; cols = d->ni; ld = d->nip; break;
+    case VAEASSOC_PROBE_RECONSTR_LOSS:
+      if (d->cfg.binary) { src = d->rec_loss; rows = 1; cols = B; ld = B; }
+      else { src = h->scalars + 4 + modality; }
+      break;
+    case VAEASSOC_PROBE_LATENT_LOSS: src = d->lat_loss; rows = 1; cols = B; ld = B; break;
+    case VAEASSOC_PROBE_VAE_COST: src = h->scalars + modality; break;
+    case VAEASSOC_PROBE_ASSOC_COST: src = h->scalars + 8; break;
+    case VAEASSOC_PROBE_D_Z_MEAN: src = d->dhd; rows = B; cols = nz; ld = d->nh; break;
+    case VAEASSOC_PROBE_D_Z_LOG_SIGMA_SQ: src = d->dhd + nz; rows = B; cols = nz; ld = d->nh; break;
+    case VAEASSOC_PROBE_EPS: src = h->eps; rows = B; cols = nz; ld = nz; break;
+    default: fail("unknown probe kind %d", kind);
+  }
+  if (rows * cols > capacity) fail("probe needs %lld floats, capacity %lld", (long long)(rows * cols), (long long)capacity);
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  CUDA_OK(cudaMemcpy2D(dst_host, (size_t)cols * 4, src, (size_t)ld * 4, (size_t)cols * 4, (size_t)rows, cudaMemcpyDeviceToHost));
+  if (n_written) *n_written = rows * cols;
+  API_END(h)
+}
+
+int vaeassoc_synth_batch(vaeassoc_handle h, uint32_t data_seed, uint32_t proj_seed, int64_t row0, int64_t n_rows,
+                         float* const* x_dev) {
+  API_BEGIN(h)
+  if (!x_dev) fail("x_dev is null");
+  for (int m = 0; m < h->cfg.n_modalities; ++m) {
+    Mod& d = h->mods[m];
+    if (!x_dev[m]) fail("x_dev[%d] is null", m);
+    if (d.proj_seed_built != proj_seed) {
+      launch_synth_projection(d.P, d.inv_std, m, d.ni, proj_seed, h->stream);
+      h->launches += 2;
+      d.proj_seed_built = proj_seed;
+    }
+    launch_synth_modality(x_dev[m], d.ni, d.P, d.inv_std, m, d.ni, d.cfg.binary, data_seed, row0, n_rows, h->stream);
+    h->launches += 1;
+  }
+  API_END(h)
+}
+
+int vaeassoc_philox_normal(vaeassoc_handle h, uint32_t seed, uint32_t tag, int64_t row0, int64_t n_rows, int32_t n_cols,
+                           uint32_t step, float* dst_dev) {
+  API_BEGIN(h)
+  if (!dst_dev || n_rows < 0 || n_cols < 1) fail("bad arguments");
+  launch_philox_normal(dst_dev, n_rows, n_cols, seed, tag, row0, step, h->stream);
+  h->launches += 1;
+  API_END(h)
+}
+
+int vaeassoc_comm_unique_id(const char* nccl_lib_path, void* id128) {
+  try {
+    std::lock_guard<std::mutex> lock(g_nccl_mutex);
+    g_nccl.load(nccl_lib_path);
+    NcclId id;
+    const int r = g_nccl.GetUniqueId(&id);
+    if (r != 0) fail("ncclGetUniqueId failed: %s", g_nccl.GetErrorString(r));
+    memcpy(id128, &id, sizeof id);
+    return 0;
+  } catch (const std::exception& e) {
+    g_create_error = e.what();
+    return 1;
+  }
+}
+
+int vaeassoc_comm_init(vaeassoc_handle h, const char* nccl_lib_path, const void* id128, int rank, int world) {
+  API_BEGIN(h)
+  if (world < 1 || rank < 0 || rank >= world) fail("bad rank %d / world %d", rank, world);
+  if (h->comm) fail("communicator already initialised");
+  {
+    std::lock_guard<std::mutex> lock(g_nccl_mutex);
+    g_nccl.load(nccl_lib_path);
+  }
+  NcclId id;
+  memcpy(&id, id128, sizeof id);
+  void* comm = nullptr;
+  const int r = g_nccl.CommInitRank(&comm, world, id, rank);
+  if (r != 0) fail("ncclCommInitRank failed: %s", g_nccl.GetErrorString(r));
+  h->comm = comm; h->rank = rank; h->world = world;
+  API_END(h)
+}
+
+int vaeassoc_comm_destroy(vaeassoc_handle h) {
+  API_BEGIN(h)
+  if (h->comm) {
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->comm_stream));
+    g_nccl.CommDestroy(h->comm);
+    h->comm = nullptr; h->world = 1; h->rank = 0;
+  }
+  API_END(h)
+}
+
+int64_t vaeassoc_launch_count(vaeassoc_handle h) { return h ? h->launches : -1; }
+
+int vaeassoc_profile_step(vaeassoc_handle h, const float* const* x_dev, const int64_t* ld, const float* eps_dev,
+                          char* names, float* ms, double* flops, double* bytes, int capacity) {
+  if (!h) return -1;
+  try {
+    check_handle(h);
+    std::lock_guard<std::mutex> lock(h->mu);
+    if (!x_dev) fail("x_dev is null");
+    cudaStream_t s = h->stream;
+    stage_inputs(h, x_dev, ld, eps_dev, s);
+    refresh_shadow(h, s);
+    std::vector<Op> all;
+    {
+      Op z; z.name = "zero_grads"; z.bytes = 4.0 * (h->n_flat + 32);
+      Ctx* c = h;
+      z.run = [c](cudaStream_t st) { CUDA_OK(cudaMemsetAsync(c->g, 0, (size_t)(c->n_flat + 32) * sizeof(float), st)); };
+      all.push_back(z);
+    }
+    for (auto* v : {&h->ops_fwd_enc, &h->ops_latent_fwd, &h->ops_fwd_dec, &h->ops_loss, &h->ops_bwd_dec, &h->ops_latent_bwd, &h->ops_bwd_enc})
+      for (auto& op : *v) all.push_back(op);
+    {
+      Ctx* c = h;
+      Op f; f.name = "finalize"; f.run = [c](cudaStream_t st) { launch_finalize(finalize_args(c, 1), st); };
+      all.push_back(f);
+      Op a; a.name = "adam"; a.bytes = (c->cfg.precision == VAEASSOC_TF32 ? 32.0 : 28.0) * c->n_flat;
+      a.run = [c](cudaStream_t st) { launch_adam(adam_args(c), st); };
+      all.push_back(a);
+    }
+    const int n = (int)std::min<size_t>(all.size(), (size_t)capacity);
+    std::vector<cudaEvent_t> ev(all.size() + 1);
+    for (auto& e : ev) CUDA_OK(cudaEventCreate(&e));
+    CUDA_OK(cudaEventRecord(ev[0], s));
+    for (size_t i = 0; i < all.size(); ++i) {
+      all[i].run(s);
+      h->launches += all[i].launches;
+      CUDA_OK(cudaEventRecord(ev[i + 1], s));
+    }
+    CUDA_OK(cudaStreamSynchronize(s));
+    for (int i = 0; i < n; ++i) {
+      float t = 0.f;
+      CUDA_OK(cudaEventElapsedTime(&t, ev[i], ev[i + 1]));
+      ms[i] = t;
+      if (flops) flops[i] = all[i].flops;
+      if (bytes) bytes[i] = all[i].bytes;
+      snprintf(names + (size_t)i * 32, 32, "%s", all[i].name.c_str());
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    return n;
+  } catch (const std::exception& e) {
+    h->err = e.what();
+    return -1;
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,147 @@
+// Internal launcher declarations of libvaeassoc (not part of the C-ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vaeassoc {
+
+// ------------------------------------------------------------------------------------------------------
+// dense layers.  Three contractions cover forward / dgrad / wgrad of y = act(x W + b)  (vae_assoc.py:187-221,
+// 259-303 and their autodiff, :373-374):
+//   NN  C[M,N]  = act(A[M,K] . B[K,N] + bias[N])                     forward
+//   NT  C[M,N]  = (A[M,K] . B[N,K]^T) (*) act'(aux[M,N])             dgrad (aux = stored activation of the layer below)
+//   TN  C[M,N] += A[K,M]^T . B[K,N];  bias_grad[N] += colsum(B)      wgrad (K = batch; split-K, fp32 atomics)
+// ------------------------------------------------------------------------------------------------------
+struct GemmArgs {
+  int M = 0, N = 0, K = 0;
+  const float* A = nullptr; int64_t lda = 0;
+  const float* B = nullptr; int64_t ldb = 0;
+  float* C = nullptr;       int64_t ldc = 0;
+  const float* bias = nullptr;
+  float* bias_grad = nullptr;
+  const float* aux = nullptr; int64_t ldaux = 0;
+  int act = 0;          // Act code: forward activation, or which act' to apply in dgrad
+  int round_out = 0;    // round stored outputs to tf32 (they feed a tcgen05 kind::tf32 GEMM)
+  int splitk = 1;       // TN only
+};
+
+void launch_gemm_nn_simt(const GemmArgs& a, cudaStream_t s);
+void launch_gemm_nt_simt(const GemmArgs& a, cudaStream_t s);
+void launch_gemm_tn_simt(const GemmArgs& a, cudaStream_t s);
+
+// tcgen05 / TMA path (gemm_tc.cu).  Returns false if the shape cannot be served (caller falls back to SIMT
+// *kernels of this library*, never to a CPU or a vendor library).
+struct TcPlan;   // opaque: tensor maps + grid for one GEMM call site, built once at handle creation
+TcPlan* tc_plan_create(int kind /*0 NN,1 NT,2 TN*/, const GemmArgs& a, char* err, int errlen);
+void tc_plan_destroy(TcPlan* p);
+void launch_gemm_tc(const TcPlan* p, cudaStream_t s);
+bool tc_supported(int kind, const GemmArgs& a);
+
+// ------------------------------------------------------------------------------------------------------
+// input staging + noise
+// ------------------------------------------------------------------------------------------------------
+struct StageArgs {
+  int n_mod = 0;
+  int batch = 0;
+  const float* src[4] = {nullptr, nullptr, nullptr, nullptr};
+  int64_t src_ld[4] = {0, 0, 0, 0};
+  float* dst[4] = {nullptr, nullptr, nullptr, nullptr};
+  int64_t dst_ld[4] = {0, 0, 0, 0};
+  int n_input[4] = {0, 0, 0, 0};
+  int round_tf32 = 0;
+  // eps: copy `eps_src` (dense [B, n_z]) or generate with Philox when null
+  const float* eps_src = nullptr;
+  float* eps_dst = nullptr;
+  int n_z = 0;
+  uint32_t eps_seed = 0;
+  int64_t global_row0 = 0;
+  const int64_t* step_dev = nullptr;   // Adam step counter t (eps of the step about to run uses t)
+};
+void launch_stage(const StageArgs& a, cudaStream_t s);
+void launch_philox_normal(float* dst, int64_t n_rows, int n_cols, uint32_t seed, uint32_t tag, int64_t row0,
+                          uint32_t step, cudaStream_t s);
+
+// ------------------------------------------------------------------------------------------------------
+// fused reparameterisation + losses (vae_assoc.py:102-103, 319-371)
+// ------------------------------------------------------------------------------------------------------
+constexpr int kMaxPartialBlocks = 1184;   // 8 x 148
+constexpr int kCostSlots = 16;            // per-block partial sums: [2m] recon, [2m+1] latent, [8] assoc
+
+struct LatentArgs {
+  int n_mod = 0, batch = 0, n_z = 0;
+  float inv_global_batch = 0.f;     // 1 / B_global  (mean terms)
+  float lambda = 0.f;               // assoc_lambda
+  float weight[4] = {0, 0, 0, 0};
+  const float* heads[4] = {nullptr, nullptr, nullptr, nullptr};   // [B, 2 n_z] = (mu | log sigma^2), ld = 2 n_z
+  const float* eps = nullptr;                                     // [B, n_z]
+  float* z[4] = {nullptr, nullptr, nullptr, nullptr};             // [B, n_z]
+  float* gstat[4] = {nullptr, nullptr, nullptr, nullptr};         // [B, 2 n_z] prior-KL + assoc-KL gradient part
+  float* latent_loss[4] = {nullptr, nullptr, nullptr, nullptr};   // [B]
+  float* partials = nullptr;                                      // [kMaxPartialBlocks][kCostSlots]
+  int with_grad = 1;
+  int round_z = 0;                  // z feeds a tcgen05 GEMM (n_z large enough): round to tf32
+};
+int launch_latent_fwd(const LatentArgs& a, cudaStream_t s);       // returns number of blocks (partials rows)
+
+struct LatentBwdArgs {
+  int n_mod = 0, batch = 0, n_z = 0;
+  const float* heads[4] = {nullptr, nullptr, nullptr, nullptr};
+  const float* gstat[4] = {nullptr, nullptr, nullptr, nullptr};
+  const float* dz[4] = {nullptr, nullptr, nullptr, nullptr};      // [B, n_z] gradient arriving from the decoder
+  const float* eps = nullptr;
+  float* dheads[4] = {nullptr, nullptr, nullptr, nullptr};        // [B, 2 n_z] = (d mu | d log sigma^2)
+  int round_out = 0;
+};
+void launch_latent_bwd(const LatentBwdArgs& a, cudaStream_t s);
+
+struct ReconArgs {
+  int batch = 0, n_input = 0, binary = 0, slot = 0;
+  float scale = 0.f;                 // binary: w / B_global ; Gaussian: w
+  const float* x = nullptr; int64_t ldx = 0;
+  const float* xhat = nullptr; int64_t ldxh = 0;   // sigmoid already applied by the GEMM epilogue when binary
+  float* da = nullptr; int64_t ldda = 0;           // d cost / d pre-activation (null: loss only)
+  float* row_loss = nullptr;                       // [B] (binary) ; null otherwise
+  float* partials = nullptr;                       // this kernel's rows of [blocks][kCostSlots]
+  int round_tf32 = 0;
+};
+int launch_recon_loss(const ReconArgs& a, cudaStream_t s);        // returns number of blocks
+
+struct FinalizeArgs {
+  int n_mod = 0;
+  int binary[4] = {0, 0, 0, 0};
+  float weight[4] = {0, 0, 0, 0};
+  float inv_global_batch = 0.f, lambda = 0.f;
+  const float* partials_latent = nullptr; int blocks_latent = 0;
+  const float* partials_recon[4] = {nullptr, nullptr, nullptr, nullptr}; int blocks_recon[4] = {0, 0, 0, 0};
+  float* scalars = nullptr;         // [16]: [m] vae_cost_m, [4+m] recon sum, [8] assoc sum, [9] cost (local)
+  float* cost_slot = nullptr;       // spare slot of the flat gradient buffer (all-reduced with the grads)
+  int64_t* step_dev = nullptr;      // incremented when `advance`
+  int advance = 0;
+};
+void launch_finalize(const FinalizeArgs& a, cudaStream_t s);
+
+// ------------------------------------------------------------------------------------------------------
+// Adam (TensorFlow ApplyAdam formulation, vae_assoc.py:373-374) over the flat buffers
+// ------------------------------------------------------------------------------------------------------
+struct AdamArgs {
+  float* p = nullptr; const float* g = nullptr; float* m = nullptr; float* v = nullptr;
+  float* p_tf32 = nullptr;          // rounded shadow copy read by the tcgen05 GEMMs (null in fp32 mode)
+  int64_t n = 0;                    // floats (multiple of 4)
+  float lr = 0.f, beta1 = 0.f, beta2 = 0.f, eps = 0.f;
+  const int64_t* step_dev = nullptr;
+  const float* cost_slot = nullptr; float* cost_hist = nullptr; int hist_cap = 0;   // publish cost of step t
+  float* last_cost = nullptr;
+};
+void launch_adam(const AdamArgs& a, cudaStream_t s);
+void launch_round_copy(const float* src, float* dst, int64_t n, cudaStream_t s);   // dst = round_tf32(src)
+void launch_publish_cost(const float* cost_slot, float* last_cost, cudaStream_t s);
+
+// ------------------------------------------------------------------------------------------------------
+// synthetic paired batches (replaces dataset.py / utils.py)
+// ------------------------------------------------------------------------------------------------------
+void launch_synth_projection(float* P, float* inv_std, int modality, int n_input, uint32_t proj_seed,
+                             cudaStream_t s);
+void launch_synth_modality(float* x, int64_t ldx, const float* P, const float* inv_std, int modality, int n_input,
+                           int binary, uint32_t data_seed, int64_t row0, int64_t n_rows, cudaStream_t s);
+
+}  // namespace vaeassoc

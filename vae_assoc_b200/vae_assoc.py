@@ -1,0 +1,564 @@
+"""Host-side mirror of the reference's model surface (/root/reference/vae_assoc.py) over libvaeassoc.
+
+Same names, argument meaning and error behaviour as the reference class (`AssocVariationalAutoEncoder`,
+vae_assoc.py:20-463) and trainer (`train`, vae_assoc.py:498-583), so vae_assoc_ujichar_img_jnt.py and
+vae_assoc_model_viewer.py stay valid callers.  Every arithmetic op goes through the C-ABI
+(include/vaeassoc.h) into hand-written sm_100a kernels; PyTorch is only the device-memory / stream /
+torch.distributed shell.  There is no CPU fallback: construction raises without the built library or a B200.
+"""
+import ctypes as C
+import datetime
+import os
+import time
+
+import numpy as np
+
+from . import _lib as L
+
+
+def _fct_name(transfer_fct):
+    """The reference passes tf.nn.relu / tf.nn.softplus callables (vae_assoc.py:26,502); accept those (by
+    __name__), the shim's functions, or plain strings."""
+    name = transfer_fct if isinstance(transfer_fct, str) else getattr(transfer_fct, "__name__", "")
+    name = name.lower()
+    if name not in ("relu", "softplus"):
+        raise ValueError("transfer_fct must be relu or softplus, got %r" % (transfer_fct,))
+    return name
+
+
+def softplus(x):   # stands in for the reference's default `tf.nn.softplus` (vae_assoc.py:26); a token, not a kernel
+    raise RuntimeError("softplus is a selector token; the activation runs inside the CUDA kernels")
+
+
+def relu(x):
+    raise RuntimeError("relu is a selector token; the activation runs inside the CUDA kernels")
+
+
+def xavier_init(fan_in, fan_out, constant=1, rng=None):
+    """vae_assoc.py:11-18 -- U(+-c*sqrt(6/(fan_in+fan_out))), [fan_in, fan_out] fp32 (host-side, seeded)."""
+    rng = np.random if rng is None else rng
+    high = constant * np.sqrt(6.0 / (fan_in + fan_out))
+    return rng.uniform(-high, high, size=(fan_in, fan_out)).astype(np.float32)
+
+
+class VaeAssocError(RuntimeError):
+    pass
+
+
+class AssocVariationalAutoEncoder(object):
+    """Drop-in for the reference class (vae_assoc.py:20).  Extra keyword-only arguments select the precision
+    (`"tf32"`: tcgen05 tensor cores, `"fp32"`: SIMT FFMA), the device and the RNG seeds."""
+
+    def __init__(self, network_architectures, binary=True, transfer_fct=softplus, weights=1.0, assoc_lambda=1.0,
+                 learning_rate=0.001, batch_size=100, precision="tf32", device=None, seed=0, eps_seed=0,
+                 use_graph=True, global_batch=None, global_row0=0):
+        import torch
+        self._torch = torch
+        self.network_architectures = network_architectures
+        self.assoc_lambda = assoc_lambda
+        n = len(network_architectures)
+        if type(binary) is list:                                   # vae_assoc.py:31-35
+            assert len(binary) == n
+            self.binary = binary
+        else:
+            self.binary = [binary] * n
+        if type(weights) is list:                                  # vae_assoc.py:37-41
+            assert len(weights) == n
+            self.weights = weights
+        else:
+            self.weights = [weights] * n
+        self.transfer_fct = transfer_fct
+        self.learning_rate = learning_rate
+        self.batch_size = batch_size
+        self.n_z = network_architectures[0]["n_z"]                 # vae_assoc.py:89
+        self.precision = precision
+        if n > L.MAX_MODALITIES:
+            raise ValueError("at most %d modalities" % L.MAX_MODALITIES)
+        if not torch.cuda.is_available():
+            raise VaeAssocError("no CUDA device: the associated-VAE train step has no CPU fallback")
+        self._lib = L.load()
+        self._device = torch.cuda.current_device() if device is None else int(device)
+        cfg = L.Config()
+        cfg.abi_version = L.ABI_VERSION
+        cfg.n_modalities = n
+        cfg.batch_size = int(batch_size)
+        cfg.n_z = int(self.n_z)
+        cfg.transfer_fct = L.SOFTPLUS if _fct_name(transfer_fct) == "softplus" else L.RELU
+        cfg.precision = {"fp32": L.FP32, "tf32": L.TF32}[precision]
+        cfg.device = self._device
+        cfg.use_graph = 1 if use_graph else 0
+        cfg.assoc_lambda = float(assoc_lambda)
+        cfg.learning_rate = float(learning_rate)
+        cfg.beta1, cfg.beta2, cfg.adam_epsilon = 0.9, 0.999, 1e-8   # tf.train.AdamOptimizer defaults (:373-374)
+        cfg.global_batch = int(global_batch or 0)
+        cfg.global_row0 = int(global_row0)
+        cfg.eps_seed = int(eps_seed) & 0xFFFFFFFF
+        for m, na in enumerate(network_architectures):
+            mod = cfg.mod[m]
+            mod.n_input = int(na["n_input"])
+            mod.n_hidden_recog_1 = int(na["n_hidden_recog_1"]); mod.n_hidden_recog_2 = int(na["n_hidden_recog_2"])
+            mod.n_hidden_gener_1 = int(na["n_hidden_gener_1"]); mod.n_hidden_gener_2 = int(na["n_hidden_gener_2"])
+            mod.hidden_conv = 1 if na.get("hidden_conv", False) else 0
+            mod.binary = 1 if self.binary[m] else 0
+            mod.weight = float(self.weights[m])
+            assert na["n_z"] == self.n_z, "all modalities share one latent size (vae_assoc.py:89-91)"
+        self._cfg = cfg
+        h = L.Handle()
+        if self._lib.vaeassoc_create(C.byref(cfg), C.byref(h)) != 0:
+            raise VaeAssocError(self._lib.vaeassoc_last_error(None).decode())
+        self._h = h
+        self._dev = torch.device("cuda", self._device)
+        self._bind_stream()
+        self._tensors = []
+        for i in range(self._lib.vaeassoc_num_tensors(h)):
+            ti = L.TensorInfo()
+            self._check(self._lib.vaeassoc_layout_query(h, i, C.byref(ti)))
+            self._tensors.append(ti)
+        self._rng = np.random.RandomState(seed)
+        self._init_weights()
+        self._prior_draws = 0
+        self._pinned = None
+        self._submitted = 0
+
+    # ---- plumbing --------------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            raise VaeAssocError(self._lib.vaeassoc_last_error(self._h).decode())
+
+    def _bind_stream(self):
+        s = self._torch.cuda.current_stream(self._dev).cuda_stream
+        self._check(self._lib.vaeassoc_set_stream(self._h, C.c_void_p(s)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.vaeassoc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _init_weights(self):
+        """Reference initialisers (vae_assoc.py:185-215,257-300): Xavier-uniform weights, zero biases."""
+        for i, ti in enumerate(self._tensors):
+            shape = tuple(ti.shape[:ti.ndim])
+            if ti.ndim == 1:
+                w = np.zeros(shape, np.float32)
+            else:
+                w = xavier_init(shape[0], shape[1], rng=self._rng)
+            self._set(L.PARAMS, i, w)
+
+    def _set(self, which, i, arr):
+        ti = self._tensors[i]
+        a = np.ascontiguousarray(arr, dtype=np.float32).reshape(int(ti.rows), int(ti.cols))
+        self._check(self._lib.vaeassoc_tensor_set(self._h, which, i, a.ctypes.data_as(C.c_void_p)))
+
+    def _get(self, which, i):
+        ti = self._tensors[i]
+        a = np.empty((int(ti.rows), int(ti.cols)), np.float32)
+        self._check(self._lib.vaeassoc_tensor_get(self._h, which, i, a.ctypes.data_as(C.c_void_p)))
+        return a.reshape(tuple(ti.shape[:ti.ndim]))
+
+    # ---- parameter / optimiser-state access (tf.Variable + tf.train.Saver surface) ---------------------
+    def variable_names(self):
+        return [t.name.decode() for t in self._tensors]
+
+    def variable_roles(self):
+        return [(t.modality, t.role.decode()) for t in self._tensors]
+
+    def get_params(self):
+        return [self._get(L.PARAMS, i) for i in range(len(self._tensors))]
+
+    def set_params(self, params):
+        flat = [p for ps in params for p in ps] if isinstance(params[0], (list, tuple)) else list(params)
+        assert len(flat) == len(self._tensors)
+        for i, p in enumerate(flat):
+            self._set(L.PARAMS, i, p)
+
+    def get_grads(self):
+        return [self._get(L.GRADS, i) for i in range(len(self._tensors))]
+
+    def get_adam_state(self):
+        step = C.c_int64()
+        self._check(self._lib.vaeassoc_step_get(self._h, C.byref(step)))
+        return ([self._get(L.ADAM_M, i) for i in range(len(self._tensors))],
+                [self._get(L.ADAM_V, i) for i in range(len(self._tensors))], int(step.value))
+
+    def set_adam_state(self, m, v, step):
+        for i in range(len(self._tensors)):
+            self._set(L.ADAM_M, i, m[i])
+            self._set(L.ADAM_V, i, v[i])
+        self._check(self._lib.vaeassoc_step_set(self._h, int(step)))
+
+    def set_precision(self, precision):
+        self._check(self._lib.vaeassoc_set_precision(self._h, {"fp32": L.FP32, "tf32": L.TF32}[precision]))
+        self.precision = precision
+
+    def launch_count(self):
+        return int(self._lib.vaeassoc_launch_count(self._h))
+
+    # ---- argument marshalling -----------------------------------------------------------------------
+    def _is_device(self, X):
+        return all(self._torch.is_tensor(x) and x.is_cuda for x in X)
+
+    def _dev_args(self, X):
+        ptrs = (C.c_void_p * L.MAX_MODALITIES)()
+        lds = (C.c_int64 * L.MAX_MODALITIES)()
+        keep = []
+        for m, x in enumerate(X):
+            na = self.network_architectures[m]
+            if x.dtype != self._torch.float32 or x.stride(1) != 1:
+                x = x.float().contiguous()
+            assert tuple(x.shape) == (self.batch_size, na["n_input"]), \
+                "modality %d: expected %s, got %s (the batch size is static, vae_assoc.py:90)" % (
+                    m, (self.batch_size, na["n_input"]), tuple(x.shape))
+            keep.append(x)
+            ptrs[m] = x.data_ptr()
+            lds[m] = x.stride(0)
+        return ptrs, lds, keep
+
+    def _host_args(self, X):
+        ptrs = (C.c_void_p * L.MAX_MODALITIES)()
+        keep = []
+        for m, x in enumerate(X):
+            na = self.network_architectures[m]
+            if self._torch.is_tensor(x):
+                x = x.detach().cpu().numpy()
+            a = np.ascontiguousarray(x, dtype=np.float32)
+            assert a.shape == (self.batch_size, na["n_input"]), \
+                "modality %d: expected %s, got %s (the batch size is static, vae_assoc.py:90)" % (
+                    m, (self.batch_size, na["n_input"]), a.shape)
+            keep.append(a)
+            ptrs[m] = a.ctypes.data
+        return ptrs, keep
+
+    def _eps_dev(self, eps):
+        if eps is None:
+            return None, None
+        t = self._torch
+        e = eps if t.is_tensor(eps) else t.as_tensor(np.asarray(eps, dtype=np.float32))
+        e = e.to(self._dev, t.float32).contiguous()
+        assert tuple(e.shape) == (self.batch_size, self.n_z)
+        return C.c_void_p(e.data_ptr()), e
+
+    def _to_dev(self, X):
+        t = self._torch
+        return [x if (t.is_tensor(x) and x.is_cuda) else t.as_tensor(np.ascontiguousarray(x, dtype=np.float32)).to(self._dev)
+                for x in X]
+
+    # ---- the reference API -------------------------------------------------------------------------
+    def partial_fit(self, X, eps=None):
+        """Train model based on mini-batch of input data.  Return cost of mini-batch.  (vae_assoc.py:378-386)
+
+        `X` = list of per-modality [batch_size, n_input] arrays (numpy -> host path with H2D inside the call,
+        CUDA tensors -> device path).  `eps` optionally injects the reparameterisation noise (parity tests)."""
+        self._bind_stream()
+        cost = C.c_float()
+        if self._is_device(X):
+            ptrs, lds, keep = self._dev_args(X)
+            ep, ekeep = self._eps_dev(eps)
+            self._check(self._lib.vaeassoc_train_step(self._h, ptrs, lds, ep))
+            self._check(self._lib.vaeassoc_cost_read(self._h, C.byref(cost)))
+        else:
+            ptrs, keep = self._host_args(X)
+            e = None if eps is None else np.ascontiguousarray(eps, dtype=np.float32)
+            self._check(self._lib.vaeassoc_partial_fit_host(
+                self._h, ptrs, None if e is None else e.ctypes.data_as(C.c_void_p), C.byref(cost)))
+        return np.float32(cost.value)
+
+    def partial_fit_async(self, X, eps=None):
+        """Same step without the per-step host synchronisation the reference pays (vae_assoc.py:383-386);
+        the cost lands in the device-side history (see `cost_history`)."""
+        if self._is_device(X):
+            ptrs, lds, keep = self._dev_args(X)
+            ep, ekeep = self._eps_dev(eps)
+            self._check(self._lib.vaeassoc_train_step(self._h, ptrs, lds, ep))
+        else:
+            ptrs, keep = self._host_args(X)
+            e = None if eps is None else np.ascontiguousarray(eps, dtype=np.float32)
+            self._check(self._lib.vaeassoc_submit_host(self._h, ptrs, None if e is None else e.ctypes.data_as(C.c_void_p)))
+
+    def compute_gradients(self, X, eps=None):
+        """Forward + backward without the Adam update; returns the cost.  Gradients: `get_grads()`."""
+        self._bind_stream()
+        X = self._to_dev(X)
+        ptrs, lds, keep = self._dev_args(X)
+        ep, ekeep = self._eps_dev(eps)
+        self._check(self._lib.vaeassoc_grad_step(self._h, ptrs, lds, ep))
+        cost = C.c_float()
+        self._check(self._lib.vaeassoc_cost_read(self._h, C.byref(cost)))
+        return np.float32(cost.value)
+
+    def last_cost(self):
+        cost = C.c_float()
+        self._check(self._lib.vaeassoc_cost_read(self._h, C.byref(cost)))
+        return np.float32(cost.value)
+
+    def cost_history(self, first_step, n):
+        out = np.empty(int(n), np.float32)
+        self._check(self._lib.vaeassoc_cost_history(self._h, int(first_step), int(n), out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def synchronize(self):
+        self._check(self._lib.vaeassoc_stream_sync(self._h))
+
+    def evaluate_cost(self, X, eps=None):
+        """vae_assoc.py:388-391"""
+        self._bind_stream()
+        X = self._to_dev(X)
+        ptrs, lds, keep = self._dev_args(X)
+        ep, ekeep = self._eps_dev(eps)
+        cost = C.c_float()
+        self._check(self._lib.vaeassoc_eval_cost(self._h, ptrs, lds, ep, C.byref(cost)))
+        return np.float32(cost.value)
+
+    def _encode(self, m, x):
+        t = self._torch
+        x = self._to_dev([x])[0]
+        if x.dtype != t.float32 or x.stride(1) != 1:
+            x = x.float().contiguous()
+        assert tuple(x.shape) == (self.batch_size, self.network_architectures[m]["n_input"])
+        mu = t.empty((self.batch_size, self.n_z), dtype=t.float32, device=self._dev)
+        self._check(self._lib.vaeassoc_encode(self._h, m, C.c_void_p(x.data_ptr()), x.stride(0),
+                                              C.c_void_p(mu.data_ptr()), None))
+        return mu.cpu().numpy()
+
+    def transform(self, X, sens_idx=None):
+        """Transform data by mapping it into the latent space (z_mean).  (vae_assoc.py:393-403)"""
+        self._bind_stream()
+        if sens_idx is None:
+            return [self._encode(m, x) for m, x in enumerate(X)]
+        assert sens_idx < len(self.network_architectures)
+        return self._encode(sens_idx, X)
+
+    def generate(self, z_mu=None):
+        """Generate data by sampling from latent space; z feeds the decoders directly.  (vae_assoc.py:405-419)"""
+        self._bind_stream()
+        t = self._torch
+        if z_mu is None:
+            # the reference draws np.random.normal((batch_size, n_z)) (:414); here Philox on the device
+            z = t.empty((self.batch_size, self.n_z), dtype=t.float32, device=self._dev)
+            self._check(self._lib.vaeassoc_philox_normal(self._h, self._cfg.eps_seed, 5, 0, self.batch_size, self.n_z,
+                                                         self._prior_draws, C.c_void_p(z.data_ptr())))
+            self._prior_draws += 1
+        else:
+            z = t.as_tensor(np.ascontiguousarray(z_mu, dtype=np.float32)).to(self._dev) if not t.is_tensor(z_mu) \
+                else z_mu.to(self._dev, t.float32).contiguous()
+        assert tuple(z.shape) == (self.batch_size, self.n_z), \
+            "z_mu must be [batch_size, n_z] (the reference's callers pad to a full batch, baxter_vae_assoc_writer.py:142-145)"
+        out = []
+        for m, na in enumerate(self.network_architectures):
+            xh = t.empty((self.batch_size, na["n_input"]), dtype=t.float32, device=self._dev)
+            self._check(self._lib.vaeassoc_decode(self._h, m, C.c_void_p(z.data_ptr()), C.c_void_p(xh.data_ptr())))
+            out.append(xh.cpu().numpy())
+        return out
+
+    def reconstruct(self, X, eps=None):
+        """Use VAE to reconstruct given data: one encode+sample+decode per modality.  (vae_assoc.py:421-425)"""
+        self._bind_stream()
+        t = self._torch
+        out = []
+        for m, x in enumerate(X):
+            na = self.network_architectures[m]
+            x = self._to_dev([x])[0]
+            if x.dtype != t.float32 or x.stride(1) != 1:
+                x = x.float().contiguous()
+            assert tuple(x.shape) == (self.batch_size, na["n_input"])
+            e = None if eps is None else (eps[m] if isinstance(eps, (list, tuple)) else eps)
+            ep, ekeep = self._eps_dev(e)
+            xh = t.empty((self.batch_size, na["n_input"]), dtype=t.float32, device=self._dev)
+            self._check(self._lib.vaeassoc_reconstruct(self._h, m, C.c_void_p(x.data_ptr()), x.stride(0), ep,
+                                                       C.c_void_p(xh.data_ptr())))
+            out.append(xh.cpu().numpy())
+        return out
+
+    # ---- probe points (the author's commented-out debugging fetches, vae_assoc.py:545-571) ----------------
+    def _probe(self, kind, m, n):
+        buf = np.empty(int(n), np.float32)
+        wrote = C.c_int64()
+        self._check(self._lib.vaeassoc_probe_get(self._h, kind, m, buf.ctypes.data_as(C.c_void_p), int(n), C.byref(wrote)))
+        return buf[:wrote.value]
+
+    def _probe_list(self, kind, cols=None):
+        out = []
+        for m, na in enumerate(self.network_architectures):
+            c = self.n_z if cols is None else cols(na)
+            out.append(self._probe(kind, m, self.batch_size * c).reshape(self.batch_size, c))
+        return out
+
+    @property
+    def z_means(self):
+        return self._probe_list(L.PROBE_Z_MEAN)
+
+    @property
+    def z_log_sigma_sqs(self):
+        return self._probe_list(L.PROBE_Z_LOG_SIGMA_SQ)
+
+    @property
+    def z_array(self):
+        return self._probe_list(L.PROBE_Z)
+
+    @property
+    def x_reconstr_means(self):
+        return self._probe_list(L.PROBE_X_RECONSTR_MEAN, cols=lambda na: na["n_input"])
+
+    @property
+    def d_z_means(self):
+        return self._probe_list(L.PROBE_D_Z_MEAN)
+
+    @property
+    def d_z_log_sigma_sqs(self):
+        return self._probe_list(L.PROBE_D_Z_LOG_SIGMA_SQ)
+
+    @property
+    def vae_reconstr_losses(self):
+        out = []
+        for m in range(len(self.network_architectures)):
+            r = self._probe(L.PROBE_RECONSTR_LOSS, m, self.batch_size)
+            out.append(r if self.binary[m] else np.float32(r[0]))
+        return out
+
+    @property
+    def vae_latent_losses(self):
+        return [self._probe(L.PROBE_LATENT_LOSS, m, self.batch_size) for m in range(len(self.network_architectures))]
+
+    @property
+    def vae_costs(self):
+        return [np.float32(self._probe(L.PROBE_VAE_COST, m, 1)[0]) for m in range(len(self.network_architectures))]
+
+    @property
+    def assoc_costs(self):
+        if len(self.network_architectures) < 2:
+            return []
+        return [np.float32(self._probe(L.PROBE_ASSOC_COST, 0, 1)[0])]   # summed over modality pairs
+
+    @property
+    def cost(self):
+        return self.last_cost()
+
+    @property
+    def last_eps(self):
+        return self._probe(L.PROBE_EPS, 0, self.batch_size * self.n_z).reshape(self.batch_size, self.n_z)
+
+    # ---- synthetic paired batches (replaces dataset.py / utils.py for benchmarks) ------------------------
+    def synth_batch(self, row0, n_rows=None, data_seed=0, proj_seed=1):
+        """Device-resident synthetic pairs for global rows [row0, row0+n_rows): list of CUDA tensors."""
+        self._bind_stream()
+        t = self._torch
+        n_rows = self.batch_size if n_rows is None else int(n_rows)
+        outs = [t.empty((n_rows, na["n_input"]), dtype=t.float32, device=self._dev) for na in self.network_architectures]
+        ptrs = (C.c_void_p * L.MAX_MODALITIES)()
+        for m, o in enumerate(outs):
+            ptrs[m] = o.data_ptr()
+        self._check(self._lib.vaeassoc_synth_batch(self._h, int(data_seed), int(proj_seed), int(row0), n_rows, ptrs))
+        return outs
+
+    def philox_normal(self, seed, tag, row0, n_rows, n_cols, step=0):
+        t = self._torch
+        out = t.empty((n_rows, n_cols), dtype=t.float32, device=self._dev)
+        self._check(self._lib.vaeassoc_philox_normal(self._h, int(seed), int(tag), int(row0), int(n_rows), int(n_cols),
+                                                     int(step), C.c_void_p(out.data_ptr())))
+        return out
+
+    # ---- data parallelism ----------------------------------------------------------------------------
+    def init_data_parallel(self):
+        """Join the NCCL communicator of the current torch.distributed job (one process per GPU)."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(), dist.get_rank()
+        path = L.nccl_library_path().encode()
+        buf = (C.c_ubyte * 128)()
+        if rank == 0:
+            if self._lib.vaeassoc_comm_unique_id(path, buf) != 0:
+                raise VaeAssocError(self._lib.vaeassoc_last_error(None).decode())
+        ids = [bytes(buf)]
+        dist.broadcast_object_list(ids, src=0)
+        buf = (C.c_ubyte * 128).from_buffer_copy(ids[0])
+        self._check(self._lib.vaeassoc_comm_init(self._h, path, buf, rank, world))
+
+    # ---- checkpoints (tf.train.Saver surface, vae_assoc.py:70,427-463) -------------------------------------
+    def save_model(self, fname=None):
+        if fname is None:
+            ts = time.time()
+            ckpt_fname = 'vae_assoc_' + datetime.datetime.fromtimestamp(ts).strftime('%Y_%m_%d_%H_%M_%S') + \
+                '_batchsize_{}.ckpt'.format(self.batch_size)
+        else:
+            ckpt_fname = fname
+        print('Saving model to {}...'.format(ckpt_fname))
+        from . import checkpoint
+        checkpoint.save(self, ckpt_fname)
+        return
+
+    def restore_model(self, folder=None, fname=None):
+        """Failures print and return, like the reference (vae_assoc.py:447-462)."""
+        model_folder = 'output' if folder is None else folder
+        if os.path.isdir(model_folder) and os.path.exists(model_folder):
+            if fname is None:
+                files = [f for f in os.listdir(model_folder) if f.endswith('.ckpt')]
+                if not files:
+                    print('No valid model file.')
+                    return
+                model_file = files[-1]
+            else:
+                model_file = fname
+            path = os.path.join(model_folder, model_file)
+            if os.path.exists(path):
+                print('Loading {}...'.format(path))
+                from . import checkpoint
+                checkpoint.load(self, path)
+            else:
+                print('Invalid or non-exist model file.')
+        else:
+            print('Invalid or non-exist model folder.')
+        return
+
+
+def train(data_sets, network_architectures, binary=True, weights=1.0, assoc_lambda=1e-5, learning_rate=0.001,
+          batch_size=100, training_epochs=10, display_step=5, early_stop=False, **model_kwargs):
+    """vae_assoc.py:498-583.  Same loop and return value `(model, avg_cost_hist)`; differences that do not change
+    results: batches are uploaded through the pipelined host path and the per-step cost is read back once per
+    epoch from the device-side history instead of synchronising every step (vae_assoc.py:383-386)."""
+    vae_assoc = AssocVariationalAutoEncoder(network_architectures, binary, transfer_fct=relu, weights=weights,
+                                            assoc_lambda=assoc_lambda, learning_rate=learning_rate,
+                                            batch_size=batch_size, **model_kwargs)
+    n_samples = data_sets.train._data.shape[0]
+    sens_indices = np.concatenate([[0], np.cumsum([na["n_input"] for na in network_architectures])])
+    n_mod = len(network_architectures)
+    avg_cost_hist = []
+    valid_cost = None
+    step = 0
+
+    def segment(batch_xs):
+        return [np.ascontiguousarray(batch_xs[:, sens_indices[i]:sens_indices[i + 1]], dtype=np.float32)
+                for i in range(n_mod)]
+
+    for epoch in range(training_epochs):
+        avg_cost = 0.
+        total_batch = int(n_samples / batch_size)
+        if early_stop:
+            if epoch % early_stop == 0:
+                curr_valid_cost = 0
+                n_valid_batches = int(data_sets.validation._data.shape[0] / batch_size)
+                for i in range(n_valid_batches):
+                    batch_xs, _ = data_sets.validation.next_batch(batch_size)
+                    curr_valid_cost += vae_assoc.evaluate_cost(segment(batch_xs)) / n_valid_batches
+                print("Validation cost=", "{:.9f}".format(curr_valid_cost))
+                if valid_cost is not None:
+                    if curr_valid_cost > valid_cost:
+                        print('Validation error increases. Early stop at epoch {} to prevent overfitting...'.format(epoch + 1))
+                        break
+                valid_cost = curr_valid_cost
+        first = step
+        for i in range(total_batch):
+            batch_xs, _ = data_sets.train.next_batch(batch_size)
+            vae_assoc.partial_fit_async(segment(batch_xs))
+            step += 1
+        if total_batch:
+            costs = vae_assoc.cost_history(first, total_batch)
+            for cost in costs:
+                avg_cost += cost / n_samples * batch_size
+                avg_cost_hist.append(avg_cost)
+        if epoch % display_step == 0:
+            print("Epoch:", '%04d' % (epoch + 1), "cost=", "{:.9f}".format(avg_cost))
+    return vae_assoc, avg_cost_hist
