@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""Benchmark of the associated-VAE train step (BASELINE.json metric: paired samples/sec per train step).
+
+    python bench.py --gpus N --steps K --warmup W                      # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W     # CPU restatement of the reference graph
+
+A "step" is one `partial_fit` of the reference model (vae_assoc.py:378-386) on one synthetic paired batch:
+forward of both encoders/decoders, losses, backward, Adam.  Workload = BASELINE.json configs[1]/[2]:
+reference architecture (image 784-500-500, joint 147-200-200, n_z 4, relu, weights [50,1], lambda 8, lr 1e-3),
+8192 pairs per GPU (global batch 8192*N: 65536 at N=8), weak scaling.  One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_SAMPLE = 7744400.0      # fwd 2 862 400 + bwd 4 882 000 (2*K*N per GEMM row)
+N_PARAMS = 1434947
+
+
+def ref_archs(n_z=4):
+    img = dict(scope="image", hidden_conv=False, n_hidden_recog_1=500, n_hidden_recog_2=500, n_hidden_gener_1=500,
+               n_hidden_gener_2=500, n_input=784, n_z=n_z)
+    jnt = dict(scope="joint", hidden_conv=False, n_hidden_recog_1=200, n_hidden_recog_2=200, n_hidden_gener_1=200,
+               n_hidden_gener_2=200, n_input=147, n_z=n_z)
+    return [img, jnt]
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tensor=d["bf16_tflops"], tensor_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tensor=1590.0, tensor_sustained=1400.0, src="fallback")
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def cpu_reference_run(batch, steps, warmup, threads=None):
+    """CPU restatement (torch fp32, all host threads) of the reference graph at its op granularity; NOT TensorFlow
+    (not installable here).  Returns (samples_per_s, ms_per_step, cores)."""
+    import torch
+    from oracle import synth, torch_twin
+    from oracle import vae_assoc_oracle as vo
+    cores = threads or os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    archs = vo.reference_archs(4)
+    params = vo.init_params(archs, 0)
+    model = torch_twin.TorchAssocVAE(archs, [True, False], "relu", [50.0, 1.0], 8.0, 1e-3, batch, params, dtype=torch.float32)
+    X = [torch.tensor(x, dtype=torch.float32) for x in synth.synth_batch(archs, [True, False], 0, 1, 0, batch)]
+    for _ in range(warmup):
+        model.partial_fit(X)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        model.partial_fit(X)          # float(cost): one host read per step, as partial_fit does (vae_assoc.py:383-386)
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, 1e3 * dt / steps, cores
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=8192, help="pairs per GPU per step")
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = ("assoc-VAE reference arch (img 784-500-500, jnt 147-200-200, n_z 4, relu, w [50,1], lambda 8, lr 1e-3), "
+                "%d pairs per GPU per step" % args.batch)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        # each step = a bounded sample (same per-GPU batch) so that the run ends within minutes
+        steps = min(args.steps, 10); warm = min(args.warmup, 2)
+        sps, ms, cores = cpu_reference_run(args.batch, steps, warm)
+        line = dict(impl="reference", metric="paired samples/sec/train step", value=sps, unit="samples/s",
+                    n_gpus=args.gpus, steps=steps, warmup=warm, ms_per_step=ms, higher_is_better=True, scaling="weak",
+                    vs_baseline=None, dtype="fp32", data="synthetic",
+                    config=dict(workload=workload, global_batch=args.batch, note="CPU restatement (torch fp32) of the "
+                                "reference graph, not TensorFlow (not installable here); one process, host cores only"),
+                    cpu_baseline=dict(value=sps, unit="samples/s", cores=cores, kind="port",
+                                      sample="%d steps of %d pairs after %d warm-up" % (steps, args.batch, warm)),
+                    e2e=dict(value=sps, unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from vae_assoc_b200 import vae_assoc
+
+    B = args.batch
+    Bg = B * world
+    model = vae_assoc.AssocVariationalAutoEncoder(ref_archs(), [True, False], transfer_fct=vae_assoc.relu,
+                                                  weights=[50, 1], assoc_lambda=8, learning_rate=1e-3, batch_size=B,
+                                                  precision=args.precision, seed=0, use_graph=not args.no_graph,
+                                                  global_batch=Bg, global_row0=rank * B)
+    if world > 1:
+        model.init_data_parallel()
+
+    # device-resident pool of distinct synthetic batches, larger than L2 (126 MB) so that no step re-reads a
+    # cached input: 16 x 30.5 MB at B = 8192
+    bytes_per_batch = B * 931 * 4
+    pool_n = max(4, int(np.ceil(2.2 * 126e6 / bytes_per_batch)))
+    pool_n = min(pool_n, 512)
+    pool = [model.synth_batch((k * world + rank) * B, B) for k in range(pool_n)]
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- kernel-resident number: inputs already in HBM ------------------------------------------------------
+    for k in range(args.warmup):
+        model.partial_fit_async(pool[k % pool_n])
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = model.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for k in range(args.steps):
+        model.partial_fit_async(pool[(args.warmup + k) % pool_n])
+    ev1.record()
+    barrier()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = model.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    last_cost = float(model.last_cost())
+    ms_step = ms_total / args.steps
+    value = Bg * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end: pinned host batches -> H2D -> step -> D2H of the cost, every step --------------------------
+    host_n = 4
+    host_pool = []
+    for k in range(host_n):
+        xs = pool[k]
+        host_pool.append([torch.empty(x.shape, dtype=torch.float32, pin_memory=True).copy_(x).numpy() for x in xs])
+    torch.cuda.synchronize()
+    e2e_steps = args.steps
+    for k in range(min(args.warmup, 5)):
+        model.partial_fit_async(host_pool[k % host_n])
+    barrier()
+    sub0 = None
+    t0 = time.perf_counter()
+    ev0.record()
+    for k in range(e2e_steps):
+        model.partial_fit_async(host_pool[k % host_n])
+    ev1.record()
+    model.synchronize()
+    barrier()
+    wall = time.perf_counter() - t0
+    e2e_ms = max_over_ranks(max(ev0.elapsed_time(ev1), wall * 1e3))
+    e2e_value = Bg * e2e_steps / (e2e_ms * 1e-3)
+
+    # ---- per-kernel roofline: one eager step with CUDA events between ops, averaged ------------------------------
+    import ctypes as C
+    from vae_assoc_b200 import _lib as L
+    cap = 128
+    names = C.create_string_buffer(32 * cap)
+    ms = (C.c_float * cap)(); fl = (C.c_double * cap)(); by = (C.c_double * cap)()
+    acc = {}
+    reps = 5
+    for r in range(reps + 1):
+        ptrs, lds, keep = model._dev_args(pool[r % pool_n])
+        n = model._lib.vaeassoc_profile_step(model._h, ptrs, lds, None, names, ms, fl, by, cap)
+        assert n > 0, model._lib.vaeassoc_last_error(model._h)
+        if r == 0:
+            continue
+        for i in range(n):
+            nm = names.raw[32 * i:32 * i + 32].split(b"\0")[0].decode()
+            a = acc.setdefault(nm, [0.0, fl[i], by[i]])
+            a[0] += ms[i] / reps
+    pk = peaks()
+    kernels = []
+    for nm, (t, f, b) in acc.items():
+        k = dict(name=nm, ms=round(t, 5))
+        if f > 0:
+            k.update(bound="tensor", achieved=f / (t * 1e-3) / 1e12, unit="TFLOP/s")
+            k["frac"] = k["achieved"] / pk["tensor"]
+        elif b > 0:
+            k.update(bound="hbm", achieved=b / (t * 1e-3) / 1e9, unit="GB/s")
+            k["frac"] = k["achieved"] / pk["hbm"]
+        kernels.append(k)
+    kernels.sort(key=lambda k: -k["ms"])
+    top = kernels[0]
+    eager_ms = sum(k["ms"] for k in kernels)
+    roofline = dict(bound=top.get("bound", "hbm"), kernel=top["name"], achieved=top.get("achieved"),
+                    peak=pk["tensor"] if top.get("bound") == "tensor" else pk["hbm"], unit=top.get("unit"),
+                    frac=top.get("frac"), traffic=None, peak_source=pk["src"],
+                    share_of_step=top["ms"] / eager_ms,
+                    note="tcgen05 kind::tf32 nominal peak is half the bf16 figure used as `peak`"
+                    if top.get("bound") == "tensor" else "")
+    step_tflops = FLOP_PER_SAMPLE * B / (ms_step * 1e-3) / 1e12
+
+    line = dict(metric="paired samples/sec/train step", value=value, unit="samples/s", n_gpus=world, steps=args.steps,
+                warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype=args.precision, data="synthetic",
+                config=dict(workload=workload, global_batch=Bg, per_gpu_batch=B, parallelism="dp%d" % world,
+                            l2="inputs rotate through a device pool of %d distinct batches (%.0f MB > 126 MB L2)"
+                               % (pool_n, pool_n * bytes_per_batch / 1e6),
+                            graph=not args.no_graph),
+                clocks=clocks, gpu_launches=int(launches),
+                e2e=dict(value=e2e_value, unit="samples/s", h2d_bytes_per_step=bytes_per_batch, d2h_bytes_per_step=4,
+                         ms_per_step=e2e_ms / e2e_steps,
+                         path="AssocVariationalAutoEncoder.partial_fit_async(numpy pinned) -> vaeassoc_submit_host"),
+                roofline=roofline, step_tflops_per_gpu=step_tflops, last_cost=last_cost,
+                kernels=kernels[:40])
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sps, cms, cores = cpu_reference_run(B, 5, 1)
+        line["cpu_baseline"] = dict(value=sps, unit="samples/s", cores=cores, kind="port", ms_per_step=cms,
+                                    sample="5 steps of %d pairs after 1 warm-up, torch-CPU fp32 restatement "
+                                           "(not TensorFlow)" % B)
+    if rank == 0:
+        print(json.dumps(line))
+    model.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

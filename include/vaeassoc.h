@@ -120,6 +120,9 @@ int vaeassoc_partial_fit_host(vaeassoc_handle h, const float* const* x_host, con
  * `vaeassoc_submit_host` returns as soon as the batch is queued; costs are read back with
  * vaeassoc_cost_history / vaeassoc_cost_read. */
 int vaeassoc_submit_host(vaeassoc_handle h, const float* const* x_host, const float* eps_host);
+/* every submit also queues an async D2H of that step's cost into a pinned host ring (4096 entries);
+ * this synchronises the stream and returns the costs of submits [first_submit, first_submit + n). */
+int vaeassoc_submit_costs(vaeassoc_handle h, int64_t first_submit, int64_t n, float* dst_host);
 
 /* evaluate_cost (vae_assoc.py:388-391): forward + loss, no gradients, no update */
 int vaeassoc_eval_cost(vaeassoc_handle h, const float* const* x_dev, const int64_t* ld, const float* eps_dev,

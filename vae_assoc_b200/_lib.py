@@ -65,6 +65,7 @@ SIGNATURES = {
     "vaeassoc_cost_history": (C.c_int, [Handle, C.c_int64, C.c_int64, C.c_void_p]),
     "vaeassoc_partial_fit_host": (C.c_int, [Handle, FloatPP, C.c_void_p, C.POINTER(C.c_float)]),
     "vaeassoc_submit_host": (C.c_int, [Handle, FloatPP, C.c_void_p]),
+    "vaeassoc_submit_costs": (C.c_int, [Handle, C.c_int64, C.c_int64, C.c_void_p]),
     "vaeassoc_eval_cost": (C.c_int, [Handle, FloatPP, I64P, C.c_void_p, C.POINTER(C.c_float)]),
     "vaeassoc_encode": (C.c_int, [Handle, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "vaeassoc_decode": (C.c_int, [Handle, C.c_int, C.c_void_p, C.c_void_p]),

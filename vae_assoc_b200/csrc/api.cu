@@ -121,10 +121,12 @@ struct vaeassoc_ctx {
   bool shadow_dirty = true;
   float *eps = nullptr, *eps_in[2] = {nullptr, nullptr}, *lat_partials = nullptr, *scalars = nullptr;
   float *cost_hist = nullptr, *last_cost = nullptr;
+  float* host_cost_ring = nullptr;   // pinned; one async D2H of the step's cost per vaeassoc_submit_host
+  static constexpr int kHostRing = 4096;
   int hist_cap = 1 << 16;
   int64_t* step_dev = nullptr;
   int lat_blocks = 0;
-  bool round_z = false;
+  bool round_z = false, round_x = false;
   int64_t launches = 0;
   // schedules
   std::vector<Op> ops_fwd_enc, ops_latent_fwd, ops_fwd_dec, ops_loss, ops_bwd_dec, ops_latent_bwd, ops_bwd_enc;
@@ -246,6 +248,7 @@ void alloc_buffers(Ctx* c) {
   c->cost_hist = c->dalloc<float>(c->hist_cap);
   c->last_cost = c->dalloc<float>(1);
   c->step_dev = c->dalloc<int64_t>(1);
+  CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&c->host_cost_ring), sizeof(float) * Ctx::kHostRing));
   for (Mod& d : c->mods) {
     d.xin[0] = c->dalloc<float>(B * d.ni);
     d.xin[1] = c->dalloc<float>(B * d.ni);
@@ -337,7 +340,7 @@ void build_ops(Ctx* c) {
   const bool tf32 = c->cfg.precision == VAEASSOC_TF32;
   const float inv_bg = 1.0f / (float)global_batch(c);
   float* P = c->p;   // biases are always read from the fp32 master
-  bool round_z = false, round_dheads = false;
+  bool round_z = false, round_dheads = false, round_x = false;
 
   for (int m = 0; m < M; ++m) {
     Mod& d = c->mods[m];
@@ -373,6 +376,7 @@ void build_ops(Ctx* c) {
     const bool r_dh2 = tc(KIND_TN, w_e2, -1) || tc(KIND_NT, d_e2, d.W2);
     const bool r_dh1 = tc(KIND_TN, w_e1, -1);
     round_z = round_z || tc(KIND_NN, f_d1, d.V1) || tc(KIND_TN, w_d1, -1);
+    round_x = round_x || tc(KIND_NN, f_e1, d.W1) || tc(KIND_TN, w_e1, -1);
     round_dheads = round_dheads || tc(KIND_TN, w_hd, -1) || tc(KIND_NT, d_hd, d.Wh);
 
     auto& enc = c->ops_enc_mod[m];
@@ -422,7 +426,7 @@ void build_ops(Ctx* c) {
     }
     a.eps = c->eps; a.partials = c->lat_partials; a.with_grad = 1; a.round_z = round_z ? 1 : 0;
     c->lat_blocks = (int)std::min<int64_t>(std::max<int64_t>((B + 255) / 256, 1), kMaxPartialBlocks);
-    c->round_z = round_z;
+    c->round_z = round_z; c->round_x = round_x;
     op.bytes = 4.0 * B * nz * (1 + M * 5);
     op.run = [a](cudaStream_t s) { launch_latent_fwd(a, s); };
     c->ops_latent_fwd.push_back(op);
@@ -572,7 +576,7 @@ void stage_inputs(Ctx* c, const float* const* x, const int64_t* ld, const float*
     a.src_ld[m] = (ld && ld[m] > 0) ? ld[m] : d.ni;
     a.dst[m] = d.xs; a.dst_ld[m] = d.nip; a.n_input[m] = d.ni;
   }
-  a.round_tf32 = c->cfg.precision == VAEASSOC_TF32 ? 1 : 0;
+  a.round_tf32 = c->round_x ? 1 : 0;
   a.eps_src = eps; a.eps_dst = want_eps ? c->eps : nullptr; a.n_z = c->cfg.n_z;
   a.eps_seed = c->cfg.eps_seed; a.global_row0 = c->cfg.global_row0; a.step_dev = c->step_dev;
   launch_stage(a, s);
@@ -714,6 +718,7 @@ int vaeassoc_destroy(vaeassoc_handle h) {
   destroy_graphs(h);
   for (TcPlan* p : h->plans) tc_plan_destroy(p);
   for (void* p : h->allocs) cudaFree(p);
+  if (h->host_cost_ring) cudaFreeHost(h->host_cost_ring);
   for (int i = 0; i < 2; ++i) {
     if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
     if (h->ev_consumed[i]) cudaEventDestroy(h->ev_consumed[i]);
@@ -906,7 +911,19 @@ int vaeassoc_submit_host(vaeassoc_handle h, const float* const* x_host, const fl
   stage_inputs(h, xd, nullptr, eps_host ? h->eps_in[slot] : nullptr, h->stream);
   CUDA_OK(cudaEventRecord(h->ev_consumed[slot], h->stream));
   run_step(h, true);
+  CUDA_OK(cudaMemcpyAsync(h->host_cost_ring + (h->submit_count % Ctx::kHostRing), h->last_cost, sizeof(float),
+                          cudaMemcpyDeviceToHost, h->stream));
   h->submit_count += 1;
+  API_END(h)
+}
+
+int vaeassoc_submit_costs(vaeassoc_handle h, int64_t first_submit, int64_t n, float* dst_host) {
+  API_BEGIN(h)
+  if (n < 0 || n > Ctx::kHostRing || first_submit < 0 || first_submit + n > h->submit_count)
+    fail("submit window [%lld,+%lld) is outside the %d most recent of %lld submits", (long long)first_submit,
+         (long long)n, Ctx::kHostRing, (long long)h->submit_count);
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  for (int64_t i = 0; i < n; ++i) dst_host[i] = h->host_cost_ring[(first_submit + i) % Ctx::kHostRing];
   API_END(h)
 }
 

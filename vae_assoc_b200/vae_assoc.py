@@ -126,8 +126,12 @@ class AssocVariationalAutoEncoder(object):
             raise VaeAssocError(self._lib.vaeassoc_last_error(self._h).decode())
 
     def _bind_stream(self):
-        s = self._torch.cuda.current_stream(self._dev).cuda_stream
-        self._check(self._lib.vaeassoc_set_stream(self._h, C.c_void_p(s)))
+        # torch's default stream has handle 0, which the C-ABI reads as "the handle's own stream": name the legacy
+        # default stream explicitly (cudaStreamLegacy == 0x1) so that torch copies/events order with our kernels
+        s = self._torch.cuda.current_stream(self._dev).cuda_stream or 1
+        if s != getattr(self, "_bound_stream", None):
+            self._check(self._lib.vaeassoc_set_stream(self._h, C.c_void_p(s)))
+            self._bound_stream = s
 
     def close(self):
         if getattr(self, "_h", None):
@@ -271,6 +275,7 @@ class AssocVariationalAutoEncoder(object):
     def partial_fit_async(self, X, eps=None):
         """Same step without the per-step host synchronisation the reference pays (vae_assoc.py:383-386);
         the cost lands in the device-side history (see `cost_history`)."""
+        self._bind_stream()
         if self._is_device(X):
             ptrs, lds, keep = self._dev_args(X)
             ep, ekeep = self._eps_dev(eps)
@@ -299,6 +304,12 @@ class AssocVariationalAutoEncoder(object):
     def cost_history(self, first_step, n):
         out = np.empty(int(n), np.float32)
         self._check(self._lib.vaeassoc_cost_history(self._h, int(first_step), int(n), out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def submit_costs(self, first_submit, n):
+        """Costs of host-path submits [first, first+n), read from the pinned ring the steps D2H into."""
+        out = np.empty(int(n), np.float32)
+        self._check(self._lib.vaeassoc_submit_costs(self._h, int(first_submit), int(n), out.ctypes.data_as(C.c_void_p)))
         return out
 
     def synchronize(self):
