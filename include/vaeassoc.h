@@ -176,6 +176,13 @@ int64_t vaeassoc_launch_count(vaeassoc_handle h);
 int vaeassoc_profile_step(vaeassoc_handle h, const float* const* x_dev, const int64_t* ld, const float* eps_dev,
                           char* names, float* ms, double* flops, double* bytes, int capacity);
 
+/* test hook: run ONE dense-layer contraction of the library on caller buffers (device pointers) and synchronise.
+ * kind 0: C = act(A[M,K] B[K,N] + bias)   1: C = (A[M,K] B[N,K]^T) * act'(aux)   2: C += A[K,M]^T B[K,N],
+ * bias_grad += colsum(B).  use_tc selects the tcgen05 kernel (fails if the shape is not served) or the SIMT one. */
+int vaeassoc_debug_gemm(vaeassoc_handle h, int kind, int use_tc, int M, int N, int K, const float* A, int64_t lda,
+                        const float* B, int64_t ldb, float* C, int64_t ldc, const float* bias, float* bias_grad,
+                        const float* aux, int64_t ldaux, int act, int round_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,6 +78,9 @@ SIGNATURES = {
     "vaeassoc_comm_init": (C.c_int, [Handle, C.c_char_p, C.c_void_p, C.c_int, C.c_int]),
     "vaeassoc_comm_destroy": (C.c_int, [Handle]),
     "vaeassoc_launch_count": (C.c_int64, [Handle]),
+    "vaeassoc_debug_gemm": (C.c_int, [Handle, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64,
+                                      C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_int64, C.c_int, C.c_int]),
     "vaeassoc_profile_step": (C.c_int, [Handle, FloatPP, I64P, C.c_void_p, C.c_char_p, C.POINTER(C.c_float),
                                         C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int]),
 }

@@ -286,7 +286,16 @@ Op make_gemm(Ctx* c, const char* name, int m, int kind, GemmArgs a, int64_t w_of
     if (!plan) fail("tcgen05 plan for %s failed: %s", op.name.c_str(), err);
     c->plans.push_back(plan);
     op.name += ".tc";
-    op.run = [plan](cudaStream_t s) { launch_gemm_tc(plan, s); };
+    if (kind == KIND_TN && a.bias_grad) {
+      const GemmArgs b = a;
+      op.launches = 2;
+      op.run = [plan, b](cudaStream_t s) {
+        launch_gemm_tc(plan, s);
+        launch_colsum(b.B, b.ldb, b.K, b.N, b.bias_grad, s);
+      };
+    } else {
+      op.run = [plan](cudaStream_t s) { launch_gemm_tc(plan, s); };
+    }
     return op;
   }
   if (w_off >= 0) a.B = c->p + w_off;
@@ -1100,6 +1109,34 @@ int vaeassoc_comm_destroy(vaeassoc_handle h) {
 }
 
 int64_t vaeassoc_launch_count(vaeassoc_handle h) { return h ? h->launches : -1; }
+
+int vaeassoc_debug_gemm(vaeassoc_handle h, int kind, int use_tc, int M, int N, int K, const float* A, int64_t lda,
+                        const float* B, int64_t ldb, float* C, int64_t ldc, const float* bias, float* bias_grad,
+                        const float* aux, int64_t ldaux, int act, int round_out) {
+  API_BEGIN(h)
+  GemmArgs a;
+  a.M = M; a.N = N; a.K = K; a.A = A; a.lda = lda; a.B = B; a.ldb = ldb; a.C = C; a.ldc = ldc; a.bias = bias;
+  a.bias_grad = bias_grad; a.aux = aux; a.ldaux = ldaux; a.act = act; a.round_out = round_out;
+  if (use_tc) {
+    if (!tc_supported(kind, a)) fail("shape not served by the tcgen05 path");
+    char err[256] = {0};
+    TcPlan* plan = tc_plan_create(kind, a, err, sizeof err);
+    if (!plan) fail("tcgen05 plan failed: %s", err);
+    launch_gemm_tc(plan, h->stream);
+    if (kind == KIND_TN && bias_grad) launch_colsum(B, ldb, K, N, bias_grad, h->stream);
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    tc_plan_destroy(plan);
+  } else {
+    switch (kind) {
+      case KIND_NN: launch_gemm_nn_simt(a, h->stream); break;
+      case KIND_NT: launch_gemm_nt_simt(a, h->stream); break;
+      default: launch_gemm_tn_simt(a, h->stream); break;
+    }
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+  }
+  CUDA_OK(cudaGetLastError());
+  API_END(h)
+}
 
 int vaeassoc_profile_step(vaeassoc_handle h, const float* const* x_dev, const int64_t* ld, const float* eps_dev,
                           char* names, float* ms, double* flops, double* bytes, int capacity) {

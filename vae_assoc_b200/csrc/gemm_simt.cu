@@ -122,11 +122,38 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(GemmArgs g, int k_per_spl
   }
 }
 
+// column sums of a [rows, cols] matrix (bias gradient = colsum of the upstream gradient) accumulated into out[cols].
+// 32 x 8 threads: a warp reads 128 contiguous bytes of one row; 8 row-slabs per CTA reduce through shared memory;
+// one fp32 RED per column per CTA.
+constexpr int CS_ROWS = 256;
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, int64_t ld, int rows, int cols,
+                                                     float* __restrict__ out) {
+  __shared__ float part[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  const int r0 = blockIdx.y * CS_ROWS, r1 = min(rows, r0 + CS_ROWS);
+  float acc = 0.f;
+  if (c < cols)
+    for (int r = r0 + ty; r < r1; r += 8) acc += X[(int64_t)r * ld + c];
+  part[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += part[i][tx];
+    atomicAdd(out + c, t);
+  }
+}
+
 inline dim3 grid_for(const GemmArgs& a, int splits) {
   return dim3((a.N + BN - 1) / BN, (a.M + BM - 1) / BM, splits);
 }
 
 }  // namespace
+
+void launch_colsum(const float* X, int64_t ld, int rows, int cols, float* out, cudaStream_t s) {
+  colsum_kernel<<<dim3((cols + 31) / 32, (rows + CS_ROWS - 1) / CS_ROWS), 256, 0, s>>>(X, ld, rows, cols, out);
+}
 
 void launch_gemm_nn_simt(const GemmArgs& a, cudaStream_t s) {
   gemm_simt_kernel<false, false, EPI_FWD><<<grid_for(a, 1), NT, 0, s>>>(a, a.K);

@@ -28,6 +28,8 @@ struct GemmArgs {
 void launch_gemm_nn_simt(const GemmArgs& a, cudaStream_t s);
 void launch_gemm_nt_simt(const GemmArgs& a, cudaStream_t s);
 void launch_gemm_tn_simt(const GemmArgs& a, cudaStream_t s);
+// out[cols] += column sums of X[rows, cols] (bias gradient when the wgrad GEMM runs on the tensor cores)
+void launch_colsum(const float* X, int64_t ld, int rows, int cols, float* out, cudaStream_t s);
 
 // tcgen05 / TMA path (gemm_tc.cu).  Returns false if the shape cannot be served (caller falls back to SIMT
 // *kernels of this library*, never to a CPU or a vendor library).
