@@ -137,6 +137,38 @@ def sigmoid(a):
     return 0.5 * (1.0 + np.tanh(0.5 * a))
 
 
+def tf32_round(x):
+    """cvt.rna.tf32.f32: round to nearest (ties away from zero) to a 10-bit mantissa, kept in an fp32 container."""
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    u = ((u + np.uint64(0x1000)) & np.uint64(0xFFFFE000)).astype(np.uint32)
+    return u.view(np.float32).astype(np.float64)
+
+
+def tc_served(M, N, K):
+    """Mirror of tc_supported() in vae_assoc_b200/csrc/gemm_tc.cu: which contractions run on tcgen05 kind::tf32
+    (row pitches / alignment always hold for the library's own buffers)."""
+    return M >= 32 and N >= 32 and K >= 32
+
+
+def tf32_plan(na, B):
+    """Where the CUDA tf32 path rounds (RNA) operands, for one dense modality at batch B -- the same producer-side
+    rules as build_ops() in vae_assoc_b200/csrc/api.cu: a tensor is rounded by its producer iff one of its consumers
+    is a tensor-core GEMM; tensor-core GEMMs read the tf32-rounded shadow of the weights, SIMT ones the master."""
+    ni, r1, r2, nz = na["n_input"], na["n_hidden_recog_1"], na["n_hidden_recog_2"], na["n_z"]
+    nh = 2 * nz
+    t = dict(
+        f_e1=tc_served(B, r1, ni), f_e2=tc_served(B, r2, r1), f_hd=tc_served(B, nh, r2),
+        f_d1=tc_served(B, r1, nz), f_d2=tc_served(B, r2, r1), f_o=tc_served(B, ni, r2),
+        w_o=tc_served(r2, ni, B), d_o=tc_served(B, r2, ni), w_d2=tc_served(r1, r2, B), d_d2=tc_served(B, r1, r2),
+        w_d1=tc_served(nz, r1, B), d_d1=tc_served(B, nz, r1), w_hd=tc_served(r2, nh, B), d_hd=tc_served(B, r2, nh),
+        w_e2=tc_served(r1, r2, B), d_e2=tc_served(B, r1, r2), w_e1=tc_served(ni, r1, B))
+    t.update(r_x=t["f_e1"] or t["w_e1"], r_h1=t["f_e2"] or t["w_e2"], r_h2=t["f_hd"] or t["w_hd"],
+             r_z=t["f_d1"] or t["w_d1"], r_g1=t["f_d2"] or t["w_d2"], r_g2=t["f_o"] or t["w_o"],
+             r_da=t["w_o"] or t["d_o"], r_dg2=t["w_d2"] or t["d_d2"], r_dg1=t["w_d1"] or t["d_d1"],
+             r_dhd=t["w_hd"] or t["d_hd"], r_dh2=t["w_e2"] or t["d_e2"], r_dh1=t["w_e1"])
+    return t
+
+
 # --------------------------------------------------------------------------------------
 # TF conv2d / conv2d_transpose (NHWC, filter [kh,kw,cin,cout]); semantics from TensorFlow's documented
 # padding rules (third-party, not vendored): SAME: out = ceil(in/s), pad_total = max((out-1)s+k-in,0),
@@ -222,12 +254,20 @@ def conv2d_transpose_bwd(y, w, s, padding, dout):
 # --------------------------------------------------------------------------------------
 # the model
 # --------------------------------------------------------------------------------------
+class _Never(dict):
+    def __missing__(self, key):
+        return False
+
+
+_NO_ROUNDING = _Never()
+
+
 class OracleAssocVAE(object):
     """Same constructor surface as the reference class (vae_assoc.py:26-27), numpy fp64 arithmetic."""
 
     def __init__(self, network_architectures, binary=True, transfer_fct="softplus", weights=1.0,
                  assoc_lambda=1.0, learning_rate=0.001, batch_size=100, params=None, seed=0,
-                 dtype=np.float64):
+                 dtype=np.float64, emulate_tf32=False):
         self.network_architectures = network_architectures
         self.assoc_lambda = assoc_lambda
         n = len(network_architectures)
@@ -239,6 +279,10 @@ class OracleAssocVAE(object):
         self.batch_size = batch_size
         self.n_z = network_architectures[0]["n_z"]                                               # :89
         self.dtype = dtype
+        # emulate_tf32: round operands to tf32 exactly where the CUDA tensor-core path does (dense modalities);
+        # products of tf32 numbers are exact in fp32, so this oracle then differs from the GPU only by fp32
+        # accumulation order -- it pins the tf32 path to ~1e-5 instead of the 2e-3 "tf32 vs exact" bound.
+        self.emulate_tf32 = emulate_tf32
         if params is None:
             params = init_params(network_architectures, seed)
         self.params = [[np.array(p, dtype=dtype) for p in ps] for ps in params]
@@ -246,6 +290,17 @@ class OracleAssocVAE(object):
         self.v = [[np.zeros_like(p) for p in ps] for ps in self.params]
         self.t = 0
         self.rng = np.random.RandomState(seed + 1)
+
+    # ---- tf32 emulation helpers ------------------------------------------------------
+    def _plan(self, m, B):
+        na = self.network_architectures[m]
+        if not self.emulate_tf32 or na["hidden_conv"]:
+            return _NO_ROUNDING
+        return tf32_plan(na, B)
+
+    @staticmethod
+    def _q(flag, a):
+        return tf32_round(a) if flag else a
 
     # ---- forward pieces -------------------------------------------------------------
     def encode(self, m, x):
@@ -261,10 +316,12 @@ class OracleAssocVAE(object):
             mu = h2 @ P[3] + P[4]                                                                # :217-218
             lv = h2 @ P[5] + P[6]                                                                # :219-221
             return mu, lv, dict(x2=x2, l05=l05, l1=l1, l2shape=l2.shape, h2=h2)
-        h1 = act(f, x @ P[0] + P[1])                                                             # :187-188
-        h2 = act(f, h1 @ P[2] + P[3])                                                            # :203-204
-        mu = h2 @ P[4] + P[5]
-        lv = h2 @ P[6] + P[7]
+        t = self._plan(m, x.shape[0])
+        x = self._q(t["r_x"], x)
+        h1 = self._q(t["r_h1"], act(f, x @ self._q(t["f_e1"], P[0]) + P[1]))                     # :187-188
+        h2 = self._q(t["r_h2"], act(f, h1 @ self._q(t["f_e2"], P[2]) + P[3]))                    # :203-204
+        mu = h2 @ self._q(t["f_hd"], P[4]) + P[5]
+        lv = h2 @ self._q(t["f_hd"], P[6]) + P[7]
         return mu, lv, dict(x=x, h1=h1, h2=h2)
 
     def decode(self, m, z):
@@ -283,9 +340,10 @@ class OracleAssocVAE(object):
             g2 = o4.reshape(o4.shape[0], -1)                                                     # :278
             a = g2 @ P[15] + P[16]                                                               # :287-291
             return sigmoid(a), dict(z2=z2, o1=o1, o2=o2, o3=o3, o4=o4, g2=g2)
-        g1 = act(f, z @ P[8] + P[9])                                                             # :257-260
-        g2 = act(f, g1 @ P[10] + P[11])                                                          # :280-283
-        a = g2 @ P[12] + P[13]
+        t = self._plan(m, z.shape[0])
+        g1 = self._q(t["r_g1"], act(f, z @ self._q(t["f_d1"], P[8]) + P[9]))                     # :257-260
+        g2 = self._q(t["r_g2"], act(f, g1 @ self._q(t["f_d2"], P[10]) + P[11]))                  # :280-283
+        a = g2 @ self._q(t["f_o"], P[12]) + P[13]
         xh = sigmoid(a) if self.binary[m] else a                                                 # :285-303
         return xh, dict(z=z, g1=g1, g2=g2)
 
@@ -295,6 +353,7 @@ class OracleAssocVAE(object):
         for m in range(len(self.network_architectures)):
             mu, lv, ec = self.encode(m, np.asarray(X[m], dtype=self.dtype))
             z = mu + np.sqrt(np.exp(lv)) * eps                                                   # :102-103
+            z = self._q(self._plan(m, z.shape[0])["r_z"], z)
             xh, dc = self.decode(m, z)
             out["z_means"].append(mu); out["z_log_sigma_sqs"].append(lv); out["z_array"].append(z)
             out["x_reconstr_means"].append(xh); out["enc"].append(ec); out["dec"].append(dc)
@@ -311,6 +370,7 @@ class OracleAssocVAE(object):
         rec, lat, costs = [], [], []
         for m in range(M):
             x = np.asarray(X[m], dtype=self.dtype)
+            x = self._q(self._plan(m, x.shape[0])["r_x"], x)      # the loss kernel reads the staged copy of x
             xh, mu, lv = fw["x_reconstr_means"][m], fw["z_means"][m], fw["z_log_sigma_sqs"][m]
             if self.binary[m]:
                 r = -np.sum(x * np.log(CE_EPS + xh) + (1 - x) * np.log(CE_EPS + 1 - xh), 1)      # :321-324  [B]
@@ -350,7 +410,8 @@ class OracleAssocVAE(object):
         # decoders
         for m in range(M):
             P, G, w = self.params[m], grads[m], self.weights[m]
-            x, xh, dc = X[m], fw["x_reconstr_means"][m], fw["dec"][m]
+            t = self._plan(m, B)
+            x, xh, dc = self._q(t["r_x"], X[m]), fw["x_reconstr_means"][m], fw["dec"][m]
             if self.binary[m]:
                 da = (w / Bg) * (-x / (CE_EPS + xh) + (1 - x) / (CE_EPS + 1 - xh)) * xh * (1 - xh)
             else:
@@ -368,12 +429,13 @@ class OracleAssocVAE(object):
                 G[8] = d.sum((0, 1, 2)); d, G[7] = conv2d_transpose_bwd(dc["z2"], P[7], 1, "VALID", d)
                 dz = d.reshape(B, self.n_z)
             else:
+                da = self._q(t["r_da"], da)
                 G[12] = dc["g2"].T @ da; G[13] = da.sum(0)
-                d = (da @ P[12].T) * act_grad_from_output(f, dc["g2"])
+                d = self._q(t["r_dg2"], (da @ self._q(t["d_o"], P[12]).T) * act_grad_from_output(f, dc["g2"]))
                 G[10] = dc["g1"].T @ d; G[11] = d.sum(0)
-                d = (d @ P[10].T) * act_grad_from_output(f, dc["g1"])
+                d = self._q(t["r_dg1"], (d @ self._q(t["d_d2"], P[10]).T) * act_grad_from_output(f, dc["g1"]))
                 G[8] = dc["z"].T @ d; G[9] = d.sum(0)
-                dz = d @ P[8].T
+                dz = d @ self._q(t["d_d1"], P[8]).T
             dz_list.append(dz)
         # latent: reparameterisation + prior KL + association KL (SURVEY 3.2 analytic gradients)
         dmu = [None] * M
@@ -401,11 +463,14 @@ class OracleAssocVAE(object):
                 d, G[1] = conv2d_bwd(ec["l05"], P[1], 2, "SAME", d)
                 _, G[0] = conv2d_bwd(ec["x2"], P[0], 2, "SAME", d)
             else:
-                G[4] = ec["h2"].T @ dmu[m]; G[5] = dmu[m].sum(0)
-                G[6] = ec["h2"].T @ dlv[m]; G[7] = dlv[m].sum(0)
-                d = (dmu[m] @ P[4].T + dlv[m] @ P[6].T) * act_grad_from_output(f, ec["h2"])
+                t = self._plan(m, B)
+                dm_, dl_ = self._q(t["r_dhd"], dmu[m]), self._q(t["r_dhd"], dlv[m])
+                G[4] = ec["h2"].T @ dm_; G[5] = dm_.sum(0)
+                G[6] = ec["h2"].T @ dl_; G[7] = dl_.sum(0)
+                d = (dm_ @ self._q(t["d_hd"], P[4]).T + dl_ @ self._q(t["d_hd"], P[6]).T) * act_grad_from_output(f, ec["h2"])
+                d = self._q(t["r_dh2"], d)
                 G[2] = ec["h1"].T @ d; G[3] = d.sum(0)
-                d = (d @ P[2].T) * act_grad_from_output(f, ec["h1"])
+                d = self._q(t["r_dh1"], (d @ self._q(t["d_e2"], P[2]).T) * act_grad_from_output(f, ec["h1"]))
                 G[0] = ec["x"].T @ d; G[1] = d.sum(0)
         probes = dict(fw)
         probes.update(ls)

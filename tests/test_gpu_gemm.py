@@ -116,7 +116,9 @@ SHAPES = [(256, 160, 96), (128, 128, 32), (100, 147, 200), (8192, 500, 784), (33
 @pytest.mark.parametrize("M,N,K", SHAPES)
 def test_forward_nn(model, use_tc, M, N, K):
     for a in (ACT_NONE, ACT_RELU, ACT_SIGMOID):
-        assert run(model, NN, use_tc, M, N, K, seed=M + N + K + a, a=a) < 5e-6
+        # sigmoid output is O(1) whatever the pre-activation: its error is the ABSOLUTE fp32 accumulation error of a
+        # K-term sum (~|sum| sqrt(K) 2^-24), not a relative one
+        assert run(model, NN, use_tc, M, N, K, seed=M + N + K + a, a=a) < (5e-5 if a == ACT_SIGMOID else 5e-6)
 
 
 @pytest.mark.parametrize("use_tc", [0, 1])
