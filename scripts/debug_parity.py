@@ -10,13 +10,15 @@ def rel(a, b):
     return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
 
 precision = sys.argv[1] if len(sys.argv) > 1 else "fp32"
+fct = os.environ.get("FCT", "relu")
+emul = os.environ.get("EMUL", "0") == "1"
 for batch in [int(x) for x in (sys.argv[2:] or ["100", "8192"])]:
     archs = vo.reference_archs(4)
-    model = va.AssocVariationalAutoEncoder(archs, [True, False], transfer_fct="relu", weights=[50, 1], assoc_lambda=8,
+    model = va.AssocVariationalAutoEncoder(archs, [True, False], transfer_fct=fct, weights=[50, 1], assoc_lambda=8,
                                            learning_rate=1e-3, batch_size=batch, precision=precision, seed=5)
     params = model.get_params()
     per_mod = [[p.astype(np.float64) for p in params[:14]], [p.astype(np.float64) for p in params[14:]]]
-    oracle = vo.OracleAssocVAE(archs, [True, False], "relu", [50., 1.], 8.0, 1e-3, batch, params=per_mod)
+    oracle = vo.OracleAssocVAE(archs, [True, False], fct, [50., 1.], 8.0, 1e-3, batch, params=per_mod, emulate_tf32=emul)
     xs = model.synth_batch(0, batch)
     X = [x.cpu().numpy() for x in xs]
     eps = philox.eps_rows(5, 0, 0, batch, 4).astype(np.float32)

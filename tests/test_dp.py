@@ -1,0 +1,118 @@
+"""Data parallelism (new in this build; the reference is single-process).
+
+CPU (gloo, world_size 2): the host-side DP logic -- row sharding, the 1/B_global scaling rule of SURVEY.md 8e, the
+global-row Philox addressing of eps and of the synthetic stream, all-reduce(SUM) of flat gradients + cost slot --
+with the ORACLE as the compute (test infrastructure), against the single-process oracle.
+GPU (NCCL, needs >= 2 B200s: `gpurun --gpus 2 -- pytest -m gpu tests/test_dp.py`): the CUDA path with its in-library
+NCCL all-reduce against the single-GPU CUDA path at the same global batch."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from oracle import make_golden, philox, synth
+from oracle import vae_assoc_oracle as vo
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _gloo_worker(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    archs = make_golden.tiny_archs()
+    Bg, B = 8, 8 // world
+    row0 = rank * B
+    o = vo.OracleAssocVAE(archs, [True, False], "relu", [50.0, 1.0], 8.0, 1e-3, B, seed=4)
+    costs = []
+    for t in range(3):
+        X = synth.synth_batch(archs, [True, False], 7, 1, t * Bg + row0, B)      # this rank's rows of the global stream
+        eps = philox.eps_rows(9, t, row0, B, archs[0]["n_z"])                    # addressed by GLOBAL row
+        c, g, _ = o.loss_and_grads(X, eps, global_batch=Bg)
+        flat = torch.tensor(np.concatenate([x.ravel() for gs in g for x in gs] + [np.array([c])]))
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)                               # grads + cost slot in one buffer
+        flat = flat.numpy()
+        costs.append(flat[-1])
+        k, gsum = 0, []
+        for gs in g:
+            row = []
+            for x in gs:
+                row.append(flat[k:k + x.size].reshape(x.shape)); k += x.size
+            gsum.append(row)
+        o.adam_step(gsum)
+    if rank == 0:
+        np.savez(out, costs=np.array(costs), **{"p%d" % i: p for i, p in enumerate(p for ps in o.params for p in ps)})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_dp_logic_gloo_world2(tmp_path):
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "dp.npz")
+    mp.spawn(_gloo_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = np.load(out)
+    archs = make_golden.tiny_archs()
+    o = vo.OracleAssocVAE(archs, [True, False], "relu", [50.0, 1.0], 8.0, 1e-3, 8, seed=4)
+    costs = []
+    for t in range(3):
+        X = synth.synth_batch(archs, [True, False], 7, 1, t * 8, 8)
+        costs.append(o.partial_fit(X, philox.eps_rows(9, t, 0, 8, archs[0]["n_z"])))
+    np.testing.assert_allclose(got["costs"], costs, rtol=1e-12)
+    for i, p in enumerate(p for ps in o.params for p in ps):
+        np.testing.assert_allclose(got["p%d" % i], p, rtol=1e-9, atol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def _nccl_worker(rank, world, port, out, precision):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from vae_assoc_b200 import vae_assoc
+    archs = vo.reference_archs(4)
+    Bg = 256
+    B = Bg // world
+    model = vae_assoc.AssocVariationalAutoEncoder(archs, [True, False], transfer_fct="relu", weights=[50, 1],
+                                                  assoc_lambda=8, learning_rate=1e-3, batch_size=B, precision=precision,
+                                                  seed=0, eps_seed=5, global_batch=Bg, global_row0=rank * B)
+    model.init_data_parallel()
+    costs = []
+    for t in range(4):
+        xs = model.synth_batch(t * Bg + rank * B, B)
+        costs.append(float(model.partial_fit(xs)))          # Philox eps addressed by global row and step
+    params = model.get_params()
+    if rank == 0:
+        np.savez(out, costs=np.array(costs), **{"p%d" % i: p for i, p in enumerate(params)})
+    dist.barrier()
+    model.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_dp_nccl_matches_single_gpu(tmp_path, precision):
+    import torch
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    from vae_assoc_b200 import build, vae_assoc
+    build.build(verbose=False)
+    out = str(tmp_path / "dp.npz")
+    mp.spawn(_nccl_worker, args=(2, _free_port(), out, precision), nprocs=2, join=True)
+    got = np.load(out)
+    archs = vo.reference_archs(4)
+    model = vae_assoc.AssocVariationalAutoEncoder(archs, [True, False], transfer_fct="relu", weights=[50, 1],
+                                                  assoc_lambda=8, learning_rate=1e-3, batch_size=256, precision=precision,
+                                                  seed=0, eps_seed=5)
+    costs = [float(model.partial_fit(model.synth_batch(t * 256, 256))) for t in range(4)]
+    # identical up to the summation order of the batch reduction (2 shards + all-reduce vs one split-K kernel)
+    np.testing.assert_allclose(got["costs"], costs, rtol=2e-5)
+    for i, p in enumerate(model.get_params()):
+        d = np.linalg.norm(got["p%d" % i].astype(np.float64) - p) / max(np.linalg.norm(p), 1e-30)
+        assert d < 1e-4, (i, d)
+    model.close()

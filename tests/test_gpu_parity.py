@@ -126,12 +126,14 @@ def check_step(model, oracle, X, eps, tol, grads=True, grad_tol=None):
 def test_gradient_step_reference_config(va, f, precision, batch):
     """One gradient step at the reference architecture: cost, the probe tensors of vae_assoc.py:545-571 and all 28
     gradients.  fp32 path vs the exact fp64 oracle: 1e-4.  tf32 path vs the oracle that rounds operands at the same
-    points (so both see the same relu masks): 1e-4 as well -- the kernels themselves add only fp32 accumulation
-    noise.  (At batch 1 nothing is tensor-core sized, so tf32 == fp32 there.)"""
+    points (so both see the same relu masks): 5e-4 -- the kernels add only fp32 accumulation noise, but a 1-ulp fp32
+    difference moves ~1e-3 of the re-rounded activations by one tf32 ulp (2^-10), which shows as ~2e-5..2e-4 in the
+    max norm (measured); the same comparison against the EXACT oracle gives 5e-4..3e-2.  (At batch 1 nothing is
+    tensor-core sized, so tf32 == fp32 there.)"""
     archs = vo.reference_archs(4)
     model, oracle = make_pair(va, archs, batch, f, precision, seed=batch)
     X, eps = inputs(archs, batch, seed=batch)
-    check_step(model, oracle, X, eps, tol=1e-4)
+    check_step(model, oracle, X, eps, tol=1e-4 if precision == "fp32" else 5e-4)
     model.close()
 
 
@@ -197,10 +199,11 @@ def test_large_batch(va, f, precision):
     c_ref, g_ref, _ = oracle.loss_and_grads(X, eps)
     assert abs(cost - c_ref) <= 1e-4 * abs(c_ref)
     for g, r, n in zip(model.get_grads(), [g for gs in g_ref for g in gs], model.variable_roles()):
+        tol = 1e-4 if precision == "fp32" else 5e-4
         if f == "softplus":
-            assert rel(g, r) < 1e-4, (n, rel(g, r))
+            assert rel(g, r) < tol, (n, rel(g, r))
         else:
-            assert rel_l2(g, r) < 1e-4, (n, rel_l2(g, r))
+            assert rel_l2(g, r) < tol, (n, rel_l2(g, r))
             assert rel(g, r) < 5e-3, (n, rel(g, r))
     model.close()
 
