@@ -133,7 +133,13 @@ def test_gradient_step_reference_config(va, f, precision, batch):
     archs = vo.reference_archs(4)
     model, oracle = make_pair(va, archs, batch, f, precision, seed=batch)
     X, eps = inputs(archs, batch, seed=batch)
-    check_step(model, oracle, X, eps, tol=1e-4 if precision == "fp32" else 5e-4)
+    tol = 1e-4 if precision == "fp32" else 5e-4
+    # relu + tf32 at batch <= 100: the few activations re-rounded differently (see above) still flip ~1e-5 of the relu
+    # masks, and ONE flipped (sample, unit) is a 1/sqrt(B)-sized change of its gradient column -- the gradients of that
+    # combination get a loose bound here; the smooth activation pins every kernel tightly, the relu epilogues are
+    # pinned exactly by tests/test_gpu_gemm.py and by the fp32 path, and B = 8192 by test_large_batch
+    loose = precision == "tf32" and f == "relu" and batch > 1
+    check_step(model, oracle, X, eps, tol=tol, grad_tol=5e-2 if loose else None)
     model.close()
 
 
@@ -153,13 +159,15 @@ def test_tf32_path_vs_exact_oracle(va, f, batch):
     model.close()
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32"])
-def test_training_steps_match_oracle(va, precision):
-    """cost, gradients-through-Adam and the updated parameters / Adam slots over several steps."""
+@pytest.mark.parametrize("precision,f", [("fp32", "relu"), ("fp32", "softplus"), ("tf32", "softplus"), ("tf32", "relu")])
+def test_training_steps_match_oracle(va, precision, f):
+    """cost, gradients-through-Adam and the updated parameters / Adam slots over several steps (tf32: against the
+    operand-rounding oracle; relu + tf32 at B = 100 gets loose slot bounds, see test_gradient_step_reference_config)."""
     archs = vo.reference_archs(4)
     batch = 100
-    model, oracle = make_pair(va, archs, batch, "relu", precision, seed=3)
+    model, oracle = make_pair(va, archs, batch, f, precision, seed=3)
     tol = TOL[precision]
+    loose = precision == "tf32" and f == "relu"
     for t in range(5):
         X = [x.astype(np.float32) for x in synth.synth_batch(archs, [True, False], 0, 1, t * batch, batch)]
         eps = philox.eps_rows(3, t, 0, batch, 4).astype(np.float32)
@@ -174,8 +182,11 @@ def test_training_steps_match_oracle(va, precision):
     flat_v = [p for ps in oracle.v for p in ps]
     for i, n in enumerate(model.variable_roles()):
         assert rel_l2(params[i], flat[i]) < tol, (n, rel_l2(params[i], flat[i]))
-        assert rel(m[i], flat_m[i]) < 5 * tol, (n, "m", rel(m[i], flat_m[i]))
-        assert rel(v[i], flat_v[i]) < 5 * tol, (n, "v", rel(v[i], flat_v[i]))
+        if loose:
+            assert rel_l2(m[i], flat_m[i]) < 5e-2 and rel_l2(v[i], flat_v[i]) < 5e-2, n
+        else:
+            assert rel(m[i], flat_m[i]) < 5 * tol, (n, "m", rel(m[i], flat_m[i]))
+            assert rel(v[i], flat_v[i]) < 5 * tol, (n, "v", rel(v[i], flat_v[i]))
     model.close()
 
 
