@@ -178,7 +178,8 @@ int vaeassoc_profile_step(vaeassoc_handle h, const float* const* x_dev, const in
 
 /* test hook: run ONE dense-layer contraction of the library on caller buffers (device pointers) and synchronise.
  * kind 0: C = act(A[M,K] B[K,N] + bias)   1: C = (A[M,K] B[N,K]^T) * act'(aux)   2: C += A[K,M]^T B[K,N],
- * bias_grad += colsum(B).  use_tc selects the tcgen05 kernel (fails if the shape is not served) or the SIMT one. */
+ * bias_grad += colsum(B).  use_tc = 1: the tcgen05 kernel (fails if the shape is not served); 0: the fp32 kernel the
+ * library would pick (skinny HBM-bound kernel when one extent <= 16, else the tiled SIMT kernel); 2: tiled SIMT. */
 int vaeassoc_debug_gemm(vaeassoc_handle h, int kind, int use_tc, int M, int N, int K, const float* A, int64_t lda,
                         const float* B, int64_t ldb, float* C, int64_t ldc, const float* bias, float* bias_grad,
                         const float* aux, int64_t ldaux, int act, int round_out);

@@ -140,3 +140,19 @@ def test_tc_unpadded_leading_dimension_with_slack(model):
     assert run(model, NN, 1, 300, 147, 200, seed=1, pad=1) < 5e-6
     assert run(model, NT, 1, 300, 200, 147, seed=2, pad=1) < 5e-6
     assert run(model, TN, 1, 147, 200, 300, seed=3, pad=1) < 5e-6
+
+
+SKINNY = [(8192, 8, 500), (100, 8, 200), (777, 6, 333), (8192, 500, 4), (100, 200, 4), (65, 147, 3), (300, 16, 64)]
+
+
+@pytest.mark.parametrize("M,N,K", SKINNY)
+def test_skinny_forward_and_dgrad(model, M, N, K):
+    """the n_z-wide layers (heads N = 2 n_z, decoder input K = n_z) on the HBM-bound skinny kernels"""
+    for a in (ACT_NONE, ACT_RELU):
+        assert run(model, NN, 0, M, N, K, seed=M + N + K + a, a=a) < 5e-6
+        assert run(model, NT, 0, M, N, K, seed=M + 2 * N + K + a, a=a) < 5e-6
+
+
+@pytest.mark.parametrize("M,N,K", [(4, 500, 8192), (500, 8, 8192), (3, 147, 65), (200, 6, 100), (16, 64, 300), (64, 16, 300)])
+def test_skinny_wgrad(model, M, N, K):
+    assert run(model, TN, 0, M, N, K, seed=M + N + 3 * K) < 5e-6

@@ -299,6 +299,11 @@ Op make_gemm(Ctx* c, const char* name, int m, int kind, GemmArgs a, int64_t w_of
     return op;
   }
   if (w_off >= 0) a.B = c->p + w_off;
+  if (skinny_supported(kind, a)) {
+    op.name += ".sk";
+    op.run = [kind, a](cudaStream_t s) { launch_gemm_skinny(kind, a, s); };
+    return op;
+  }
   switch (kind) {
     case KIND_NN: op.run = [a](cudaStream_t s) { launch_gemm_nn_simt(a, s); }; break;
     case KIND_NT: op.run = [a](cudaStream_t s) { launch_gemm_nt_simt(a, s); }; break;
@@ -1117,7 +1122,7 @@ int vaeassoc_debug_gemm(vaeassoc_handle h, int kind, int use_tc, int M, int N, i
   GemmArgs a;
   a.M = M; a.N = N; a.K = K; a.A = A; a.lda = lda; a.B = B; a.ldb = ldb; a.C = C; a.ldc = ldc; a.bias = bias;
   a.bias_grad = bias_grad; a.aux = aux; a.ldaux = ldaux; a.act = act; a.round_out = round_out;
-  if (use_tc) {
+  if (use_tc == 1) {
     if (!tc_supported(kind, a)) fail("shape not served by the tcgen05 path");
     char err[256] = {0};
     TcPlan* plan = tc_plan_create(kind, a, err, sizeof err);
@@ -1127,10 +1132,14 @@ int vaeassoc_debug_gemm(vaeassoc_handle h, int kind, int use_tc, int M, int N, i
     CUDA_OK(cudaStreamSynchronize(h->stream));
     tc_plan_destroy(plan);
   } else {
-    switch (kind) {
-      case KIND_NN: launch_gemm_nn_simt(a, h->stream); break;
-      case KIND_NT: launch_gemm_nt_simt(a, h->stream); break;
-      default: launch_gemm_tn_simt(a, h->stream); break;
+    if (use_tc == 0 && skinny_supported(kind, a)) {
+      launch_gemm_skinny(kind, a, h->stream);
+    } else {
+      switch (kind) {
+        case KIND_NN: launch_gemm_nn_simt(a, h->stream); break;
+        case KIND_NT: launch_gemm_nt_simt(a, h->stream); break;
+        default: launch_gemm_tn_simt(a, h->stream); break;
+      }
     }
     CUDA_OK(cudaStreamSynchronize(h->stream));
   }

@@ -31,6 +31,10 @@ void launch_gemm_tn_simt(const GemmArgs& a, cudaStream_t s);
 // out[cols] += column sums of X[rows, cols] (bias gradient when the wgrad GEMM runs on the tensor cores)
 void launch_colsum(const float* X, int64_t ld, int rows, int cols, float* out, cudaStream_t s);
 
+// HBM-bound kernels for contractions with one extent <= 16 (the n_z-wide heads / decoder input layer), gemm_skinny.cu
+bool skinny_supported(int kind /*0 NN,1 NT,2 TN*/, const GemmArgs& a);
+void launch_gemm_skinny(int kind, const GemmArgs& a, cudaStream_t s);
+
 // tcgen05 / TMA path (gemm_tc.cu).  Returns false if the shape cannot be served (caller falls back to SIMT
 // *kernels of this library*, never to a CPU or a vendor library).
 struct TcPlan;   // opaque: tensor maps + grid for one GEMM call site, built once at handle creation
