@@ -184,12 +184,17 @@ def main():
         return float(t.item())
 
     # ---- kernel-resident number: inputs already in HBM ------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                 # nvidia-smi needs ~1 s to produce its first line: start before the warm-up
     for k in range(args.warmup):
         model.partial_fit_async(pool[k % pool_n])
     barrier()
-    sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        t_wait = time.time()
+        while not sampler.lines and time.time() - t_wait < 3.0:
+            time.sleep(0.05)
+        sampler.lines.clear()           # keep only samples taken during the timed region
     l0 = model.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -199,6 +204,13 @@ def main():
     barrier()
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     launches = model.launch_count() - l0
+    if rank == 0 and ms_total < 400.0:
+        # keep the same work running until the 100 ms sampler has seen the region (these steps are not timed)
+        t_more = time.time()
+        while len(sampler.lines) < 3 and time.time() - t_more < 2.0:
+            for k in range(20):
+                model.partial_fit_async(pool[k % pool_n])
+            model.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     last_cost = float(model.last_cost())
     ms_step = ms_total / args.steps

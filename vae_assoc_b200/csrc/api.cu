@@ -131,6 +131,9 @@ struct vaeassoc_ctx {
   // schedules
   std::vector<Op> ops_fwd_enc, ops_latent_fwd, ops_fwd_dec, ops_loss, ops_bwd_dec, ops_latent_bwd, ops_bwd_enc;
   std::vector<std::vector<Op>> ops_enc_mod, ops_dec_mod;   // per-modality forward slices (encode / decode)
+  std::vector<std::vector<Op>> ops_loss_mod, ops_bwd_dec_mod, ops_bwd_enc_mod;   // per-modality: run concurrently
+  cudaStream_t side[VAEASSOC_MAX_MODALITIES - 1] = {nullptr, nullptr, nullptr};   // modality m > 0 runs on side[m-1]
+  cudaEvent_t ev_fork = nullptr, ev_join[VAEASSOC_MAX_MODALITIES - 1] = {nullptr, nullptr, nullptr};
   std::vector<TcPlan*> plans;
   // graphs
   cudaGraphExec_t graph_train = nullptr, graph_grad = nullptr, graph_a1 = nullptr, graph_a2 = nullptr,
@@ -349,6 +352,7 @@ void build_ops(Ctx* c) {
   c->ops_bwd_dec.clear(); c->ops_latent_bwd.clear(); c->ops_bwd_enc.clear();
   const int M = c->cfg.n_modalities;
   c->ops_enc_mod.assign(M, {}); c->ops_dec_mod.assign(M, {});
+  c->ops_loss_mod.assign(M, {}); c->ops_bwd_dec_mod.assign(M, {}); c->ops_bwd_enc_mod.assign(M, {});
   const int B = c->cfg.batch_size, nz = c->cfg.n_z;
   const int f = fwd_act(c);
   const bool tf32 = c->cfg.precision == VAEASSOC_TF32;
@@ -404,19 +408,21 @@ void build_ops(Ctx* c) {
     for (auto& op : enc) c->ops_fwd_enc.push_back(op);
     for (auto& op : dec) c->ops_fwd_dec.push_back(op);
 
-    auto& bd = c->ops_bwd_dec;
+    auto& bd = c->ops_bwd_dec_mod[m];
     bd.push_back(make_gemm(c, "wgrad_out", m, KIND_TN, w_o, -1, false));
     bd.push_back(make_gemm(c, "dgrad_out", m, KIND_NT, d_o, d.Vo, r_dg2));
     bd.push_back(make_gemm(c, "wgrad_dec2", m, KIND_TN, w_d2, -1, false));
     bd.push_back(make_gemm(c, "dgrad_dec2", m, KIND_NT, d_d2, d.V2, r_dg1));
     bd.push_back(make_gemm(c, "wgrad_dec1", m, KIND_TN, w_d1, -1, false));
     bd.push_back(make_gemm(c, "dgrad_dec1", m, KIND_NT, d_d1, d.V1, false));
-    auto& be = c->ops_bwd_enc;
+    auto& be = c->ops_bwd_enc_mod[m];
     be.push_back(make_gemm(c, "wgrad_heads", m, KIND_TN, w_hd, -1, false));
     be.push_back(make_gemm(c, "dgrad_heads", m, KIND_NT, d_hd, d.Wh, r_dh2));
     be.push_back(make_gemm(c, "wgrad_enc2", m, KIND_TN, w_e2, -1, false));
     be.push_back(make_gemm(c, "dgrad_enc2", m, KIND_NT, d_e2, d.W2, r_dh1));
     be.push_back(make_gemm(c, "wgrad_enc1", m, KIND_TN, w_e1, -1, false));
+    for (auto& o : bd) c->ops_bwd_dec.push_back(o);
+    for (auto& o : be) c->ops_bwd_enc.push_back(o);
 
     Op op; op.name = "recon_loss." + std::to_string(m);
     ReconArgs a;
@@ -429,6 +435,7 @@ void build_ops(Ctx* c) {
     op.bytes = 4.0 * 3 * B * d.ni;
     op.run = [a](cudaStream_t s) { launch_recon_loss(a, s); };
     c->ops_loss.push_back(op);
+    c->ops_loss_mod[m].push_back(op);
   }
   {
     Op op; op.name = "latent_fwd";
@@ -489,19 +496,45 @@ AdamArgs adam_args(Ctx* c) {
   return a;
 }
 
+// The modalities only meet in the latent kernels (shared eps, association KL): between those joins each modality's
+// chain of layers runs on its own stream (modality 0 on `s`, modality m on side[m-1]).  Under stream capture the
+// event edges become graph dependencies, so the replayed graph has one branch per modality; the small joint-modality
+// GEMMs (10 % of the FLOPs, latency-bound) then hide inside the image-modality ones.
+cudaStream_t mod_stream(Ctx* c, int m, cudaStream_t s) { return m == 0 ? s : c->side[m - 1]; }
+void fork_modalities(Ctx* c, cudaStream_t s) {
+  if (c->cfg.n_modalities < 2) return;
+  CUDA_OK(cudaEventRecord(c->ev_fork, s));
+  for (int m = 1; m < c->cfg.n_modalities; ++m) CUDA_OK(cudaStreamWaitEvent(c->side[m - 1], c->ev_fork, 0));
+}
+void join_modalities(Ctx* c, cudaStream_t s) {
+  for (int m = 1; m < c->cfg.n_modalities; ++m) {
+    CUDA_OK(cudaEventRecord(c->ev_join[m - 1], c->side[m - 1]));
+    CUDA_OK(cudaStreamWaitEvent(s, c->ev_join[m - 1], 0));
+  }
+}
+
 // segment A1: zero grads, forward, losses, decoder backward   (gradient bucket 0 complete at its end)
 void enqueue_a1(Ctx* c, cudaStream_t s) {
+  const int M = c->cfg.n_modalities;
   CUDA_OK(cudaMemsetAsync(c->g, 0, (size_t)(c->n_flat + 32) * sizeof(float), s));
-  run_ops(c, c->ops_fwd_enc, s);
+  fork_modalities(c, s);
+  for (int m = 0; m < M; ++m) run_ops(c, c->ops_enc_mod[m], mod_stream(c, m, s));
+  join_modalities(c, s);
   run_ops(c, c->ops_latent_fwd, s);
-  run_ops(c, c->ops_fwd_dec, s);
-  run_ops(c, c->ops_loss, s);
-  run_ops(c, c->ops_bwd_dec, s);
+  fork_modalities(c, s);
+  for (int m = 0; m < M; ++m) {
+    run_ops(c, c->ops_dec_mod[m], mod_stream(c, m, s));
+    run_ops(c, c->ops_loss_mod[m], mod_stream(c, m, s));
+    run_ops(c, c->ops_bwd_dec_mod[m], mod_stream(c, m, s));
+  }
+  join_modalities(c, s);
 }
 // segment A2: latent + encoder backward, cost finalize (bucket 1 + cost slot complete at its end)
 void enqueue_a2(Ctx* c, cudaStream_t s, int advance) {
   run_ops(c, c->ops_latent_bwd, s);
-  run_ops(c, c->ops_bwd_enc, s);
+  fork_modalities(c, s);
+  for (int m = 0; m < c->cfg.n_modalities; ++m) run_ops(c, c->ops_bwd_enc_mod[m], mod_stream(c, m, s));
+  join_modalities(c, s);
   launch_finalize(finalize_args(c, advance), s);
   c->launches += 1;
 }
@@ -709,6 +742,11 @@ int vaeassoc_create(const vaeassoc_config* cfg, vaeassoc_handle* out) {
       CUDA_OK(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
       CUDA_OK(cudaEventCreateWithFlags(&c->ev_consumed[i], cudaEventDisableTiming));
     }
+    for (int i = 0; i < VAEASSOC_MAX_MODALITIES - 1; ++i) {
+      CUDA_OK(cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
+      CUDA_OK(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
+    }
+    CUDA_OK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&c->ev_bucket, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming));
     build_layout(c);
@@ -737,6 +775,11 @@ int vaeassoc_destroy(vaeassoc_handle h) {
     if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
     if (h->ev_consumed[i]) cudaEventDestroy(h->ev_consumed[i]);
   }
+  for (int i = 0; i < VAEASSOC_MAX_MODALITIES - 1; ++i) {
+    if (h->side[i]) cudaStreamDestroy(h->side[i]);
+    if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+  }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_bucket) cudaEventDestroy(h->ev_bucket);
   if (h->ev_comm) cudaEventDestroy(h->ev_comm);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);

@@ -4,6 +4,8 @@
 // A 64x64 GEMM tile wastes 8-16x of its lanes on these; each kernel below instead streams the one large operand
 // exactly once with coalesced loads and keeps the skinny operand in registers / shared memory.  Algorithmic bytes
 // = 4 * (large operand + output); no tensor cores (intensity 2-4 FLOP/B).
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -25,11 +27,11 @@ __device__ __forceinline__ float epilogue(const GemmArgs& g, float v, int m, int
 // lanes stride K (coalesced reads of the A row), N partial sums per lane, shuffle reduce.
 template <bool B_T>
 __global__ void __launch_bounds__(256) skinny_out_kernel(GemmArgs g) {
-  extern __shared__ float sB[];                    // [K][N] (n fastest) whatever the global layout
-  const int N = g.N, K = g.K;
+  extern __shared__ float sB[];                    // [K][NP]: row stride NP = N|1 (odd) keeps the lane-strided reads conflict-free
+  const int N = g.N, K = g.K, NP = g.N | 1;
   for (int i = threadIdx.x; i < K * N; i += blockDim.x) {
     const int k = i / N, n = i - k * N;
-    sB[i] = B_T ? g.B[(int64_t)n * g.ldb + k] : g.B[(int64_t)k * g.ldb + n];
+    sB[k * NP + n] = B_T ? g.B[(int64_t)n * g.ldb + k] : g.B[(int64_t)k * g.ldb + n];
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -38,12 +40,20 @@ __global__ void __launch_bounds__(256) skinny_out_kernel(GemmArgs g) {
 #pragma unroll
     for (int n = 0; n < SK; ++n) acc[n] = 0.f;
     const float* __restrict__ a = g.A + (int64_t)m * g.lda;
-    for (int k = lane; k < K; k += 32) {
-      const float av = a[k];
-      const float* b = sB + k * N;
+    int k = lane;
+    for (; k + 96 < K; k += 128) {          // four independent 128-byte row segments in flight per warp
+      const float a0 = a[k], a1 = a[k + 32], a2 = a[k + 64], a3 = a[k + 96];
 #pragma unroll
       for (int n = 0; n < SK; ++n)
-        if (n < N) acc[n] = fmaf(av, b[n], acc[n]);
+        if (n < N)
+          acc[n] = fmaf(a3, sB[(k + 96) * NP + n],
+                        fmaf(a2, sB[(k + 64) * NP + n], fmaf(a1, sB[(k + 32) * NP + n], fmaf(a0, sB[k * NP + n], acc[n]))));
+    }
+    for (; k < K; k += 32) {
+      const float av = a[k];
+#pragma unroll
+      for (int n = 0; n < SK; ++n)
+        if (n < N) acc[n] = fmaf(av, sB[k * NP + n], acc[n]);
     }
 #pragma unroll
     for (int n = 0; n < SK; ++n)
@@ -56,18 +66,26 @@ __global__ void __launch_bounds__(256) skinny_out_kernel(GemmArgs g) {
   }
 }
 
-// ---- (b)/(d): C[M,N] = A[M, K<=16] . B ; one thread per output element, coalesced over n.
+// ---- (b)/(d): C[M,N] = A[M, K<=16] . B.  Thread <-> output column n with B[:, n] held in registers; the CTA walks
+// a chunk of rows, reading each A row (K floats, warp-uniform -> one broadcast transaction) and writing C coalesced.
+constexpr int IN_ROWS = 16;
 template <bool B_T>
-__global__ void __launch_bounds__(256) skinny_in_kernel(GemmArgs g) {
+__global__ void __launch_bounds__(128) skinny_in_kernel(GemmArgs g) {
   const int K = g.K;
-  const int64_t total = (int64_t)g.M * g.N;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int m = (int)(i / g.N), n = (int)(i - (int64_t)m * g.N);
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m0 = blockIdx.y * IN_ROWS, m1 = min(g.M, m0 + IN_ROWS);
+  if (n >= g.N) return;
+  float b[SK];
+#pragma unroll
+  for (int k = 0; k < SK; ++k)
+    b[k] = (k < K) ? (B_T ? __ldg(g.B + (int64_t)n * g.ldb + k) : __ldg(g.B + (int64_t)k * g.ldb + n)) : 0.f;
+#pragma unroll 4
+  for (int m = m0; m < m1; ++m) {
     const float* __restrict__ a = g.A + (int64_t)m * g.lda;
     float acc = 0.f;
 #pragma unroll
     for (int k = 0; k < SK; ++k)
-      if (k < K) acc = fmaf(a[k], B_T ? __ldg(g.B + (int64_t)n * g.ldb + k) : __ldg(g.B + (int64_t)k * g.ldb + n), acc);
+      if (k < K) acc = fmaf(__ldg(a + k), b[k], acc);
     g.C[(int64_t)m * g.ldc + n] = epilogue(g, acc, m, n);
   }
 }
@@ -75,7 +93,7 @@ __global__ void __launch_bounds__(256) skinny_in_kernel(GemmArgs g) {
 // ---- (e)/(f): wgrad C[M,N] += A[K,M]^T . B[K,N] with min(M,N) <= 16, K = batch.  The wide operand is streamed once
 // (thread per wide column, coalesced), the skinny operand's rows are broadcast from shared memory; each CTA reduces
 // ROWS batch rows and issues one fp32 RED per output element.  bias_grad += colsum(B).
-constexpr int ROWS = 128;
+constexpr int ROWS = 32;
 template <bool SKINNY_M>
 __global__ void __launch_bounds__(128) skinny_wgrad_kernel(GemmArgs g) {
   __shared__ float sS[ROWS][SK];
@@ -95,6 +113,7 @@ __global__ void __launch_bounds__(128) skinny_wgrad_kernel(GemmArgs g) {
   for (int s = 0; s < SK; ++s) acc[s] = 0.f;
   float colsum = 0.f;
   if (w < W) {
+#pragma unroll 8
     for (int r = r0; r < r1; ++r) {
       const float x = wide[(int64_t)r * ldw + w];
       colsum += x;
@@ -131,8 +150,8 @@ inline int cap_grid(int64_t blocks) {
 
 bool skinny_supported(int kind, const GemmArgs& a) {
   switch (kind) {
-    case 0: return (a.N <= SK && (int64_t)a.K * a.N * 4 <= 48 * 1024) || a.K <= SK;
-    case 1: return (a.N <= SK && (int64_t)a.K * a.N * 4 <= 48 * 1024) || a.K <= SK;
+    case 0:
+    case 1: return (a.N <= SK && (int64_t)a.K * (a.N | 1) * 4 <= 48 * 1024) || a.K <= SK;
     default: return a.M <= SK || a.N <= SK;
   }
 }
@@ -140,12 +159,13 @@ bool skinny_supported(int kind, const GemmArgs& a) {
 void launch_gemm_skinny(int kind, const GemmArgs& a, cudaStream_t s) {
   if (kind == 0 || kind == 1) {
     if (a.K <= SK) {
-      const int grid = cap_grid(((int64_t)a.M * a.N + 255) / 256);
-      if (kind == 0) skinny_in_kernel<false><<<grid, 256, 0, s>>>(a);
-      else skinny_in_kernel<true><<<grid, 256, 0, s>>>(a);
+      dim3 grid((a.N + 127) / 128, (a.M + IN_ROWS - 1) / IN_ROWS);
+      if (kind == 0) skinny_in_kernel<false><<<grid, 128, 0, s>>>(a);
+      else skinny_in_kernel<true><<<grid, 128, 0, s>>>(a);
     } else {
-      const int grid = cap_grid((a.M + 7) / 8);
-      const size_t smem = (size_t)a.K * a.N * 4;
+      // each CTA stages B in shared memory once and then walks rows: 4 CTAs per SM, grid-stride over the rows
+      const int grid = (int)std::min<int64_t>((a.M + 7) / 8, 4 * kNumSMs);
+      const size_t smem = (size_t)a.K * (a.N | 1) * 4;
       if (kind == 0) skinny_out_kernel<false><<<grid, 256, smem, s>>>(a);
       else skinny_out_kernel<true><<<grid, 256, smem, s>>>(a);
     }

@@ -238,15 +238,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
+    // TMEM -> registers (thread = output row, 32 columns) -> shared-memory transpose -> global, so that every
+    // global access of the epilogue (bias, stored activation for act', C) is a coalesced 128-byte row segment.
+    // The staging tile aliases pipeline stage 0: when tmem_full fires every TMA load has landed and every MMA has
+    // consumed its operands, so the stage buffers are dead.
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int row = m0 + q * 32 + lane;
     if (nkb > 0) {
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
     }
-    const bool row_ok = row < g.M;
-    float* crow = g.C + (int64_t)row * g.ldc;
-    const float* auxrow = (KIND == KIND_NT && g.aux) ? g.aux + (int64_t)row * g.ldaux : nullptr;
+    float* stg = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw))) + q * (32 * 33);
+    const int row0 = m0 + q * 32;
+    const int nrows = min(32, g.M - row0);  // warp-uniform
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t v[32];
@@ -256,46 +259,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0u;
       }
-      const int nb = n0 + c * 32;
-      if (!row_ok || nb >= g.N) continue;
-      const bool full = (nb + 32 <= g.N);
-      const bool vec_ok = full && ((g.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0);
-      if (KIND == KIND_TN) {
-        if (vec_ok) {
+      const int col = n0 + c * 32 + lane;
+      if (n0 + c * 32 >= g.N || nrows <= 0) continue;          // warp-uniform
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)      // split-K reduction: 128-bit fp32 RED into the flat gradient buffer
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow + nb + j), "r"(v[j]), "r"(v[j + 1]),
-                         "r"(v[j + 2]), "r"(v[j + 3]) : "memory");
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nb + j < g.N) atomicAdd(crow + nb + j, __uint_as_float(v[j]));
-        }
-      } else {
-        float o[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(v[j]);
-          const int n = nb + j;
-          if (KIND == KIND_NN) {
-            if (g.bias && n < g.N) x += __ldg(g.bias + n);
-            x = apply_act(g.act, x);
+      for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(v[j]);   // bank (lane + j) % 32: conflict-free
+      __syncwarp();
+      const bool col_ok = col < g.N;
+      const float bias_v = (KIND == KIND_NN && g.bias && col_ok) ? __ldg(g.bias + col) : 0.f;
+#pragma unroll 4
+      for (int r = 0; r < nrows; ++r) {
+        float x = stg[r * 33 + lane];
+        if (col_ok) {
+          const int64_t row = row0 + r;
+          if (KIND == KIND_TN) {
+            atomicAdd(g.C + row * g.ldc + col, x);            // split-K reduction: one 128-byte RED per warp
           } else {
-            if (auxrow && n < g.N) x *= act_grad_from_output(g.act, auxrow[n]);
+            if (KIND == KIND_NN) x = apply_act(g.act, x + bias_v);
+            else if (g.aux) x *= act_grad_from_output(g.act, g.aux[row * g.ldaux + col]);
+            if (g.round_out) x = round_tf32(x);
+            g.C[row * g.ldc + col] = x;
           }
-          if (g.round_out) x = round_tf32(x);
-          o[j] = x;
-        }
-        if (vec_ok) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(crow + nb + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nb + j < g.N) crow[nb + j] = o[j];
         }
       }
+      __syncwarp();
     }
   }
   tc_fence_before();

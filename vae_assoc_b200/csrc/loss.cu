@@ -260,21 +260,19 @@ __global__ void __launch_bounds__(256) recon_loss_kernel(ReconArgs a) {
 // finalize: fixed-order sum of the block partials -> scalars, local cost into the gradient buffer's spare slot
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) finalize_kernel(FinalizeArgs a) {
-  __shared__ float red[32];
   __shared__ float sums[kCostSlots];
-  // latent + assoc partials
-  for (int slot = 0; slot < kCostSlots; ++slot) {
+  // one warp per needed quantity (recon m, latent m, assoc): lanes stride the block partials, fixed-order shuffle sum
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int nq = 2 * a.n_mod + 1;
+  for (int qi = warp; qi < nq; qi += nwarps) {
+    const float* src; int nblk, slot;
+    if (qi == 2 * a.n_mod) { src = a.partials_latent; nblk = a.blocks_latent; slot = 8; }
+    else if (qi & 1) { src = a.partials_latent; nblk = a.blocks_latent; slot = qi; }
+    else { src = a.partials_recon[qi >> 1]; nblk = a.blocks_recon[qi >> 1]; slot = qi; }
     float acc = 0.f;
-    for (int b = threadIdx.x; b < a.blocks_latent; b += blockDim.x) acc += a.partials_latent[(int64_t)b * kCostSlots + slot];
-    const float t = block_sum(acc, red);
-    if (threadIdx.x == 0) sums[slot] = t;
-  }
-  for (int m = 0; m < a.n_mod; ++m) {
-    float acc = 0.f;
-    for (int b = threadIdx.x; b < a.blocks_recon[m]; b += blockDim.x)
-      acc += a.partials_recon[m][(int64_t)b * kCostSlots + 2 * m];
-    const float t = block_sum(acc, red);
-    if (threadIdx.x == 0) sums[2 * m] = t;
+    for (int b = lane; b < nblk; b += 32) acc += src[(int64_t)b * kCostSlots + slot];
+    acc = warp_sum(acc);
+    if (lane == 0) sums[slot] = acc;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
