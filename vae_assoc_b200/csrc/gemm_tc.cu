@@ -243,13 +243,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // The staging tile aliases pipeline stage 0: when tmem_full fires every TMA load has landed and every MMA has
     // consumed its operands, so the stage buffers are dead.
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    float* stg = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw))) + q * (32 * 33);
+    const int row0 = m0 + q * 32;
+    const int nrows = min(32, g.M - row0);  // warp-uniform
+    const bool use_aux = (KIND == KIND_NT) && g.aux != nullptr;
+    // act'(stored activation) does not depend on the accumulator: its 32 x 128-byte row segments per chunk are
+    // requested up front (32 independent loads in flight per lane), the first chunk while the main loop still runs
+    float auxv[32];
+    auto load_aux = [&](int c) {
+      const int col = n0 + c * 32 + lane;
+#pragma unroll
+      for (int r = 0; r < 32; ++r)
+        auxv[r] = (use_aux && r < nrows && col < g.N) ? g.aux[(int64_t)(row0 + r) * g.ldaux + col] : 1.0f;
+    };
+    if (use_aux) load_aux(0);
     if (nkb > 0) {
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
     }
-    float* stg = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw))) + q * (32 * 33);
-    const int row0 = m0 + q * 32;
-    const int nrows = min(32, g.M - row0);  // warp-uniform
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t v[32];
@@ -266,22 +277,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       __syncwarp();
       const bool col_ok = col < g.N;
       const float bias_v = (KIND == KIND_NN && g.bias && col_ok) ? __ldg(g.bias + col) : 0.f;
-#pragma unroll 4
-      for (int r = 0; r < nrows; ++r) {
-        float x = stg[r * 33 + lane];
-        if (col_ok) {
-          const int64_t row = row0 + r;
+#pragma unroll
+      for (int r = 0; r < 32; ++r) {
+        if (r < nrows && col_ok) {
+          float x = stg[r * 33 + lane];
+          float* dst = g.C + (int64_t)(row0 + r) * g.ldc + col;
           if (KIND == KIND_TN) {
-            atomicAdd(g.C + row * g.ldc + col, x);            // split-K reduction: one 128-byte RED per warp
+            atomicAdd(dst, x);                                  // split-K reduction: one 128-byte RED per warp
           } else {
             if (KIND == KIND_NN) x = apply_act(g.act, x + bias_v);
-            else if (g.aux) x *= act_grad_from_output(g.act, g.aux[row * g.ldaux + col]);
+            else if (use_aux) x *= act_grad_from_output(g.act, auxv[r]);
             if (g.round_out) x = round_tf32(x);
-            g.C[row * g.ldc + col] = x;
+            *dst = x;
           }
         }
       }
       __syncwarp();
+      if (use_aux && c + 1 < BN / 32) load_aux(c + 1);
     }
   }
   tc_fence_before();
