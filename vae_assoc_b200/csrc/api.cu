@@ -96,6 +96,17 @@ struct Mod {               // one modality (dense variant)
         *dh2 = nullptr, *dh1 = nullptr, *gstat = nullptr, *lat_loss = nullptr, *rec_loss = nullptr,
         *partials = nullptr;
   int recon_blocks = 0;
+  // ---- hidden_conv=True variant (vae_assoc.py:169-199,249-291; deconv.py) -------------------------------------
+  bool conv = false;
+  int s0 = 0, s1 = 0, s2 = 0, s3 = 0;        // encoder spatial sizes 28 -> 14 -> 7 -> 3
+  int e1 = 0, e2 = 0, e3 = 0;                // encoder depths r1, 2 r1, r2
+  int q1 = 0, q2 = 0, q3 = 0;                // decoder depths g1, g1/2, g2
+  int t1 = 0, t2 = 0, t3 = 0, t4 = 0;        // decoder spatial sizes 3 -> 7 -> 14 -> 28
+  int64_t C1 = 0, C2 = 0, C3 = 0, D1 = 0, d1 = 0, D2 = 0, d2 = 0, D3 = 0, d3 = 0, D4 = 0, d4 = 0;   // flat offsets (Wo/bo reuse Vo/co)
+  float *P1 = nullptr, *P2 = nullptr, *P3 = nullptr;             // encoder patch matrices (kept for the wgrads)
+  float *l05 = nullptr, *l1 = nullptr, *dl1 = nullptr, *dl05 = nullptr;
+  float *cols1 = nullptr, *cols2 = nullptr, *cols3 = nullptr, *cols4 = nullptr;   // deconv columns; reused as backward patches
+  float *o1 = nullptr, *o2 = nullptr, *o3 = nullptr, *dd3 = nullptr, *dd2 = nullptr, *dd1 = nullptr;
   // synthetic generator state
   float *P = nullptr, *inv_std = nullptr;
   uint32_t proj_seed_built = 0xFFFFFFFFu;
@@ -179,6 +190,23 @@ void add_tensor(Ctx* c, int m, const char* scope, int scope_entry, int var_idx, 
   c->tensors.push_back(t);
 }
 
+void add_named(Ctx* c, int m, const char* name, const char* role, int ndim, std::initializer_list<int> shape,
+               int64_t offset, int64_t rows, int64_t cols, int64_t ld) {
+  vaeassoc_tensor_info t;
+  memset(&t, 0, sizeof t);
+  snprintf(t.name, sizeof t.name, "%s", name);
+  snprintf(t.role, sizeof t.role, "%s", role);
+  t.modality = m; t.ndim = ndim;
+  int i = 0;
+  for (int s : shape) t.shape[i++] = s;
+  t.offset = offset; t.rows = rows; t.cols = cols; t.ld = ld;
+  c->tensors.push_back(t);
+}
+
+// TensorFlow SAME rule for stride-2, VALID otherwise (vae_assoc.py:174-197)
+inline int same_out(int n, int s) { return (n + s - 1) / s; }
+inline int same_pad_before(int n, int k, int s) { int o = same_out(n, s); int t = (o - 1) * s + k - n; return t > 0 ? t / 2 : 0; }
+
 void build_layout(Ctx* c) {
   const int M = c->cfg.n_modalities;
   const int nz = c->cfg.n_z;
@@ -188,16 +216,45 @@ void build_layout(Ctx* c) {
   for (int m = 0; m < M; ++m) {
     Mod& d = c->mods[m];
     d.cfg = c->cfg.mod[m];
-    if (d.cfg.hidden_conv) fail("modality %d: hidden_conv=True (conv/deconv variant) is not available in this build", m);
+    d.conv = d.cfg.hidden_conv != 0;
     d.ni = d.cfg.n_input; d.nip = (int)round_up(d.ni, 4);
     d.r1 = d.cfg.n_hidden_recog_1; d.r1p = (int)round_up(d.r1, 4);
     d.r2 = d.cfg.n_hidden_recog_2; d.r2p = (int)round_up(d.r2, 4);
     d.nz = nz; d.nh = 2 * nz; d.nhp = (int)round_up(d.nh, 4);
     if (d.ni <= 0 || d.r1 <= 0 || d.r2 <= 0) fail("modality %d: layer sizes must be positive", m);
+    if (d.conv) {
+      // encoder 28 -> 14 -> 7 (5x5, stride 2, SAME) -> 3 (5x5 VALID); decoder 1 -> 3 (3x3) -> 7 (5x5) -> 14 -> 28
+      if (!d.cfg.binary)
+        fail("modality %d: hidden_conv with a Gaussian output is ill-formed in the reference (vae_assoc.py:299-303 "
+             "multiplies [B, n_input] by [n_hidden_recog_2, n_input])", m);
+      d.s0 = (int)lround(sqrt((double)d.ni));
+      if (d.s0 * d.s0 != d.ni) fail("modality %d: hidden_conv needs a square image, n_input = %d", m, d.ni);
+      d.s1 = same_out(d.s0, 2); d.s2 = same_out(d.s1, 2); d.s3 = d.s2 - 5 + 1;
+      if (d.s3 < 1) fail("modality %d: image too small for the conv encoder", m);
+      d.e1 = d.r1; d.e2 = 2 * d.r1; d.e3 = d.r2;
+      d.q1 = d.cfg.n_hidden_gener_1; d.q2 = d.q1 / 2; d.q3 = d.cfg.n_hidden_gener_2;
+      if (d.q1 < 2 || d.q3 < 1) fail("modality %d: n_hidden_gener_1 >= 2 and n_hidden_gener_2 >= 1 required", m);
+      d.t1 = 3; d.t2 = d.t1 + 4; d.t3 = d.t2 * 2; d.t4 = d.t3 * 2;
+      if (d.t4 * d.t4 != d.ni)
+        fail("modality %d: the deconv chain of vae_assoc.py:251-277 produces %dx%d, n_input = %d", m, d.t4, d.t4, d.ni);
+      if ((d.e1 % 4) || (d.e2 % 4) || (d.e3 % 4) || (d.q1 % 4) || (d.q2 % 4) || (d.q3 % 4))
+        fail("modality %d: conv depths must be multiples of 4 (16-byte rows)", m);
+      // the flattened conv output plays the role of the second hidden layer for the heads
+      d.r2 = d.s3 * d.s3 * d.e3; d.r2p = d.r2;
+    }
   }
   // bucket 0: decoders, in the order their gradients complete (output layer first)
   for (int m = 0; m < M; ++m) {
     Mod& d = c->mods[m];
+    if (d.conv) {
+      const int nzp = (int)round_up(nz, 4);
+      d.Vo = take(d.ni, d.nip); d.co = take(1, d.nip);                       // Wo [n_input, n_input], bo   (:287-288)
+      d.D4 = take(25 * 1, d.q3);      d.d4 = take(1, 4);                     // [5,5,1,g2]      (:273-277)
+      d.D3 = take(25 * d.q3, d.q2);   d.d3 = take(1, d.q3);                  // [5,5,g2,g1/2]   (:268-272)
+      d.D2 = take(25 * d.q2, d.q1);   d.d2 = take(1, d.q2);                  // [5,5,g1/2,g1]   (:263-267)
+      d.D1 = take(9 * d.q1, nzp);     d.d1 = take(1, d.q1);                  // [3,3,g1,n_z]    (:251-255)
+      continue;
+    }
     d.Vo = take(d.r2, d.nip); d.co = take(1, d.nip);
     d.V2 = take(d.r1, d.r2p); d.c2 = take(1, d.r2p);
     d.V1 = take(d.nz, d.r1p); d.c1 = take(1, d.r1p);
@@ -207,6 +264,10 @@ void build_layout(Ctx* c) {
   for (int m = 0; m < M; ++m) {
     Mod& d = c->mods[m];
     d.Wh = take(d.r2, d.nhp); d.bh = take(1, d.nhp);
+    if (d.conv) {
+      d.C3 = take(25 * d.e2, d.e3); d.C2 = take(25 * d.e1, d.e2); d.C1 = take(25, d.e1);   // (:194-197,:179-183,:174-178)
+      continue;
+    }
     d.W2 = take(d.r1, d.r2p); d.b2 = take(1, d.r2p);
     d.W1 = take(d.ni, d.r1p); d.b1 = take(1, d.r1p);
   }
@@ -218,6 +279,32 @@ void build_layout(Ctx* c) {
   for (int m = 0; m < M; ++m) {
     const Mod& d = c->mods[m];
     const char* sc = default_scopes[m];
+    if (d.conv) {
+      // conv_2d weights are plain tf.Variables (vae_assoc.py:471-473); deconv2d ones are prettytensor variables
+      // 'weights' / 'bias' of layer scopes deconv2d, deconv2d_1, ... (deconv.py:92,110-114)
+      char nm[48];
+      const int nzp = (int)round_up(nz, 4);
+      add_tensor(c, m, sc, 0, 0, "C1", 4, {5, 5, 1, d.e1}, d.C1, 25, d.e1, d.e1);
+      add_tensor(c, m, sc, 0, 1, "C2", 4, {5, 5, d.e1, d.e2}, d.C2, 25 * d.e1, d.e2, d.e2);
+      add_tensor(c, m, sc, 0, 2, "C3", 4, {5, 5, d.e2, d.e3}, d.C3, 25 * d.e2, d.e3, d.e3);
+      add_tensor(c, m, sc, 0, 3, "Wmu", 2, {d.r2, nz}, d.Wh, d.r2, nz, d.nhp);
+      add_tensor(c, m, sc, 0, 4, "bmu", 1, {nz}, d.bh, 1, nz, d.nhp);
+      add_tensor(c, m, sc, 0, 5, "Wls", 2, {d.r2, nz}, d.Wh + nz, d.r2, nz, d.nhp);
+      add_tensor(c, m, sc, 0, 6, "bls", 1, {nz}, d.bh + nz, 1, nz, d.nhp);
+      const int64_t woff[4] = {d.D1, d.D2, d.D3, d.D4}, boff[4] = {d.d1, d.d2, d.d3, d.d4};
+      const int kk[4] = {3, 5, 5, 5}, od[4] = {d.q1, d.q2, d.q3, 1}, id[4] = {nz, d.q1, d.q2, d.q3};
+      const int64_t wld[4] = {nzp, d.q1, d.q2, d.q3};
+      const char* wr[4] = {"D1", "D2", "D3", "D4"}; const char* br[4] = {"d1", "d2", "d3", "d4"};
+      for (int l = 0; l < 4; ++l) {
+        if (l == 0) snprintf(nm, sizeof nm, "%s_1/deconv2d/weights", sc); else snprintf(nm, sizeof nm, "%s_1/deconv2d_%d/weights", sc, l);
+        add_named(c, m, nm, wr[l], 4, {kk[l], kk[l], od[l], id[l]}, woff[l], (int64_t)kk[l] * kk[l] * od[l], id[l], wld[l]);
+        if (l == 0) snprintf(nm, sizeof nm, "%s_1/deconv2d/bias", sc); else snprintf(nm, sizeof nm, "%s_1/deconv2d_%d/bias", sc, l);
+        add_named(c, m, nm, br[l], 1, {od[l]}, boff[l], 1, od[l], (int64_t)round_up(od[l], 4));
+      }
+      add_tensor(c, m, sc, 1, 0, "Wo", 2, {d.ni, d.ni}, d.Vo, d.ni, d.ni, d.nip);
+      add_tensor(c, m, sc, 1, 1, "bo", 1, {d.ni}, d.co, 1, d.ni, d.nip);
+      continue;
+    }
     add_tensor(c, m, sc, 0, 0, "W1", 2, {d.ni, d.r1}, d.W1, d.ni, d.r1, d.r1p);
     add_tensor(c, m, sc, 0, 1, "b1", 1, {d.r1}, d.b1, 1, d.r1, d.r1p);
     add_tensor(c, m, sc, 0, 2, "W2", 2, {d.r1, d.r2}, d.W2, d.r1, d.r2, d.r2p);
@@ -258,15 +345,28 @@ void alloc_buffers(Ctx* c) {
     d.xs = c->dalloc<float>(B * d.nip);
     d.h1 = c->dalloc<float>(B * d.r1p);  d.h2 = c->dalloc<float>(B * d.r2p);
     d.hd = c->dalloc<float>(B * d.nh);   d.z = c->dalloc<float>(B * nz);
-    d.g1 = c->dalloc<float>(B * d.r1p);  d.g2 = c->dalloc<float>(B * d.r2p);
+    d.g1 = c->dalloc<float>(B * d.r1p);  d.g2 = c->dalloc<float>(B * std::max(d.r2p, d.nip));   // conv: g2 = last deconv output [B, n_input]
     d.xh = c->dalloc<float>(B * d.nip);  d.da = c->dalloc<float>(B * d.nip);
-    d.dg2 = c->dalloc<float>(B * d.r2p); d.dg1 = c->dalloc<float>(B * d.r1p);
+    d.dg2 = c->dalloc<float>(B * std::max(d.r2p, d.nip)); d.dg1 = c->dalloc<float>(B * d.r1p);
     d.dz = c->dalloc<float>(B * nz);     d.dhd = c->dalloc<float>(B * d.nh);
     d.dh2 = c->dalloc<float>(B * d.r2p); d.dh1 = c->dalloc<float>(B * d.r1p);
     d.gstat = c->dalloc<float>(B * d.nh);
     d.lat_loss = c->dalloc<float>(B);    d.rec_loss = c->dalloc<float>(B);
     d.partials = c->dalloc<float>((int64_t)kMaxPartialBlocks * kCostSlots);
     d.P = c->dalloc<float>(4 * d.ni);    d.inv_std = c->dalloc<float>(d.ni);
+    if (d.conv) {
+      const int64_t n1 = B * d.s1 * d.s1, n2 = B * d.s2 * d.s2, n3 = B * d.s3 * d.s3;       // encoder rows
+      const int64_t m1 = B * d.t1 * d.t1, m2 = B * d.t2 * d.t2, m3 = B * d.t3 * d.t3;       // decoder rows (per input pixel)
+      d.P1 = c->dalloc<float>(n1 * 28);             d.l05 = c->dalloc<float>(n1 * d.e1);  d.dl05 = c->dalloc<float>(n1 * d.e1);
+      d.P2 = c->dalloc<float>(n2 * 25 * d.e1);      d.l1 = c->dalloc<float>(n2 * d.e2);   d.dl1 = c->dalloc<float>(n2 * d.e2);
+      d.P3 = c->dalloc<float>(n3 * 25 * d.e2);
+      d.cols1 = c->dalloc<float>(B * 9 * d.q1);     d.o1 = c->dalloc<float>(m1 * d.q1);   d.dd1 = c->dalloc<float>(m1 * d.q1);
+      d.cols2 = c->dalloc<float>(std::max(m1 * 25 * d.q2, n3 * 25 * d.e2));
+      d.o2 = c->dalloc<float>(m2 * d.q2);           d.dd2 = c->dalloc<float>(m2 * d.q2);
+      d.cols3 = c->dalloc<float>(std::max(m2 * 25 * d.q3, n2 * 25 * d.e1));
+      d.o3 = c->dalloc<float>(m3 * d.q3);           d.dd3 = c->dalloc<float>(m3 * d.q3);
+      d.cols4 = c->dalloc<float>(m3 * 28);
+    }
   }
 }
 
@@ -344,6 +444,118 @@ void destroy_graphs(Ctx* c) {
   }
 }
 
+// ---- hidden_conv=True modality: conv / deconv layers as im2col -> GEMM -> col2im (conv.cu) ------------------------
+Op make_im2col(const char* name, int m, const float* x, int B, int H, int C, int k, int s, int pb, int OH, float* out,
+               int64_t ldo) {
+  Op op; op.name = std::string(name) + "." + std::to_string(m);
+  Im2colArgs a;
+  a.x = x; a.B = B; a.H = H; a.W = H; a.C = C; a.k = k; a.s = s; a.pb = pb; a.OH = OH; a.OW = OH; a.out = out; a.ldo = ldo;
+  op.bytes = 4.0 * ((double)B * H * H * C + (double)B * OH * OH * k * k * C);
+  op.run = [a](cudaStream_t st) { launch_im2col(a, st); };
+  return op;
+}
+Op make_col2im(const char* name, int m, const float* cols, int64_t ldc, int B, int H, int C, int h, int k, int s, int pb,
+               const float* bias, int act, bool round_out, float* out) {
+  Op op; op.name = std::string(name) + "." + std::to_string(m);
+  Col2imArgs a;
+  a.cols = cols; a.ldc = ldc; a.B = B; a.H = H; a.W = H; a.C = C; a.h = h; a.w = h; a.k = k; a.s = s; a.pb = pb;
+  a.bias = bias; a.act = act; a.round_out = round_out ? 1 : 0; a.out = out;
+  op.bytes = 4.0 * ((double)B * H * H * C + (double)B * h * h * k * k * C);
+  op.run = [a](cudaStream_t st) { launch_col2im(a, st); };
+  return op;
+}
+Op make_colsum(const char* name, int m, const float* X, int64_t ld, int64_t rows, int cols, float* out) {
+  Op op; op.name = std::string(name) + "." + std::to_string(m);
+  op.bytes = 4.0 * rows * cols;
+  op.run = [=](cudaStream_t st) { launch_colsum(X, ld, (int)rows, cols, out, st); };
+  return op;
+}
+GemmArgs gemm_plain(int M, int N, int K, const float* A, int64_t lda, int64_t ldb, float* C, int64_t ldc) {
+  GemmArgs a;
+  a.M = M; a.N = N; a.K = K; a.A = A; a.lda = lda; a.ldb = ldb; a.C = C; a.ldc = ldc;
+  return a;
+}
+
+void build_ops_conv(Ctx* c, int m) {
+  Mod& d = c->mods[m];
+  const int B = c->cfg.batch_size, nz = c->cfg.n_z;
+  const bool tf32 = c->cfg.precision == VAEASSOC_TF32;
+  const bool R = tf32;                       // conv modality, tf32 mode: every GEMM operand is rounded by its producer
+  const int nzp = (int)round_up(nz, 4);
+  float* P = c->p; float* G = c->g;
+  const int n1 = B * d.s1 * d.s1, n2 = B * d.s2 * d.s2, n3 = B * d.s3 * d.s3;
+  const int m1 = B * d.t1 * d.t1, m2 = B * d.t2 * d.t2, m3 = B * d.t3 * d.t3;
+  const int pb_s = same_pad_before(d.s0, 5, 2);          // = 1 for 28 -> 14 and 14 -> 7, and for the SAME deconvs
+  auto& enc = c->ops_enc_mod[m];
+  auto& dec = c->ops_dec_mod[m];
+  auto& bd = c->ops_bwd_dec_mod[m];
+  auto& be = c->ops_bwd_enc_mod[m];
+  auto W = [&](GemmArgs a, int64_t off) { (void)off; return a; };
+  (void)W;
+
+  // ---------------- encoder: three bias-free linear convs (vae_assoc.py:172-199), then the heads --------------------
+  enc.push_back(make_im2col("enc_im2col1", m, d.xs, B, d.s0, 1, 5, 2, pb_s, d.s1, d.P1, 28));
+  enc.push_back(make_gemm(c, "enc_conv1", m, KIND_NN, gemm_plain(n1, d.e1, 25, d.P1, 28, d.e1, d.l05, d.e1), d.C1, R));
+  enc.push_back(make_im2col("enc_im2col2", m, d.l05, B, d.s1, d.e1, 5, 2, same_pad_before(d.s1, 5, 2), d.s2, d.P2, 25 * d.e1));
+  enc.push_back(make_gemm(c, "enc_conv2", m, KIND_NN, gemm_plain(n2, d.e2, 25 * d.e1, d.P2, 25 * d.e1, d.e2, d.l1, d.e2), d.C2, R));
+  enc.push_back(make_im2col("enc_im2col3", m, d.l1, B, d.s2, d.e2, 5, 1, 0, d.s3, d.P3, 25 * d.e2));
+  enc.push_back(make_gemm(c, "enc_conv3", m, KIND_NN, gemm_plain(n3, d.e3, 25 * d.e2, d.P3, 25 * d.e2, d.e3, d.h2, d.e3), d.C3, R));
+  enc.push_back(make_gemm(c, "fwd_heads", m, KIND_NN,
+                          gemm_fwd(B, d.nh, d.r2, d.h2, d.r2p, nullptr, d.nhp, P + d.bh, d.hd, d.nh, ACT_NONE), d.Wh, false));
+
+  // ---------------- decoder: four deconv2d + bias + SIGMOID (deconv_2d default, vae_assoc.py:491), dense 784x784 ----
+  dec.push_back(make_gemm(c, "dec_cols1", m, KIND_NT, gemm_plain(B, 9 * d.q1, nz, d.z, nz, nzp, d.cols1, 9 * d.q1), d.D1, false));
+  dec.push_back(make_col2im("dec_deconv1", m, d.cols1, 9 * d.q1, B, d.t1, d.q1, 1, 3, 1, 0, P + d.d1, ACT_SIGMOID, R, d.o1));
+  dec.push_back(make_gemm(c, "dec_cols2", m, KIND_NT, gemm_plain(m1, 25 * d.q2, d.q1, d.o1, d.q1, d.q1, d.cols2, 25 * d.q2), d.D2, false));
+  dec.push_back(make_col2im("dec_deconv2", m, d.cols2, 25 * d.q2, B, d.t2, d.q2, d.t1, 5, 1, 0, P + d.d2, ACT_SIGMOID, R, d.o2));
+  dec.push_back(make_gemm(c, "dec_cols3", m, KIND_NT, gemm_plain(m2, 25 * d.q3, d.q2, d.o2, d.q2, d.q2, d.cols3, 25 * d.q3), d.D3, false));
+  dec.push_back(make_col2im("dec_deconv3", m, d.cols3, 25 * d.q3, B, d.t3, d.q3, d.t2, 5, 2, pb_s, P + d.d3, ACT_SIGMOID, R, d.o3));
+  dec.push_back(make_gemm(c, "dec_cols4", m, KIND_NT, gemm_plain(m3, 25, d.q3, d.o3, d.q3, d.q3, d.cols4, 28), d.D4, false));
+  dec.push_back(make_col2im("dec_deconv4", m, d.cols4, 28, B, d.t4, 1, d.t3, 5, 2, pb_s, P + d.d4, ACT_SIGMOID, R, d.g2));
+  GemmArgs f_o = gemm_fwd(B, d.ni, d.ni, d.g2, d.nip, nullptr, d.nip, P + d.co, d.xh, d.nip, ACT_SIGMOID);
+  dec.push_back(make_gemm(c, "fwd_out", m, KIND_NN, f_o, d.Vo, false));
+
+  // ---------------- decoder backward ----------------------------------------------------------------------------------
+  bd.push_back(make_gemm(c, "wgrad_out", m, KIND_TN, gemm_wgrad(B, d.ni, d.ni, d.g2, d.nip, d.da, d.nip, G + d.Vo, d.nip, G + d.co), -1, false));
+  bd.push_back(make_gemm(c, "dgrad_out", m, KIND_NT, gemm_dgrad(B, d.ni, d.ni, d.da, d.nip, nullptr, d.nip, d.dg2, d.nip, d.g2, d.nip, ACT_SIGMOID), d.Vo, R));
+  // deconv4: d4 = dg2 [B,28,28,1]
+  bd.push_back(make_colsum("bgrad_deconv4", m, d.dg2, 1, (int64_t)B * d.ni, 1, G + d.d4));
+  bd.push_back(make_im2col("bwd_im2col4", m, d.dg2, B, d.t4, 1, 5, 2, pb_s, d.t3, d.cols4, 28));
+  bd.push_back(make_gemm(c, "wgrad_deconv4", m, KIND_TN, gemm_wgrad(m3, 25, d.q3, d.cols4, 28, d.o3, d.q3, G + d.D4, d.q3, nullptr), -1, false));
+  { GemmArgs a = gemm_plain(m3, d.q3, 25, d.cols4, 28, d.q3, d.dd3, d.q3); a.aux = d.o3; a.ldaux = d.q3; a.act = ACT_SIGMOID;
+    bd.push_back(make_gemm(c, "dgrad_deconv4", m, KIND_NN, a, d.D4, R)); }
+  bd.push_back(make_colsum("bgrad_deconv3", m, d.dd3, d.q3, m3, d.q3, G + d.d3));
+  bd.push_back(make_im2col("bwd_im2col3", m, d.dd3, B, d.t3, d.q3, 5, 2, pb_s, d.t2, d.cols3, 25 * d.q3));
+  bd.push_back(make_gemm(c, "wgrad_deconv3", m, KIND_TN, gemm_wgrad(m2, 25 * d.q3, d.q2, d.cols3, 25 * d.q3, d.o2, d.q2, G + d.D3, d.q2, nullptr), -1, false));
+  { GemmArgs a = gemm_plain(m2, d.q2, 25 * d.q3, d.cols3, 25 * d.q3, d.q2, d.dd2, d.q2); a.aux = d.o2; a.ldaux = d.q2; a.act = ACT_SIGMOID;
+    bd.push_back(make_gemm(c, "dgrad_deconv3", m, KIND_NN, a, d.D3, R)); }
+  bd.push_back(make_colsum("bgrad_deconv2", m, d.dd2, d.q2, m2, d.q2, G + d.d2));
+  bd.push_back(make_im2col("bwd_im2col2", m, d.dd2, B, d.t2, d.q2, 5, 1, 0, d.t1, d.cols2, 25 * d.q2));
+  bd.push_back(make_gemm(c, "wgrad_deconv2", m, KIND_TN, gemm_wgrad(m1, 25 * d.q2, d.q1, d.cols2, 25 * d.q2, d.o1, d.q1, G + d.D2, d.q1, nullptr), -1, false));
+  { GemmArgs a = gemm_plain(m1, d.q1, 25 * d.q2, d.cols2, 25 * d.q2, d.q1, d.dd1, d.q1); a.aux = d.o1; a.ldaux = d.q1; a.act = ACT_SIGMOID;
+    bd.push_back(make_gemm(c, "dgrad_deconv2", m, KIND_NN, a, d.D2, R)); }
+  bd.push_back(make_colsum("bgrad_deconv1", m, d.dd1, d.q1, m1, d.q1, G + d.d1));
+  // deconv1 maps the 1x1 latent "image" to 3x3: its patch matrix is dd1 itself, viewed [B, 9 g1]
+  bd.push_back(make_gemm(c, "wgrad_deconv1", m, KIND_TN, gemm_wgrad(B, 9 * d.q1, nz, d.dd1, 9 * d.q1, d.z, nz, G + d.D1, nzp, nullptr), -1, false));
+  bd.push_back(make_gemm(c, "dgrad_deconv1", m, KIND_NN, gemm_plain(B, nz, 9 * d.q1, d.dd1, 9 * d.q1, nzp, d.dz, nz), d.D1, false));
+
+  // ---------------- encoder backward (linear convs: no activation gradient, no bias) ---------------------------------
+  be.push_back(make_gemm(c, "wgrad_heads", m, KIND_TN, gemm_wgrad(B, d.r2, d.nh, d.h2, d.r2p, d.dhd, d.nh, G + d.Wh, d.nhp, G + d.bh), -1, false));
+  be.push_back(make_gemm(c, "dgrad_heads", m, KIND_NT, gemm_dgrad(B, d.r2, d.nh, d.dhd, d.nh, nullptr, d.nhp, d.dh2, d.r2p, nullptr, 0, ACT_NONE), d.Wh, R));
+  be.push_back(make_gemm(c, "wgrad_conv3", m, KIND_TN, gemm_wgrad(n3, 25 * d.e2, d.e3, d.P3, 25 * d.e2, d.dh2, d.e3, G + d.C3, d.e3, nullptr), -1, false));
+  be.push_back(make_gemm(c, "dcols_conv3", m, KIND_NT, gemm_plain(n3, 25 * d.e2, d.e3, d.dh2, d.e3, d.e3, d.cols2, 25 * d.e2), d.C3, false));
+  be.push_back(make_col2im("dgrad_conv3", m, d.cols2, 25 * d.e2, B, d.s2, d.e2, d.s3, 5, 1, 0, nullptr, ACT_NONE, R, d.dl1));
+  be.push_back(make_gemm(c, "wgrad_conv2", m, KIND_TN, gemm_wgrad(n2, 25 * d.e1, d.e2, d.P2, 25 * d.e1, d.dl1, d.e2, G + d.C2, d.e2, nullptr), -1, false));
+  be.push_back(make_gemm(c, "dcols_conv2", m, KIND_NT, gemm_plain(n2, 25 * d.e1, d.e2, d.dl1, d.e2, d.e2, d.cols3, 25 * d.e1), d.C2, false));
+  be.push_back(make_col2im("dgrad_conv2", m, d.cols3, 25 * d.e1, B, d.s1, d.e1, d.s2, 5, 2, same_pad_before(d.s1, 5, 2), nullptr, ACT_NONE, R, d.dl05));
+  be.push_back(make_gemm(c, "wgrad_conv1", m, KIND_TN, gemm_wgrad(n1, 25, d.e1, d.P1, 28, d.dl05, d.e1, G + d.C1, d.e1, nullptr), -1, false));
+
+  for (auto& op : enc) c->ops_fwd_enc.push_back(op);
+  for (auto& op : dec) c->ops_fwd_dec.push_back(op);
+  for (auto& op : bd) c->ops_bwd_dec.push_back(op);
+  for (auto& op : be) c->ops_bwd_enc.push_back(op);
+}
+
 void build_ops(Ctx* c) {
   destroy_graphs(c);
   for (TcPlan* p : c->plans) tc_plan_destroy(p);
@@ -360,8 +572,30 @@ void build_ops(Ctx* c) {
   float* P = c->p;   // biases are always read from the fp32 master
   bool round_z = false, round_dheads = false, round_x = false;
 
+  auto add_recon = [&](int m, bool round_da) {
+    Mod& d = c->mods[m];
+    Op op; op.name = "recon_loss." + std::to_string(m);
+    ReconArgs a;
+    a.batch = B; a.n_input = d.ni; a.binary = d.cfg.binary; a.slot = 2 * m;
+    a.scale = d.cfg.binary ? d.cfg.weight * inv_bg : d.cfg.weight;
+    a.x = d.xs; a.ldx = d.nip; a.xhat = d.xh; a.ldxh = d.nip; a.da = d.da; a.ldda = d.nip;
+    a.row_loss = d.rec_loss; a.partials = d.partials;
+    a.round_tf32 = round_da ? 1 : 0;
+    d.recon_blocks = (int)std::min<int64_t>(std::max<int64_t>((B + 7) / 8, 1), kMaxPartialBlocks);
+    op.bytes = 4.0 * 3 * B * d.ni;
+    op.run = [a](cudaStream_t s) { launch_recon_loss(a, s); };
+    c->ops_loss.push_back(op);
+    c->ops_loss_mod[m].push_back(op);
+  };
+
   for (int m = 0; m < M; ++m) {
     Mod& d = c->mods[m];
+    if (d.conv) {
+      build_ops_conv(c, m);
+      add_recon(m, tf32);
+      round_x = round_x || tf32;
+      continue;
+    }
     // argument sets of every dense contraction of this modality
     GemmArgs f_e1 = gemm_fwd(B, d.r1, d.ni, d.xs, d.nip, nullptr, d.r1p, P + d.b1, d.h1, d.r1p, f);
     GemmArgs f_e2 = gemm_fwd(B, d.r2, d.r1, d.h1, d.r1p, nullptr, d.r2p, P + d.b2, d.h2, d.r2p, f);
@@ -424,18 +658,7 @@ void build_ops(Ctx* c) {
     for (auto& o : bd) c->ops_bwd_dec.push_back(o);
     for (auto& o : be) c->ops_bwd_enc.push_back(o);
 
-    Op op; op.name = "recon_loss." + std::to_string(m);
-    ReconArgs a;
-    a.batch = B; a.n_input = d.ni; a.binary = d.cfg.binary; a.slot = 2 * m;
-    a.scale = d.cfg.binary ? d.cfg.weight * inv_bg : d.cfg.weight;
-    a.x = d.xs; a.ldx = d.nip; a.xhat = d.xh; a.ldxh = d.nip; a.da = d.da; a.ldda = d.nip;
-    a.row_loss = d.rec_loss; a.partials = d.partials;
-    a.round_tf32 = (tc(KIND_TN, w_o, -1) || tc(KIND_NT, d_o, d.Vo)) ? 1 : 0;
-    d.recon_blocks = (int)std::min<int64_t>(std::max<int64_t>((B + 7) / 8, 1), kMaxPartialBlocks);
-    op.bytes = 4.0 * 3 * B * d.ni;
-    op.run = [a](cudaStream_t s) { launch_recon_loss(a, s); };
-    c->ops_loss.push_back(op);
-    c->ops_loss_mod[m].push_back(op);
+    add_recon(m, tc(KIND_TN, w_o, -1) || tc(KIND_NT, d_o, d.Vo));
   }
   {
     Op op; op.name = "latent_fwd";

@@ -100,7 +100,9 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(GemmArgs g, int k_per_spl
       float v = acc[i][j];
       if (EPI == EPI_FWD) {
         if (g.bias) v += g.bias[gn];
-        v = apply_act(g.act, v);
+        // with `aux` the forward form computes a gradient: v * act'(aux) (deconv backward, conv.cu) instead of act(v)
+        if (g.aux) v *= act_grad_from_output(g.act, g.aux[(int64_t)gm * g.ldaux + gn]);
+        else v = apply_act(g.act, v);
         if (g.round_out) v = round_tf32(v);
         g.C[(int64_t)gm * g.ldc + gn] = v;
       } else if (EPI == EPI_DGRAD) {

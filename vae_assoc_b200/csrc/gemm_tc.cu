@@ -246,7 +246,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     float* stg = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw))) + q * (32 * 33);
     const int row0 = m0 + q * 32;
     const int nrows = min(32, g.M - row0);  // warp-uniform
-    const bool use_aux = (KIND == KIND_NT) && g.aux != nullptr;
+    const bool use_aux = (KIND != KIND_TN) && g.aux != nullptr;   // NN + aux: v * act'(aux) instead of act(v)
     // act'(stored activation) does not depend on the accumulator: its 32 x 128-byte row segments per chunk are
     // requested up front (32 independent loads in flight per lane), the first chunk while the main loop still runs
     float auxv[32];
@@ -285,8 +285,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (KIND == KIND_TN) {
             atomicAdd(dst, x);                                  // split-K reduction: one 128-byte RED per warp
           } else {
-            if (KIND == KIND_NN) x = apply_act(g.act, x + bias_v);
-            else if (use_aux) x *= act_grad_from_output(g.act, auxv[r]);
+            if (KIND == KIND_NN) x += bias_v;
+            if (use_aux) x *= act_grad_from_output(g.act, auxv[r]);
+            else if (KIND == KIND_NN) x = apply_act(g.act, x);
             if (g.round_out) x = round_tf32(x);
             *dst = x;
           }

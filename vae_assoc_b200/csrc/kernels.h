@@ -44,6 +44,29 @@ void launch_gemm_tc(const TcPlan* p, cudaStream_t s);
 bool tc_supported(int kind, const GemmArgs& a);
 
 // ------------------------------------------------------------------------------------------------------
+// conv / transposed-conv layers of the hidden_conv=True modality as im2col -> GEMM -> col2im (conv.cu)
+// ------------------------------------------------------------------------------------------------------
+struct Im2colArgs {
+  const float* x = nullptr;          // [B, H, W, C] dense NHWC
+  int B = 0, H = 0, W = 0, C = 0;
+  int k = 0, s = 1, pb = 0;          // kernel, stride, pad_before (TensorFlow SAME/VALID rule)
+  int OH = 0, OW = 0;                // conv output size = number of patch rows per image
+  float* out = nullptr; int64_t ldo = 0;   // [B*OH*OW, k*k*C] with row pitch ldo
+};
+void launch_im2col(const Im2colArgs& a, cudaStream_t s);
+
+struct Col2imArgs {
+  const float* cols = nullptr; int64_t ldc = 0;   // [B*h*w, k*k*C]
+  int B = 0, H = 0, W = 0, C = 0;    // output [B, H, W, C]
+  int h = 0, w = 0;                  // spatial size of the column rows
+  int k = 0, s = 1, pb = 0;
+  const float* bias = nullptr;       // [C] or null
+  int act = 0, round_out = 0;
+  float* out = nullptr;
+};
+void launch_col2im(const Col2imArgs& a, cudaStream_t s);
+
+// ------------------------------------------------------------------------------------------------------
 // input staging + noise
 // ------------------------------------------------------------------------------------------------------
 struct StageArgs {

@@ -148,8 +148,22 @@ class AssocVariationalAutoEncoder(object):
         """Reference initialisers (vae_assoc.py:185-215,257-300): Xavier-uniform weights, zero biases."""
         for i, ti in enumerate(self._tensors):
             shape = tuple(ti.shape[:ti.ndim])
+            role = ti.role.decode()
             if ti.ndim == 1:
-                w = np.zeros(shape, np.float32)
+                w = np.zeros(shape, np.float32)                      # every bias starts at zero (deconv.py:113 too)
+            elif role in ("C1", "C2", "C3"):
+                # conv_2d -> weight_variable: tf.truncated_normal(stddev=0.1) (vae_assoc.py:471-473,482)
+                w = self._rng.normal(size=shape)
+                bad = np.abs(w) > 2.0
+                while bad.any():
+                    w[bad] = self._rng.normal(size=int(bad.sum()))
+                    bad = np.abs(w) > 2.0
+                w = (0.1 * w).astype(np.float32)
+            elif role in ("D1", "D2", "D3", "D4"):
+                # deconv2d: prettytensor xavier_init(out*k*k, in*k*k), filter [k,k,out,in] (deconv.py:78-84)
+                k2 = shape[0] * shape[1]
+                lim = np.sqrt(6.0 / (shape[2] * k2 + shape[3] * k2))
+                w = self._rng.uniform(-lim, lim, size=shape).astype(np.float32)
             else:
                 w = xavier_init(shape[0], shape[1], rng=self._rng)
             self._set(L.PARAMS, i, w)
