@@ -13,6 +13,7 @@ def t(r, c): return torch.randn(r, c, device=dev)
 p = lambda x: C.c_void_p(x.data_ptr())
 cases = [("NN", 0, B, 500, 500, t(B, 500), 500, t(500, 500), 500, t(B, 500), 500),
          ("NN784", 0, B, 784, 500, t(B, 500), 500, t(500, 784), 784, t(B, 784), 784),
+         ("NNj", 0, B, 200, 147, t(B, 148), 148, t(147, 200), 200, t(B, 200), 200),
          ("NT", 1, B, 500, 500, t(B, 500), 500, t(500, 500), 500, t(B, 500), 500),
          ("TN", 2, 500, 500, B, t(B, 500), 500, t(B, 500), 500, t(500, 500), 500)]
 for name, kind, M, N, K, A, lda, Bm, ldb, Cm, ldc in cases:

@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <functional>
 #include <mutex>
 #include <stdexcept>
@@ -1396,6 +1397,7 @@ int vaeassoc_debug_gemm(vaeassoc_handle h, int kind, int use_tc, int M, int N, i
     launch_gemm_tc(plan, h->stream);
     if (kind == KIND_TN && bias_grad) launch_colsum(B, ldb, K, N, bias_grad, h->stream);
     CUDA_OK(cudaStreamSynchronize(h->stream));
+    if (getenv("VAEASSOC_TC_TIMELINE")) tc_debug_timeline(plan, h->stream);
     tc_plan_destroy(plan);
   } else {
     if (use_tc == 0 && skinny_supported(kind, a)) {

@@ -26,6 +26,8 @@
 
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
+#include <vector>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -146,7 +148,19 @@ struct TcArgs {
   const float* aux; int64_t ldaux;
   int act, round_out;
   int kblocks_per_split;     // BK-blocks of the contraction handled by one CTA (blockIdx.z)
+  unsigned long long* timeline;   // debug only (VAEASSOC_TC_TIMELINE): 8 stamps per CTA, else null
 };
+
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ unsigned smid() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %smid;" : "=r"(r));
+  return r;
+}
 
 template <int KIND, int BN>
 struct Cfg {
@@ -180,6 +194,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int kb0 = blockIdx.z * g.kblocks_per_split;
   const int kb1 = min(total_kb, kb0 + g.kblocks_per_split);
   const int nkb = kb1 - kb0;
+  unsigned long long* tl = g.timeline
+      ? g.timeline + 8ull * (blockIdx.x + gridDim.x * (blockIdx.y + (unsigned long long)gridDim.y * blockIdx.z)) : nullptr;
+  if (tl && threadIdx.x == 0) { tl[0] = gtimer(); tl[1] = clock64(); tl[7] = smid(); }
 
   if (threadIdx.x == 0) {
     prefetch_tensormap(&map_a);
@@ -193,6 +210,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  if (tl && threadIdx.x == 0) tl[2] = clock64();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -225,6 +243,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int s = i % C::STAGES;
         mbar_wait(full_bar(s), (i / C::STAGES) & 1);
         tc_fence_after();
+        if (tl && i == 0) tl[3] = clock64();
         const uint32_t sa = base + s * C::STAGE_BYTES, sb = sa + C::A_BYTES;
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k) {
@@ -235,6 +254,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         umma_commit(empty_bar(s));          // frees the smem slot once these MMAs have read it
       }
       umma_commit(tmem_full_bar);           // accumulator complete
+      if (tl) tl[4] = clock64();
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
@@ -261,6 +281,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
     }
+    if (tl && warp == 2 && lane == 0) tl[5] = clock64();
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t v[32];
@@ -297,6 +318,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (use_aux && c + 1 < BN / 32) load_aux(c + 1);
     }
   }
+  if (tl && warp == 2 && lane == 0) tl[6] = clock64();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -385,7 +407,7 @@ TcPlan* tc_plan_create(int kind, const GemmArgs& a, char* err, int errlen) {
   if (!ok) { delete p; return nullptr; }
   TcArgs& t = p->args;
   t.M = a.M; t.N = a.N; t.K = a.K; t.C = a.C; t.ldc = a.ldc; t.bias = a.bias; t.aux = a.aux; t.ldaux = a.ldaux;
-  t.act = a.act; t.round_out = a.round_out;
+  t.act = a.act; t.round_out = a.round_out; t.timeline = nullptr;
   const int tiles_m = (a.M + BM - 1) / BM, tiles_n = (a.N + BN - 1) / BN;
   const int total_kb = (a.K + BK - 1) / BK;
   int splits = 1;
@@ -417,6 +439,32 @@ TcPlan* tc_plan_create(int kind, const GemmArgs& a, char* err, int errlen) {
 }
 
 void tc_plan_destroy(TcPlan* p) { delete p; }
+
+// debug only: run the plan once with per-CTA time stamps and print the phase medians (cycles) to stderr
+void tc_debug_timeline(TcPlan* p, cudaStream_t s) {
+  const size_t n = (size_t)p->grid.x * p->grid.y * p->grid.z;
+  unsigned long long* dev = nullptr;
+  if (cudaMalloc(&dev, n * 64) != cudaSuccess) return;
+  cudaMemsetAsync(dev, 0, n * 64, s);
+  p->args.timeline = dev;
+  launch_gemm_tc(p, s);
+  p->args.timeline = nullptr;
+  std::vector<unsigned long long> h(n * 8);
+  cudaStreamSynchronize(s);
+  cudaMemcpy(h.data(), dev, n * 64, cudaMemcpyDeviceToHost);
+  cudaFree(dev);
+  auto med = [&](int a, int b) {
+    std::vector<long long> v;
+    for (size_t i = 0; i < n; ++i) v.push_back((long long)(h[8 * i + b] - h[8 * i + a]));
+    std::sort(v.begin(), v.end());
+    fprintf(stderr, " [%d->%d] min %lld med %lld max %lld |", a, b, v[0], v[n / 2], v[n - 1]);
+  };
+  unsigned long long g0 = ~0ull, g1 = 0;
+  for (size_t i = 0; i < n; ++i) { g0 = std::min(g0, h[8 * i]); g1 = std::max(g1, h[8 * i]); }
+  fprintf(stderr, "[tc timeline] kind %d grid (%u,%u,%u) start spread %llu ns; cycles:", p->kind, p->grid.x, p->grid.y, p->grid.z, g1 - g0);
+  med(1, 2); med(2, 3); med(3, 4); med(4, 5); med(5, 6); med(1, 6);
+  fprintf(stderr, "\n");
+}
 
 void launch_gemm_tc(const TcPlan* p, cudaStream_t s) {
   constexpr int BN = 128;

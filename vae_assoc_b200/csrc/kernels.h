@@ -41,6 +41,7 @@ struct TcPlan;   // opaque: tensor maps + grid for one GEMM call site, built onc
 TcPlan* tc_plan_create(int kind /*0 NN,1 NT,2 TN*/, const GemmArgs& a, char* err, int errlen);
 void tc_plan_destroy(TcPlan* p);
 void launch_gemm_tc(const TcPlan* p, cudaStream_t s);
+void tc_debug_timeline(TcPlan* p, cudaStream_t s);   // debug: per-CTA phase stamps to stderr
 bool tc_supported(int kind, const GemmArgs& a);
 
 // ------------------------------------------------------------------------------------------------------
