@@ -144,10 +144,11 @@ def tf32_round(x):
     return u.view(np.float32).astype(np.float64)
 
 
-def tc_served(M, N, K):
-    """Mirror of tc_supported() in vae_assoc_b200/csrc/gemm_tc.cu: which contractions run on tcgen05 kind::tf32
-    (row pitches / alignment always hold for the library's own buffers)."""
-    return M >= 32 and N >= 32 and K >= 32
+def tc_served(batch, aligned=True):
+    """Mirror of tc_supported() in vae_assoc_b200/csrc/gemm_tc2.cu: a contraction runs on tcgen05 kind::tf32 iff its
+    batch extent is >= 32 and every row pitch is a multiple of 4 floats (the library pads all pitches except those of
+    the [B, n_z] / [B, 2 n_z] latent tensors)."""
+    return batch >= 32 and aligned
 
 
 def tf32_plan(na, B):
@@ -155,13 +156,13 @@ def tf32_plan(na, B):
     rules as build_ops() in vae_assoc_b200/csrc/api.cu: a tensor is rounded by its producer iff one of its consumers
     is a tensor-core GEMM; tensor-core GEMMs read the tf32-rounded shadow of the weights, SIMT ones the master."""
     ni, r1, r2, nz = na["n_input"], na["n_hidden_recog_1"], na["n_hidden_recog_2"], na["n_z"]
-    nh = 2 * nz
+    a4, a2 = nz % 4 == 0, nz % 2 == 0          # pitch of z / dz is n_z, of the heads / dheads 2 n_z
     t = dict(
-        f_e1=tc_served(B, r1, ni), f_e2=tc_served(B, r2, r1), f_hd=tc_served(B, nh, r2),
-        f_d1=tc_served(B, r1, nz), f_d2=tc_served(B, r2, r1), f_o=tc_served(B, ni, r2),
-        w_o=tc_served(r2, ni, B), d_o=tc_served(B, r2, ni), w_d2=tc_served(r1, r2, B), d_d2=tc_served(B, r1, r2),
-        w_d1=tc_served(nz, r1, B), d_d1=tc_served(B, nz, r1), w_hd=tc_served(r2, nh, B), d_hd=tc_served(B, r2, nh),
-        w_e2=tc_served(r1, r2, B), d_e2=tc_served(B, r1, r2), w_e1=tc_served(ni, r1, B))
+        f_e1=tc_served(B), f_e2=tc_served(B), f_hd=tc_served(B, a2),
+        f_d1=tc_served(B, a4), f_d2=tc_served(B), f_o=tc_served(B),
+        w_o=tc_served(B), d_o=tc_served(B), w_d2=tc_served(B), d_d2=tc_served(B),
+        w_d1=tc_served(B, a4), d_d1=tc_served(B, a4), w_hd=tc_served(B, a2), d_hd=tc_served(B, a2),
+        w_e2=tc_served(B), d_e2=tc_served(B), w_e1=tc_served(B))
     t.update(r_x=t["f_e1"] or t["w_e1"], r_h1=t["f_e2"] or t["w_e2"], r_h2=t["f_hd"] or t["w_hd"],
              r_z=t["f_d1"] or t["w_d1"], r_g1=t["f_d2"] or t["w_d2"], r_g2=t["f_o"] or t["w_o"],
              r_da=t["w_o"] or t["d_o"], r_dg2=t["w_d2"] or t["d_d2"], r_dg1=t["w_d1"] or t["d_d1"],

@@ -98,13 +98,17 @@ def test_philox_and_generator_match_oracle(va):
 
 
 def check_step(model, oracle, X, eps, tol, grads=True, grad_tol=None):
+    # z is a tensor-core operand (decoder input layer) in tf32 mode, i.e. re-rounded to a 10-bit mantissa by its
+    # producer: an fp32-ulp difference in mu + sigma*eps next to a rounding boundary moves that entry by one tf32 ulp
+    # (2^-10 relative), whatever the kernels do
+    z_tol = tol if model.precision == "fp32" else max(tol, 2.0 ** -10)
     cost = model.compute_gradients(X, eps)
     c_ref, g_ref, pr = oracle.loss_and_grads(X, eps)
     assert abs(cost - c_ref) <= tol * abs(c_ref), (cost, c_ref)
     for m in range(len(X)):
         assert rel(model.z_means[m], pr["z_means"][m]) < tol
         assert rel(model.z_log_sigma_sqs[m], pr["z_log_sigma_sqs"][m]) < tol
-        assert rel(model.z_array[m], pr["z_array"][m]) < tol
+        assert rel(model.z_array[m], pr["z_array"][m]) < z_tol
         assert rel(model.x_reconstr_means[m], pr["x_reconstr_means"][m]) < tol
         assert rel(model.vae_latent_losses[m], pr["vae_latent_losses"][m]) < tol
         assert rel(model.vae_reconstr_losses[m], pr["vae_reconstr_losses"][m]) < tol

@@ -83,6 +83,8 @@ struct Op {
   std::function<void(cudaStream_t)> run;
   double flops = 0, bytes = 0;
   int launches = 1;
+  bool side = false;   // weight-gradient contraction: nothing downstream in the backward chain reads its result, so it
+                       // runs on the modality's side stream, concurrently with the dgrad chain
 };
 
 struct Mod {               // one modality (dense variant)
@@ -146,6 +148,9 @@ struct vaeassoc_ctx {
   std::vector<std::vector<Op>> ops_loss_mod, ops_bwd_dec_mod, ops_bwd_enc_mod;   // per-modality: run concurrently
   cudaStream_t side[VAEASSOC_MAX_MODALITIES - 1] = {nullptr, nullptr, nullptr};   // modality m > 0 runs on side[m-1]
   cudaEvent_t ev_fork = nullptr, ev_join[VAEASSOC_MAX_MODALITIES - 1] = {nullptr, nullptr, nullptr};
+  cudaStream_t wstream[VAEASSOC_MAX_MODALITIES] = {nullptr, nullptr, nullptr, nullptr};   // wgrad branch of modality m
+  cudaEvent_t ev_wfork[VAEASSOC_MAX_MODALITIES] = {nullptr, nullptr, nullptr, nullptr},
+              ev_wjoin[VAEASSOC_MAX_MODALITIES] = {nullptr, nullptr, nullptr, nullptr};
   std::vector<TcPlan*> plans;
   // graphs
   cudaGraphExec_t graph_train = nullptr, graph_grad = nullptr, graph_a1 = nullptr, graph_a2 = nullptr,
@@ -379,6 +384,7 @@ enum { KIND_NN = 0, KIND_NT = 1, KIND_TN = 2 };
 Op make_gemm(Ctx* c, const char* name, int m, int kind, GemmArgs a, int64_t w_off, bool round_out) {
   Op op;
   op.name = std::string(name) + "." + std::to_string(m);
+  op.side = (kind == KIND_TN);
   const bool tf32 = c->cfg.precision == VAEASSOC_TF32;
   a.round_out = (tf32 && round_out) ? 1 : 0;
   op.flops = 2.0 * a.M * a.N * a.K;
@@ -697,6 +703,29 @@ void run_ops(Ctx* c, std::vector<Op>& ops, cudaStream_t s) {
   }
 }
 
+// backward slice of modality m on stream s: the dgrad chain stays on s, every weight-gradient op forks onto the
+// modality's wgrad stream at the point where its dY is complete; the branch joins s again at the end of the slice
+// (under stream capture the event edges become graph dependencies)
+void run_bwd_ops(Ctx* c, int m, std::vector<Op>& ops, cudaStream_t s) {
+  cudaStream_t w = c->wstream[m];
+  bool forked = false;
+  for (Op& op : ops) {
+    if (op.side) {
+      CUDA_OK(cudaEventRecord(c->ev_wfork[m], s));
+      CUDA_OK(cudaStreamWaitEvent(w, c->ev_wfork[m], 0));
+      op.run(w);
+      forked = true;
+    } else {
+      op.run(s);
+    }
+    c->launches += op.launches;
+  }
+  if (forked) {
+    CUDA_OK(cudaEventRecord(c->ev_wjoin[m], w));
+    CUDA_OK(cudaStreamWaitEvent(s, c->ev_wjoin[m], 0));
+  }
+}
+
 FinalizeArgs finalize_args(Ctx* c, int advance) {
   FinalizeArgs a;
   a.n_mod = c->cfg.n_modalities;
@@ -749,7 +778,7 @@ void enqueue_a1(Ctx* c, cudaStream_t s) {
   for (int m = 0; m < M; ++m) {
     run_ops(c, c->ops_dec_mod[m], mod_stream(c, m, s));
     run_ops(c, c->ops_loss_mod[m], mod_stream(c, m, s));
-    run_ops(c, c->ops_bwd_dec_mod[m], mod_stream(c, m, s));
+    run_bwd_ops(c, m, c->ops_bwd_dec_mod[m], mod_stream(c, m, s));
   }
   join_modalities(c, s);
 }
@@ -757,7 +786,7 @@ void enqueue_a1(Ctx* c, cudaStream_t s) {
 void enqueue_a2(Ctx* c, cudaStream_t s, int advance) {
   run_ops(c, c->ops_latent_bwd, s);
   fork_modalities(c, s);
-  for (int m = 0; m < c->cfg.n_modalities; ++m) run_ops(c, c->ops_bwd_enc_mod[m], mod_stream(c, m, s));
+  for (int m = 0; m < c->cfg.n_modalities; ++m) run_bwd_ops(c, m, c->ops_bwd_enc_mod[m], mod_stream(c, m, s));
   join_modalities(c, s);
   launch_finalize(finalize_args(c, advance), s);
   c->launches += 1;
@@ -970,6 +999,11 @@ int vaeassoc_create(const vaeassoc_config* cfg, vaeassoc_handle* out) {
       CUDA_OK(cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
       CUDA_OK(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
     }
+    for (int i = 0; i < VAEASSOC_MAX_MODALITIES; ++i) {
+      CUDA_OK(cudaStreamCreateWithFlags(&c->wstream[i], cudaStreamNonBlocking));
+      CUDA_OK(cudaEventCreateWithFlags(&c->ev_wfork[i], cudaEventDisableTiming));
+      CUDA_OK(cudaEventCreateWithFlags(&c->ev_wjoin[i], cudaEventDisableTiming));
+    }
     CUDA_OK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&c->ev_bucket, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming));
@@ -1002,6 +1036,11 @@ int vaeassoc_destroy(vaeassoc_handle h) {
   for (int i = 0; i < VAEASSOC_MAX_MODALITIES - 1; ++i) {
     if (h->side[i]) cudaStreamDestroy(h->side[i]);
     if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+  }
+  for (int i = 0; i < VAEASSOC_MAX_MODALITIES; ++i) {
+    if (h->wstream[i]) cudaStreamDestroy(h->wstream[i]);
+    if (h->ev_wfork[i]) cudaEventDestroy(h->ev_wfork[i]);
+    if (h->ev_wjoin[i]) cudaEventDestroy(h->ev_wjoin[i]);
   }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_bucket) cudaEventDestroy(h->ev_bucket);
@@ -1446,16 +1485,19 @@ int vaeassoc_profile_step(vaeassoc_handle h, const float* const* x_dev, const in
     std::vector<cudaEvent_t> ev(all.size() + 1);
     for (auto& e : ev) CUDA_OK(cudaEventCreate(&e));
     CUDA_OK(cudaEventRecord(ev[0], s));
+    // each op runs kReps times back to back between its two events (an event pair around ONE launch measures
+    // mostly the launch gap: ~8 us against kernels of 5-30 us); accumulating ops (wgrad) just accumulate kReps times
+    constexpr int kReps = 4;
     for (size_t i = 0; i < all.size(); ++i) {
-      all[i].run(s);
-      h->launches += all[i].launches;
+      for (int r = 0; r < kReps; ++r) all[i].run(s);
+      h->launches += kReps * all[i].launches;
       CUDA_OK(cudaEventRecord(ev[i + 1], s));
     }
     CUDA_OK(cudaStreamSynchronize(s));
     for (int i = 0; i < n; ++i) {
       float t = 0.f;
       CUDA_OK(cudaEventElapsedTime(&t, ev[i], ev[i + 1]));
-      ms[i] = t;
+      ms[i] = t / kReps;
       if (flops) flops[i] = all[i].flops;
       if (bytes) bytes[i] = all[i].bytes;
       snprintf(names + (size_t)i * 32, 32, "%s", all[i].name.c_str());

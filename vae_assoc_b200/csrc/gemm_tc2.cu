@@ -364,11 +364,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             break;
           case ACT_SOFTPLUS:
 #pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = softplus_f(x[j]);
+            for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.0f) + __logf(1.0f + __expf(-fabsf(x[j])));
             break;
           case ACT_SIGMOID:
 #pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = sigmoid_f(x[j]);
+            for (int j = 0; j < 32; ++j) x[j] = __fdividef(1.0f, 1.0f + __expf(-x[j]));
             break;
           default: break;
         }
@@ -389,7 +389,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             break;
           case ACT_SOFTPLUS:
 #pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] *= 1.0f - expf(-h[j]);
+            for (int j = 0; j < 32; ++j) x[j] *= 1.0f - __expf(-h[j]);
             break;
           case ACT_SIGMOID:
 #pragma unroll
@@ -485,10 +485,11 @@ bool tc_supported(int kind, const GemmArgs& a) {
     return false;
   if ((a.lda & 3) || (a.ldb & 3) || (a.ldc & 3)) return false;
   if (a.aux && ((reinterpret_cast<uintptr_t>(a.aux) & 15) || (a.ldaux & 3))) return false;
-  // worth a tensor-core tile: skinny shapes (n_z-wide heads, K = n_z) stay on the HBM-bound SIMT kernels
-  if (a.M < 32 || a.N < 32 || a.K < 32) return false;
-  (void)kind;
-  return true;
+  // every contraction whose batch extent fills a tile row block runs here, including the n_z-wide ones (heads,
+  // decoder input layer): those are HBM-bound and the TMA pipeline streams the one large operand exactly once;
+  // out-of-range rows / columns of the narrow operand are zero-filled by TMA at no HBM cost
+  const int batch = (kind == KIND_TN) ? a.K : a.M;
+  return batch >= 32;
 }
 
 TcPlan* tc_plan_create(int kind, const GemmArgs& a, char* err, int errlen) {
@@ -525,7 +526,7 @@ TcPlan* tc_plan_create(int kind, const GemmArgs& a, char* err, int errlen) {
   if (kind == KIND_TN) {
     // split the batch contraction so that every SM pair has a cluster; each split keeps >= 4 k-blocks
     const int pairs = kNumSMs / 2;
-    const int want = (pairs + tiles_m * tiles_nn - 1) / (tiles_m * tiles_nn);
+    const int want = pairs / (tiles_m * tiles_nn);      // floor: one wave of clusters
     splits = std::max(1, std::min(want, total_kb / 4));
     if (a.splitk > 1) splits = std::min(a.splitk, total_kb);
   }
