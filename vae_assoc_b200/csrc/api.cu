@@ -83,6 +83,8 @@ struct Op {
   std::function<void(cudaStream_t)> run;
   double flops = 0, bytes = 0;
   int launches = 1;
+  int kind = -1;        // tensor-core contraction: 0 NN, 1 NT, 2 TN (else -1) and its final arguments
+  GemmArgs gargs;
   bool side = false;   // weight-gradient contraction: nothing downstream in the backward chain reads its result, so it
                        // runs on the modality's side stream, concurrently with the dgrad chain
 };
@@ -151,7 +153,15 @@ struct vaeassoc_ctx {
   cudaStream_t wstream[VAEASSOC_MAX_MODALITIES] = {nullptr, nullptr, nullptr, nullptr};   // wgrad branch of modality m
   cudaEvent_t ev_wfork[VAEASSOC_MAX_MODALITIES] = {nullptr, nullptr, nullptr, nullptr},
               ev_wjoin[VAEASSOC_MAX_MODALITIES] = {nullptr, nullptr, nullptr, nullptr};
-  std::vector<TcPlan*> plans;
+  // tensor-core path: one plan (problems + tile tasks) per handle; gsync = row-block counters, then two words per
+  // launch site (queue head, clusters-left), all self-cleaning (zero between launches)
+  GroupPlan* gplan = nullptr;
+  uint32_t* gsync = nullptr;
+  int n_ctr = 0, max_sites = 0;
+  struct Seg { int site = 0, reset_first = 0, reset_count = 0; };
+  Seg seg_enc, seg_dec, seg_bwd_dec, seg_bwd_enc;     // fused segments of the train step (dense modalities, tf32)
+  bool fused = false;
+  std::vector<Op> ops_colsum_dec, ops_colsum_enc;     // bias gradients that no GEMM epilogue produces (d a, d heads)
   // graphs
   cudaGraphExec_t graph_train = nullptr, graph_grad = nullptr, graph_a1 = nullptr, graph_a2 = nullptr,
                   graph_adam = nullptr;
@@ -163,8 +173,10 @@ struct vaeassoc_ctx {
   template <typename T>
   T* dalloc(int64_t n, bool zero = true) {
     void* ptr = nullptr;
-    CUDA_OK(cudaMalloc(&ptr, (size_t)std::max<int64_t>(n, 1) * sizeof(T)));
-    if (zero) CUDA_OK(cudaMemset(ptr, 0, (size_t)std::max<int64_t>(n, 1) * sizeof(T)));
+    // + 256 B: the 3-D tensor maps of MN-major GEMM operands may read up to 124 B past the last row (gemm_group.cu)
+    const size_t bytes = (size_t)std::max<int64_t>(n, 1) * sizeof(T) + 256;
+    CUDA_OK(cudaMalloc(&ptr, bytes));
+    if (zero) CUDA_OK(cudaMemset(ptr, 0, bytes));
     allocs.push_back(ptr);
     return reinterpret_cast<T*>(ptr);
   }
@@ -336,6 +348,13 @@ void alloc_buffers(Ctx* c) {
   c->m = c->dalloc<float>(c->n_flat);
   c->v = c->dalloc<float>(c->n_flat);
   c->p_tf32 = c->dalloc<float>(c->n_flat);
+  {
+    // row-block counters: 8 activation / gradient tensors per modality x row blocks of 256; then the launch sites
+    const int64_t rb = (B + 255) / 256;
+    c->n_ctr = (int)(c->cfg.n_modalities * 8 * rb);
+    c->max_sites = 1024;
+    c->gsync = c->dalloc<uint32_t>(c->n_ctr + 2 * c->max_sites);
+  }
   c->eps = c->dalloc<float>(B * nz);
   c->eps_in[0] = c->dalloc<float>(B * nz);
   c->eps_in[1] = c->dalloc<float>(B * nz);
@@ -391,20 +410,45 @@ Op make_gemm(Ctx* c, const char* name, int m, int kind, GemmArgs a, int64_t w_of
   op.bytes = 4.0 * ((double)a.M * a.K + (double)a.K * a.N + (double)a.M * a.N * (kind == KIND_NT && a.aux ? 2 : 1));
   if (w_off >= 0) a.B = c->p_tf32 + w_off;
   if (tf32 && tc_supported(kind, a)) {
+    // one launch of the persistent tile kernel over this contraction's tiles (no dependencies); the fused train-step
+    // segments (build_segments) reuse the same arguments
     char err[256] = {0};
-    TcPlan* plan = tc_plan_create(kind, a, err, sizeof err);
-    if (!plan) fail("tcgen05 plan for %s failed: %s", op.name.c_str(), err);
-    c->plans.push_back(plan);
+    const int site = group_begin(c->gplan);
+    if (site >= c->max_sites - 1) fail("too many tensor-core launch sites");
+    const int prob = group_add_problem(c->gplan, kind, a, err, sizeof err);
+    if (prob < 0) fail("tcgen05 plan for %s failed: %s", op.name.c_str(), err);
+    const int tm = group_problem_tiles_m(c->gplan, prob), tn = group_problem_tiles_n(c->gplan, prob);
+    const int kb = group_problem_kblocks(c->gplan, prob);
+    if (kind == KIND_TN) {
+      // split the batch contraction into row-block ranges so that every SM pair gets a task
+      const int rbs = (kb + 7) / 8;
+      int splits = std::max(1, std::min(rbs, (kNumSMs / 2) / std::max(1, tm * tn)));
+      if (a.splitk > 1) splits = std::min(a.splitk, rbs);
+      const int per = (rbs + splits - 1) / splits;
+      for (int r0 = 0; r0 < rbs; r0 += per)
+        for (int i = 0; i < tm; ++i)
+          for (int j = 0; j < tn; ++j)
+            group_add_task(c->gplan, prob, i, j, r0 * 8, std::min(per * 8, kb - r0 * 8), -1, 0, 0, -1, 0, -1);
+    } else {
+      for (int i = 0; i < tm; ++i)
+        for (int j = 0; j < tn; ++j) group_add_task(c->gplan, prob, i, j, 0, kb, -1, 0, 0, -1, 0, -1);
+    }
+    if (!group_end(c->gplan, err, sizeof err)) fail("%s", err);
     op.name += ".tc";
+    op.kind = kind;
+    op.gargs = a;
+    Ctx* cc = c;
     if (kind == KIND_TN && a.bias_grad) {
       const GemmArgs b = a;
       op.launches = 2;
-      op.run = [plan, b](cudaStream_t s) {
-        launch_gemm_tc(plan, s);
+      op.run = [cc, site, b](cudaStream_t s) {
+        group_launch(cc->gplan, site, cc->gsync + cc->n_ctr + 2 * site, 0, 0, s);
         launch_colsum(b.B, b.ldb, b.K, b.N, b.bias_grad, s);
       };
     } else {
-      op.run = [plan](cudaStream_t s) { launch_gemm_tc(plan, s); };
+      op.run = [cc, site](cudaStream_t s) {
+        group_launch(cc->gplan, site, cc->gsync + cc->n_ctr + 2 * site, 0, 0, s);
+      };
     }
     return op;
   }
@@ -563,10 +607,14 @@ void build_ops_conv(Ctx* c, int m) {
   for (auto& op : be) c->ops_bwd_enc.push_back(op);
 }
 
+void build_segments(Ctx* c);
+
 void build_ops(Ctx* c) {
   destroy_graphs(c);
-  for (TcPlan* p : c->plans) tc_plan_destroy(p);
-  c->plans.clear();
+  group_destroy(c->gplan);
+  c->gplan = group_create();
+  c->fused = false;
+  c->ops_colsum_dec.clear(); c->ops_colsum_enc.clear();
   c->ops_fwd_enc.clear(); c->ops_latent_fwd.clear(); c->ops_fwd_dec.clear(); c->ops_loss.clear();
   c->ops_bwd_dec.clear(); c->ops_latent_bwd.clear(); c->ops_bwd_enc.clear();
   const int M = c->cfg.n_modalities;
@@ -694,6 +742,121 @@ void build_ops(Ctx* c) {
     op.run = [a](cudaStream_t s) { launch_latent_bwd(a, s); };
     c->ops_latent_bwd.push_back(op);
   }
+  build_segments(c);
+}
+
+// ---- fused train-step segments (dense modalities, tf32) -------------------------------------------------------------
+// The layers of a segment become ONE launch of the persistent tile kernel: tasks in dependency order, linked by
+// row-block counters (tensor T of modality m over rows [256 rb, +256) is complete when its counter reaches
+// 16 x (N-tiles of the producing layer)).  Counter index = (T * n_modalities + m) * RB + rb.
+enum { T_H1 = 0, T_H2, T_G1, T_G2, T_DG2, T_DG1, T_DH2, T_DH1 };
+
+void build_segments(Ctx* c) {
+  const int M = c->cfg.n_modalities;
+  const int B = c->cfg.batch_size;
+  const int RB = (B + 255) / 256;
+  bool ok = c->cfg.precision == VAEASSOC_TF32 && !getenv("VAEASSOC_NO_FUSE");
+  const bool nodeps = getenv("VAEASSOC_DEBUG_NODEPS") != nullptr;   // timing experiments only: wrong results
+  for (int m = 0; m < M && ok; ++m) {
+    if (c->mods[m].conv) { ok = false; break; }
+    if (c->ops_enc_mod[m].size() != 3 || c->ops_dec_mod[m].size() != 3 || c->ops_bwd_dec_mod[m].size() != 6 ||
+        c->ops_bwd_enc_mod[m].size() != 5) { ok = false; break; }
+    for (auto* v : {&c->ops_enc_mod[m], &c->ops_dec_mod[m], &c->ops_bwd_dec_mod[m], &c->ops_bwd_enc_mod[m]})
+      for (const Op& op : *v) ok = ok && op.kind >= 0;
+  }
+  char err[256] = {0};
+  if (ok) {
+    GroupPlan* g = c->gplan;
+    auto ctr = [&](int m, int T, int rb) { return (T * M + m) * RB + rb; };
+    // tiles of a row-wise layer (NN / NT): one task per (row block, column tile)
+    auto add_rowwise = [&](const Op& op, int m, int inT, int in_tn, int outT, float* colsum) -> int {
+      if (nodeps) { inT = -1; outT = -1; }
+      GemmArgs a = op.gargs;
+      a.bias_grad = colsum;
+      const int prob = group_add_problem(g, op.kind, a, err, sizeof err);
+      if (prob < 0) fail("segment plan for %s failed: %s", op.name.c_str(), err);
+      const int tm = group_problem_tiles_m(g, prob), tn = group_problem_tiles_n(g, prob), kb = group_problem_kblocks(g, prob);
+      for (int i = 0; i < tm; ++i)
+        for (int j = 0; j < tn; ++j)
+          group_add_task(g, prob, i, j, 0, kb, inT >= 0 ? ctr(m, inT, i) : -1, inT >= 0 ? 1 : 0,
+                         kGroupSignalsPerTile * in_tn, -1, 0, outT >= 0 ? ctr(m, outT, i) : -1);
+      return tn;
+    };
+    // weight gradient (TN): the batch contraction is cut into row-block ranges; a task waits for dY over its range
+    auto add_wgrad = [&](const Op& op, int m, int dyT, int dy_tn) {
+      const bool external = dyT < 0;
+      if (nodeps) dyT = -1;
+      GemmArgs a = op.gargs;
+      a.bias_grad = nullptr;
+      const int prob = group_add_problem(g, op.kind, a, err, sizeof err);
+      if (prob < 0) fail("segment plan for %s failed: %s", op.name.c_str(), err);
+      const int tm = group_problem_tiles_m(g, prob), tn = group_problem_tiles_n(g, prob), kb = group_problem_kblocks(g, prob);
+      const int rbs = (kb + 7) / 8;
+      const int splits = std::max(1, std::min(rbs, (kNumSMs / 2) / std::max(1, tm * tn)));
+      const int per = (rbs + splits - 1) / splits;
+      for (int r0 = 0; r0 < rbs; r0 += per) {
+        const int nrb = std::min(per, rbs - r0);
+        for (int i = 0; i < tm; ++i)
+          for (int j = 0; j < tn; ++j)
+            group_add_task(g, prob, i, j, r0 * 8, std::min(nrb * 8, kb - r0 * 8), dyT >= 0 ? ctr(m, dyT, r0) : -1,
+                           dyT >= 0 ? nrb : 0, kGroupSignalsPerTile * dy_tn, -1, 0, -1);
+      }
+      if (external && op.gargs.bias_grad) {
+        // dY comes from an elementwise kernel (loss / latent backward): its column sums need their own launch
+        const GemmArgs b = op.gargs;
+        Op cs; cs.name = "bgrad_" + op.name; cs.bytes = 4.0 * b.K * b.N;
+        cs.run = [b](cudaStream_t s) { launch_colsum(b.B, b.ldb, b.K, b.N, b.bias_grad, s); };
+        return cs;
+      }
+      return Op();
+    };
+    auto begin = [&](Ctx::Seg& sg, int T0) {
+      sg.site = group_begin(g);
+      if (sg.site >= c->max_sites - 1) fail("too many tensor-core launch sites");
+      sg.reset_first = ctr(0, T0, 0);
+      sg.reset_count = 2 * M * RB;
+    };
+    auto end = [&](Ctx::Seg& sg) { (void)sg; if (!group_end(g, err, sizeof err)) fail("%s", err); };
+    std::vector<int> tn1(M), tn2(M);
+    // encoder forward: enc1 -> h1 -> enc2 -> h2 -> heads
+    begin(c->seg_enc, T_H1);
+    for (int m = 0; m < M; ++m) tn1[m] = add_rowwise(c->ops_enc_mod[m][0], m, -1, 0, T_H1, nullptr);
+    for (int m = 0; m < M; ++m) tn2[m] = add_rowwise(c->ops_enc_mod[m][1], m, T_H1, tn1[m], T_H2, nullptr);
+    for (int m = 0; m < M; ++m) add_rowwise(c->ops_enc_mod[m][2], m, T_H2, tn2[m], -1, nullptr);
+    end(c->seg_enc);
+    // decoder forward: dec1 -> g1 -> dec2 -> g2 -> out
+    begin(c->seg_dec, T_G1);
+    for (int m = 0; m < M; ++m) tn1[m] = add_rowwise(c->ops_dec_mod[m][0], m, -1, 0, T_G1, nullptr);
+    for (int m = 0; m < M; ++m) tn2[m] = add_rowwise(c->ops_dec_mod[m][1], m, T_G1, tn1[m], T_G2, nullptr);
+    for (int m = 0; m < M; ++m) add_rowwise(c->ops_dec_mod[m][2], m, T_G2, tn2[m], -1, nullptr);
+    end(c->seg_dec);
+    // decoder backward; ops: 0 wgrad_out 1 dgrad_out 2 wgrad_dec2 3 dgrad_dec2 4 wgrad_dec1 5 dgrad_dec1.  The dgrad
+    // epilogue that produces dY also produces the bias gradient (column sums) of the layer that consumes dY
+    begin(c->seg_bwd_dec, T_DG2);
+    for (int m = 0; m < M; ++m) { auto& bd = c->ops_bwd_dec_mod[m]; tn1[m] = add_rowwise(bd[1], m, -1, 0, T_DG2, bd[2].gargs.bias_grad); }
+    for (int m = 0; m < M; ++m) { Op cs = add_wgrad(c->ops_bwd_dec_mod[m][0], m, -1, 0); if (cs.run) c->ops_colsum_dec.push_back(cs); }
+    for (int m = 0; m < M; ++m) { auto& bd = c->ops_bwd_dec_mod[m]; tn2[m] = add_rowwise(bd[3], m, T_DG2, tn1[m], T_DG1, bd[4].gargs.bias_grad); }
+    for (int m = 0; m < M; ++m) add_wgrad(c->ops_bwd_dec_mod[m][2], m, T_DG2, tn1[m]);
+    for (int m = 0; m < M; ++m) add_rowwise(c->ops_bwd_dec_mod[m][5], m, T_DG1, tn2[m], -1, nullptr);
+    for (int m = 0; m < M; ++m) add_wgrad(c->ops_bwd_dec_mod[m][4], m, T_DG1, tn2[m]);
+    end(c->seg_bwd_dec);
+    // encoder backward; ops: 0 wgrad_heads 1 dgrad_heads 2 wgrad_enc2 3 dgrad_enc2 4 wgrad_enc1
+    begin(c->seg_bwd_enc, T_DH2);
+    for (int m = 0; m < M; ++m) { auto& be = c->ops_bwd_enc_mod[m]; tn1[m] = add_rowwise(be[1], m, -1, 0, T_DH2, be[2].gargs.bias_grad); }
+    for (int m = 0; m < M; ++m) { Op cs = add_wgrad(c->ops_bwd_enc_mod[m][0], m, -1, 0); if (cs.run) c->ops_colsum_enc.push_back(cs); }
+    for (int m = 0; m < M; ++m) { auto& be = c->ops_bwd_enc_mod[m]; tn2[m] = add_rowwise(be[3], m, T_DH2, tn1[m], T_DH1, be[4].gargs.bias_grad); }
+    for (int m = 0; m < M; ++m) add_wgrad(c->ops_bwd_enc_mod[m][2], m, T_DH2, tn1[m]);
+    for (int m = 0; m < M; ++m) add_wgrad(c->ops_bwd_enc_mod[m][4], m, T_DH1, tn2[m]);
+    end(c->seg_bwd_enc);
+    c->fused = true;
+  }
+  group_set_counters(c->gplan, c->gsync, c->n_ctr);
+  if (!group_upload(c->gplan, err, sizeof err)) fail("%s", err);
+}
+
+void launch_seg(Ctx* c, const Ctx::Seg& sg, cudaStream_t s) {
+  group_launch(c->gplan, sg.site, c->gsync + c->n_ctr + 2 * sg.site, sg.reset_first, sg.reset_count, s);
+  c->launches += 1;
 }
 
 void run_ops(Ctx* c, std::vector<Op>& ops, cudaStream_t s) {
@@ -766,10 +929,35 @@ void join_modalities(Ctx* c, cudaStream_t s) {
   }
 }
 
+// bias gradients that no GEMM epilogue produces run on a side stream next to the fused segment that follows
+void fork_colsums(Ctx* c, std::vector<Op>& ops, cudaStream_t s) {
+  if (ops.empty()) return;
+  CUDA_OK(cudaEventRecord(c->ev_wfork[0], s));
+  CUDA_OK(cudaStreamWaitEvent(c->wstream[0], c->ev_wfork[0], 0));
+  run_ops(c, ops, c->wstream[0]);
+  CUDA_OK(cudaEventRecord(c->ev_wjoin[0], c->wstream[0]));
+}
+void join_colsums(Ctx* c, std::vector<Op>& ops, cudaStream_t s) {
+  if (!ops.empty()) CUDA_OK(cudaStreamWaitEvent(s, c->ev_wjoin[0], 0));
+}
+
 // segment A1: zero grads, forward, losses, decoder backward   (gradient bucket 0 complete at its end)
 void enqueue_a1(Ctx* c, cudaStream_t s) {
   const int M = c->cfg.n_modalities;
   CUDA_OK(cudaMemsetAsync(c->g, 0, (size_t)(c->n_flat + 32) * sizeof(float), s));
+  if (c->fused) {
+    // four launches of the persistent tile kernel carry every dense layer of both modalities (csrc/gemm_group.cu)
+    launch_seg(c, c->seg_enc, s);
+    run_ops(c, c->ops_latent_fwd, s);
+    launch_seg(c, c->seg_dec, s);
+    fork_modalities(c, s);
+    for (int m = 0; m < M; ++m) run_ops(c, c->ops_loss_mod[m], mod_stream(c, m, s));
+    join_modalities(c, s);
+    fork_colsums(c, c->ops_colsum_dec, s);
+    launch_seg(c, c->seg_bwd_dec, s);
+    join_colsums(c, c->ops_colsum_dec, s);
+    return;
+  }
   fork_modalities(c, s);
   for (int m = 0; m < M; ++m) run_ops(c, c->ops_enc_mod[m], mod_stream(c, m, s));
   join_modalities(c, s);
@@ -785,9 +973,15 @@ void enqueue_a1(Ctx* c, cudaStream_t s) {
 // segment A2: latent + encoder backward, cost finalize (bucket 1 + cost slot complete at its end)
 void enqueue_a2(Ctx* c, cudaStream_t s, int advance) {
   run_ops(c, c->ops_latent_bwd, s);
-  fork_modalities(c, s);
-  for (int m = 0; m < c->cfg.n_modalities; ++m) run_bwd_ops(c, m, c->ops_bwd_enc_mod[m], mod_stream(c, m, s));
-  join_modalities(c, s);
+  if (c->fused) {
+    fork_colsums(c, c->ops_colsum_enc, s);
+    launch_seg(c, c->seg_bwd_enc, s);
+    join_colsums(c, c->ops_colsum_enc, s);
+  } else {
+    fork_modalities(c, s);
+    for (int m = 0; m < c->cfg.n_modalities; ++m) run_bwd_ops(c, m, c->ops_bwd_enc_mod[m], mod_stream(c, m, s));
+    join_modalities(c, s);
+  }
   launch_finalize(finalize_args(c, advance), s);
   c->launches += 1;
 }
@@ -1026,7 +1220,7 @@ int vaeassoc_destroy(vaeassoc_handle h) {
   cudaDeviceSynchronize();
   if (h->comm) { g_nccl.CommDestroy(h->comm); h->comm = nullptr; }
   destroy_graphs(h);
-  for (TcPlan* p : h->plans) tc_plan_destroy(p);
+  group_destroy(h->gplan);
   for (void* p : h->allocs) cudaFree(p);
   if (h->host_cost_ring) cudaFreeHost(h->host_cost_ring);
   for (int i = 0; i < 2; ++i) {
@@ -1430,14 +1624,30 @@ int vaeassoc_debug_gemm(vaeassoc_handle h, int kind, int use_tc, int M, int N, i
   a.bias_grad = bias_grad; a.aux = aux; a.ldaux = ldaux; a.act = act; a.round_out = round_out;
   if (use_tc == 1) {
     if (!tc_supported(kind, a)) fail("shape not served by the tcgen05 path");
+    // a throw-away one-problem plan through the same persistent tile kernel the train step uses
     char err[256] = {0};
-    TcPlan* plan = tc_plan_create(kind, a, err, sizeof err);
-    if (!plan) fail("tcgen05 plan failed: %s", err);
-    launch_gemm_tc(plan, h->stream);
+    GroupPlan* plan = group_create();
+    const int dsite = group_begin(plan);
+    const int prob = group_add_problem(plan, kind, a, err, sizeof err);
+    if (prob < 0) { group_destroy(plan); fail("tcgen05 plan failed: %s", err); }
+    const int tm = group_problem_tiles_m(plan, prob), tn = group_problem_tiles_n(plan, prob);
+    const int kb = group_problem_kblocks(plan, prob);
+    const int rbs = (kb + 7) / 8;
+    const int splits = kind == KIND_TN ? std::max(1, std::min(rbs, (kNumSMs / 2) / std::max(1, tm * tn))) : 1;
+    const int per = (rbs + splits - 1) / splits;
+    for (int r0 = 0; r0 < (kind == KIND_TN ? rbs : 1); r0 += per)
+      for (int i = 0; i < tm; ++i)
+        for (int j = 0; j < tn; ++j)
+          group_add_task(plan, prob, i, j, kind == KIND_TN ? r0 * 8 : 0,
+                         kind == KIND_TN ? std::min(per * 8, kb - r0 * 8) : kb, -1, 0, 0, -1, 0, -1);
+    group_set_counters(plan, h->gsync, h->n_ctr);
+    if (!group_end(plan, err, sizeof err) || !group_upload(plan, err, sizeof err)) { group_destroy(plan); fail("%s", err); }
+    group_launch(plan, dsite, h->gsync + h->n_ctr + 2 * (h->max_sites - 1), 0, 0, h->stream);
     if (kind == KIND_TN && bias_grad) launch_colsum(B, ldb, K, N, bias_grad, h->stream);
     CUDA_OK(cudaStreamSynchronize(h->stream));
-    if (getenv("VAEASSOC_TC_TIMELINE")) tc_debug_timeline(plan, h->stream);
-    tc_plan_destroy(plan);
+    if (getenv("VAEASSOC_TC_TIMELINE"))
+      group_debug_timeline(plan, dsite, h->gsync + h->n_ctr + 2 * (h->max_sites - 1), 0, 0, h->stream);
+    group_destroy(plan);
   } else {
     if (use_tc == 0 && skinny_supported(kind, a)) {
       launch_gemm_skinny(kind, a, h->stream);
@@ -1471,8 +1681,28 @@ int vaeassoc_profile_step(vaeassoc_handle h, const float* const* x_dev, const in
       z.run = [c](cudaStream_t st) { CUDA_OK(cudaMemsetAsync(c->g, 0, (size_t)(c->n_flat + 32) * sizeof(float), st)); };
       all.push_back(z);
     }
-    for (auto* v : {&h->ops_fwd_enc, &h->ops_latent_fwd, &h->ops_fwd_dec, &h->ops_loss, &h->ops_bwd_dec, &h->ops_latent_bwd, &h->ops_bwd_enc})
-      for (auto& op : *v) all.push_back(op);
+    if (h->fused) {
+      // the train step's own launches: four fused segments + the elementwise kernels between them
+      Ctx* c = h;
+      auto seg_op = [&](const char* name, const Ctx::Seg* sg, std::initializer_list<std::vector<Op>*> members) {
+        Op o; o.name = name;
+        for (auto* v : members) for (auto& op : *v) o.flops += op.flops;
+        o.run = [c, sg](cudaStream_t st) { launch_seg(c, *sg, st); c->launches -= 1; };
+        all.push_back(o);
+      };
+      seg_op("seg_fwd_enc", &h->seg_enc, {&h->ops_fwd_enc});
+      for (auto& op : h->ops_latent_fwd) all.push_back(op);
+      seg_op("seg_fwd_dec", &h->seg_dec, {&h->ops_fwd_dec});
+      for (auto& op : h->ops_loss) all.push_back(op);
+      for (auto& op : h->ops_colsum_dec) all.push_back(op);
+      seg_op("seg_bwd_dec", &h->seg_bwd_dec, {&h->ops_bwd_dec});
+      for (auto& op : h->ops_latent_bwd) all.push_back(op);
+      for (auto& op : h->ops_colsum_enc) all.push_back(op);
+      seg_op("seg_bwd_enc", &h->seg_bwd_enc, {&h->ops_bwd_enc});
+    } else {
+      for (auto* v : {&h->ops_fwd_enc, &h->ops_latent_fwd, &h->ops_fwd_dec, &h->ops_loss, &h->ops_bwd_dec, &h->ops_latent_bwd, &h->ops_bwd_enc})
+        for (auto& op : *v) all.push_back(op);
+    }
     {
       Ctx* c = h;
       Op f; f.name = "finalize"; f.run = [c](cudaStream_t st) { launch_finalize(finalize_args(c, 1), st); };
@@ -1480,6 +1710,11 @@ int vaeassoc_profile_step(vaeassoc_handle h, const float* const* x_dev, const in
       Op a; a.name = "adam"; a.bytes = (c->cfg.precision == VAEASSOC_TF32 ? 32.0 : 28.0) * c->n_flat;
       a.run = [c](cudaStream_t st) { launch_adam(adam_args(c), st); };
       all.push_back(a);
+    }
+    if (h->fused && getenv("VAEASSOC_TC_TIMELINE")) {
+      CUDA_OK(cudaStreamSynchronize(s));
+      for (const Ctx::Seg* sg : {&h->seg_enc, &h->seg_dec, &h->seg_bwd_dec, &h->seg_bwd_enc})
+        group_debug_timeline(h->gplan, sg->site, h->gsync + h->n_ctr + 2 * sg->site, sg->reset_first, sg->reset_count, s);
     }
     const int n = (int)std::min<size_t>(all.size(), (size_t)capacity);
     std::vector<cudaEvent_t> ev(all.size() + 1);

@@ -1,0 +1,979 @@
+// Persistent, grouped, dataflow tcgen05 / TMA GEMM for sm_100a -- the tensor-core path of the assoc-VAE train step.
+//
+// One launch executes a LIST OF TILE TASKS drawn from several dense-layer contractions ("problems") of the step:
+//
+//   kind NN  C[M,N]  = act(A[M,K] . B[K,N] + bias)          forward   (vae_assoc.py:187-188,203-204,282-283,295-303)
+//   kind NT  C[M,N]  = (A[M,K] . B[N,K]^T) (*) act'(aux)    dgrad     (autodiff of the above, :373-374)
+//   kind TN  C[M,N] += A[K,M]^T . B[K,N]                    wgrad     (K = batch, split into tasks, TMA reduce-add)
+//
+// Why: at the reference sizes one layer is 0.5-6 GFLOP, i.e. 3-8 us of tensor time; launched one kernel per layer
+// (34 GEMMs + 12 column sums per step) the fixed cost of a launch -- grid start, barrier / TMEM set-up, first
+// operand latency, epilogue drain, ~9 us -- exceeds the useful work.  Rows of the batch are independent through the
+// whole network, so the layers of a segment (encoder forward, decoder forward, decoder backward, encoder backward;
+// both modalities) become ONE launch: each task names the row-block counters it must see complete before its operands
+// may be loaded (the tiles of the producing layer over the same 256 rows) and the counter it bumps when its own
+// output is globally visible.  Tasks are listed in dependency order and handed out IN THAT ORDER from a global
+// atomic queue to whichever cluster is free, so the smallest unfinished task is always held by a running cluster
+// and is never blocked -- no deadlock, whatever share of the SMs other streams (NCCL, column sums) occupy.
+//
+// Tile engine (per cluster of two CTAs, `tcgen05.mma.cta_group::2`, UMMA 256 x BN x 8, kind::tf32):
+//   warp 0     TMA producer: waits the task's counters, then streams A (its 128 rows) and B (its BN/2 columns)
+//              k-blocks of 32 into a 4-stage ring; both CTAs' loads complete on the leader's `full` barrier.
+//              The leader's producer is also the scheduler: it pops the queue two tasks ahead and publishes each
+//              task index through a 4-slot ring (shared memory of both CTAs, mbarrier full / empty) to every role
+//   warp 1     leader CTA: MMA issuer; accumulators double-buffered in TMEM (2 x 256 columns) so the epilogue of
+//              task i overlaps the main loop of task i+1; `tcgen05.commit` multicasts to both CTAs
+//   warps 2-9  epilogue: tcgen05.ld (thread = row, 32 columns) -> bias / activation / act'(aux tile via TMA) ->
+//              swizzled smem staging -> TMA store (NN, NT) or TMA reduce-add (TN); then release the accumulator
+//              and, once the stores are complete, bump the task's counter (release, gpu scope)
+// Operands are fp32 in HBM, rounded to tf32 by their producers.  TMA zero-fills loads past M / N / K and clips
+// stores (in 16-byte units: columns N..roundup4(N) receive zeros), so only 16-byte row pitches are required.
+//
+// Shared-memory operand layouts (canonical UMMA layouts):
+//   K-major  operand: tile [R rows][32 k] -> R rows of 128 B, one TMA box {32, R}; SWIZZLE_128B, SBO = 1024 B;
+//            the four K=8 MMAs of a stage advance the start address by 32 B.
+//   MN-major operand: tile [R/32 chunks][32 k rows][32 mn]; for 32-bit operands the only UMMA layout is
+//            SWIZZLE_128B_BASE32B (TMA mode SWIZZLE_128B_ATOM_32B): LBO = 4096 B, SBO = 512 B; the four MMAs of a
+//            stage advance the start by 1024 B.  ONE TMA instruction fills it: the matrix is described as a 3-D
+//            tensor {32 mn, k, mn-chunk} with strides {4 B, pitch, 128 B} and the box is {32, 32, R/32}.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vaeassoc {
+
+namespace {
+
+constexpr int BM_CTA = 128;      // rows of the tile per CTA; UMMA M = 256 over the pair
+constexpr int BM = 2 * BM_CTA;
+constexpr int BK = 32;           // fp32 elements per stage = one 128-byte swizzle row
+constexpr int UMMA_K = 8;        // tf32: 32 bytes per instruction
+constexpr int kEpiWarps = 8;     // two warps per TMEM lane quarter, each takes every other 32-column chunk
+constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int kStages = 4;
+constexpr int A_BYTES = BM_CTA * BK * 4;          // 16 KB
+constexpr int B_BYTES_MAX = 128 * BK * 4;         // BN/2 <= 128 columns
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES_MAX;
+constexpr int CHUNK_BYTES = 32 * 32 * 4;          // one 32 x 32 fp32 epilogue box
+constexpr int EPI_WARP_BYTES = 3 * CHUNK_BYTES;   // 2 output staging buffers + 1 aux tile per epilogue warp
+constexpr int kAccCols = 256;                     // TMEM columns per accumulator
+constexpr int kTmemCols = 2 * kAccCols;
+constexpr int kSched = 8;                        // depth of the task-index ring
+constexpr int SMEM_BYTES = kStages * STAGE_BYTES + kEpiWarps * EPI_WARP_BYTES + 512 /*barriers, task ring*/ + 1024 /*align*/;
+static_assert(SMEM_BYTES <= 232448, "more than the 227 KB a CTA may opt into");
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of the same shared-memory offset in CTA `rank` of the cluster (shared::cluster window)
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// arrive on a barrier of any CTA of the cluster; release: orders this thread's earlier shared-memory writes
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+// no memory ordering (a release at cluster scope costs a MEMBAR.GPU + L1 invalidate); `dep` is a register the arrive
+// must wait for (e.g. the value just read from the slot this arrive hands back)
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t bar_cluster, uint32_t dep) {
+  asm volatile("{\n\t.reg .b32 dummy;\n\tmov.b32 dummy, %1;\n\t"
+               "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];\n\t}" ::"r"(bar_cluster), "r"(dep) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// acquire at cluster scope: the waiter reads shared memory written by the peer CTA before its arrive
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded waits: a protocol bug must surface as a launch failure, never as a hung GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
+    if (spins > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  for (uint32_t spins = 0; !mbar_try_wait_cluster(bar, parity); ++spins) {
+    if (spins > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_complete() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// arrives (once the MMAs issued so far have completed) on the barrier at this offset in both CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// publishes one word into the shared memory of a CTA of the cluster and completes 4 transaction bytes on that CTA's
+// barrier -- the data is visible to whoever observes the barrier phase (async proxy, like a TMA load): no fence needed
+__device__ __forceinline__ void st_async_u32(uint32_t addr_cluster, uint32_t v, uint32_t bar_cluster) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.u32 [%0], %1, [%2];"
+               ::"r"(addr_cluster), "r"(v), "r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_cluster_relaxed(uint32_t bar_cluster, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.relaxed.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(bar_cluster), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout): start [0,14) >>4, LBO [16,30) >>4,
+// SBO [32,46) >>4, version [46,48) = 1, layout_type [61,64): 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+__device__ __forceinline__ uint64_t desc_k_major(uint32_t addr) { return make_desc(addr, 16, 1024, 2); }
+__device__ __forceinline__ uint64_t desc_mn_major(uint32_t addr) { return make_desc(addr, BK * 128, 512, 1); }
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format [4,6)=1 (F32), a/b_format [7,10),[10,13)=2 (TF32),
+// a_major bit 15, b_major bit 16 (1 = MN-major), n_dim [17,23) = N>>3, m_dim [24,29) = M>>4
+__device__ __forceinline__ uint32_t make_idesc(int m, int n, bool a_mn, bool b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// byte offset of 16-byte chunk j of row r inside a 32 x 32 fp32 box written / read by TMA with SWIZZLE_128B
+__device__ __forceinline__ uint32_t swz(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
+
+}  // namespace
+
+// one dense-layer contraction; lives in global memory (the TMA unit reads the tensor maps from there)
+struct alignas(64) GProblem {
+  CUtensorMap map_a, map_b, map_c, map_aux;
+  int M, N, K, BN;           // output rows, output cols, contraction length, tile width (64, 128, 192 or 256)
+  int a_mn, b_mn;            // operand is MN-major (M / N index contiguous in HBM)
+  int reduce;                // epilogue adds into C (TMA reduce-add): wgrad tasks share an output tile
+  int act, round_out, has_aux;
+  int pad0, pad1;
+  const float* bias;
+  float* colsum;             // epilogue adds the column sums of its output tile here (bias gradient), or null
+};
+static_assert(sizeof(GProblem) % 64 == 0, "tensor maps must stay 64-byte aligned inside the array");
+
+// one output tile (256 x BN) of one problem over k-blocks [kb0, kb0 + nkb); 64 bytes, the problem's scalars are
+// repeated here so that a role needs ONE load per task (prefetched while the previous task runs)
+struct alignas(16) GTask {
+  int problem, m_blk, n_blk, kb0;
+  int nkb;
+  int wait_ctr, wait_cnt, wait_val;   // operands are ready once counters[wait_ctr .. +wait_cnt) have all reached wait_val
+  int wait2_ctr, wait2_val;           // a second counter (or -1)
+  int signal_ctr;                     // bumped by each of the 16 epilogue warps when the tile is globally visible, or -1
+  int bn;                             // tile width of the problem
+  int flags;                          // bit 0 a_mn, 1 b_mn, 2 reduce, 3 has_aux, 4 round_out, 5 colsum
+  int act, M, N;
+};
+static_assert(sizeof(GTask) == 64, "GTask is loaded as four 16-byte words");
+enum { TF_A_MN = 1, TF_B_MN = 2, TF_REDUCE = 4, TF_AUX = 8, TF_ROUND = 16, TF_COLSUM = 32 };
+
+namespace {
+
+__device__ __forceinline__ void wait_counter(const uint32_t* ctr, uint32_t need) {
+  const long long t0 = clock64();
+  while (ld_acquire_gpu(ctr) < need) {
+    __nanosleep(64);
+    if (clock64() - t0 > 4000000000ll) __trap();    // ~2 s: a scheduling bug must not hang the GPU
+  }
+}
+
+// one lane of the (converged) warp.  With `elect.sync` the compiler knows the guarded region runs on a single thread
+// and issues UTMALDG / UTMASTG / UTCHMMA straight from uniform registers; behind `if (lane == 0)` every such
+// instruction whose operands came from memory (task fields) was wrapped in an R2UR.BROADCAST waterfall loop
+// (~130 cycles per TMA issue: the producer needed 0.64 us per k-block instead of 0.4)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// value of lane 0 in every lane
+__device__ __forceinline__ int bcast(int v) { return __shfl_sync(0xffffffffu, v, 0); }
+
+__device__ __forceinline__ GTask load_task(const GTask* __restrict__ tasks, int t) {
+  GTask tk;
+  if (t >= 0) {
+    const int4* src = reinterpret_cast<const int4*>(tasks + t);
+    int4* dst = reinterpret_cast<int4*>(&tk);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dst[i] = __ldg(src + i);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) reinterpret_cast<int*>(&tk)[i] = 0;
+  }
+  return tk;
+}
+
+// the problems of one launch travel as a __grid_constant__ kernel parameter: the TMA unit fetches tensor maps from
+// param / const space through its descriptor cache; with the maps in plain global memory every cp.async.bulk.tensor
+// paid a descriptor fetch (~250 cycles, measured: 1 340 instead of 680 cycles per k-block)
+template <int NP>
+struct GParams { GProblem p[NP]; };
+
+template <int NP>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_group_kernel(const __grid_constant__ GParams<NP> params, const GTask* __restrict__ tasks, int ntasks,
+                  uint32_t* __restrict__ counters, uint32_t* __restrict__ queue, int reset_first, int reset_count,
+                  unsigned long long* __restrict__ tl) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t epi_base = base + kStages * STAGE_BYTES;
+  const uint32_t bar_base = epi_base + kEpiWarps * EPI_WARP_BYTES;
+  // barriers: full[s] (leader CTA only), empty[s], tmem_full[2], tmem_empty[2] (leader CTA only), aux[epilogue warp],
+  // sched_full[kSched], sched_empty[kSched] (leader CTA only); then the TMEM slot and the task-index ring
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
+  auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
+  auto aux_bar = [&](int e) { return bar_base + 8u * (2 * kStages + 4 + e); };
+  auto sched_full_bar = [&](int r) { return bar_base + 8u * (2 * kStages + 4 + kEpiWarps + r); };
+  auto sched_empty_bar = [&](int r) { return bar_base + 8u * (2 * kStages + 4 + kEpiWarps + kSched + r); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4 + kEpiWarps + 2 * kSched);
+  auto sched_task = [&](int r) { return tmem_slot + 8u + 4u * r; };
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  // consumers of a published task index: leader MMA lane + peer producer lane + 2 x kEpiWarps epilogue lanes
+  constexpr uint32_t kSchedConsumers = 2 + 2 * kEpiWarps;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), 2 * kEpiWarps); }
+    for (int e = 0; e < kEpiWarps; ++e) mbar_init(aux_bar(e), 1);
+    for (int r = 0; r < kSched; ++r) { mbar_init(sched_full_bar(r), 1); mbar_init(sched_empty_bar(r), kSchedConsumers); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair(tmem_slot, kTmemCols);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const unsigned long long t_entry = tl ? gtimer() : 0ull;
+
+  // consumer side of the task ring: next task index (or -1 when the queue is drained); one calling lane per role
+  uint32_t fetches = 0;
+  auto next_task = [&]() -> int {
+    const int r = (int)(fetches % kSched);
+    mbar_wait(sched_full_bar(r), (fetches / kSched) & 1);
+    const uint32_t t = lds_u32(sched_task(r));
+    mbar_arrive_cluster_relaxed(mapa(sched_empty_bar(r), 0), t);
+    ++fetches;
+    return (int)t;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs); the leader's is also the scheduler =====================
+    // the whole warp walks the loop (uniform control flow and operands); lane 0 waits and issues
+    uint32_t published = 0;
+    auto publish = [&](uint32_t idx) -> int {       // leader lane 0: hand task index `idx` to every role of the pair
+      const int t = idx < (uint32_t)ntasks ? (int)idx : -1;
+      const int r = (int)(published % kSched);
+      mbar_wait(sched_empty_bar(r), ((published / kSched) & 1) ^ 1);
+#pragma unroll
+      for (uint32_t cta = 0; cta < 2; ++cta) {
+        const uint32_t bar = mapa(sched_full_bar(r), cta);
+        mbar_arrive_expect_tx_cluster_relaxed(bar, 4u);
+        st_async_u32(mapa(sched_task(r), cta), (uint32_t)t, bar);
+      }
+      ++published;
+      return t;
+    };
+    // first task = the cluster's index (no atomic, no cluster starts with two); the next ones come from the queue,
+    // popped at the start of the running task and published once its first stages are in flight
+    const int nclusters = (int)(gridDim.x >> 1);
+    int t = ((int)(blockIdx.x >> 1) < ntasks) ? (int)(blockIdx.x >> 1) : -1;
+    if (lane == 0) {
+      if (rank == 0) publish((uint32_t)(t >= 0 ? t : ntasks)); else t = next_task();
+    }
+    t = bcast(t);
+    GTask tk = load_task(tasks, t);
+    uint32_t it = 0;                       // k-block counter across tasks: stage = it % kStages
+    const uint32_t full_leader0 = mapa(full_bar(0), 0);
+    while (t >= 0) {
+      uint32_t raw = 0;
+      if (lane == 0 && rank == 0) raw = atomicAdd(queue, 1u);      // consumed below, after the first loads are issued
+      const GProblem* p = &params.p[tk.problem];
+      const int BN = tk.bn, BNH = BN >> 1;
+      const bool a_mn = (tk.flags & TF_A_MN) != 0, b_mn = (tk.flags & TF_B_MN) != 0;
+      const int m0 = tk.m_blk * BM + (int)rank * BM_CTA;      // this CTA's rows of A
+      const int nb0 = tk.n_blk * BN + (int)rank * BNH;        // this CTA's slice of B
+      const uint32_t stage_tx = 2u * (A_BYTES + (uint32_t)BNH * BK * 4);
+      if (lane == 0) {
+        if (tk.wait_cnt > 0 || tk.wait2_ctr >= 0) {
+          for (int c = 0; c < tk.wait_cnt; ++c) wait_counter(counters + tk.wait_ctr + c, (uint32_t)tk.wait_val);
+          if (tk.wait2_ctr >= 0) wait_counter(counters + tk.wait2_ctr, (uint32_t)tk.wait2_val);
+          fence_proxy_async_all();           // the producing tasks' TMA stores -> our TMA loads
+        }
+        if (tl && rank == 0) { tl[8 * t + 0] = gtimer(); tl[8 * t + 5] = blockIdx.x >> 1; tl[8 * t + 6] = t_entry; }
+      }
+      __syncwarp();
+      int t_after = -1;
+      const int announce = min(tk.nkb, kStages) - 1;
+      for (int i = 0; i < tk.nkb; ++i, ++it) {
+        const int s = (int)(it % kStages);
+        const uint32_t sa = base + s * STAGE_BYTES, sb = sa + A_BYTES;
+        const uint32_t full_leader = full_leader0 + 8u * s;
+        const int k0 = (tk.kb0 + i) * BK;
+        if (elect_one()) {
+          mbar_wait(empty_bar(s), ((it / kStages) & 1) ^ 1);
+          if (tl && t == 0 && i < 64) tl[8 * ntasks + (rank ? 128 : 0) + i] = gtimer();
+          if (rank == 0) mbar_arrive_expect_tx(full_bar(s), stage_tx);
+          // MN-major operands: one 3-D box {32 mn, 32 k, chunks} lands as [chunk][k][32 mn] (see make_map_mn)
+          if (a_mn) tma_load_3d_pair(sa, &p->map_a, full_leader, 0, k0, m0 >> 5);
+          else tma_load_2d_pair(sa, &p->map_a, full_leader, k0, m0);
+          if (b_mn) tma_load_3d_pair(sb, &p->map_b, full_leader, 0, k0, nb0 >> 5);
+          else tma_load_2d_pair(sb, &p->map_b, full_leader, k0, nb0);
+          if (i == announce)                 // the next task: known to every role while this one streams
+            t_after = (rank == 0) ? publish((uint32_t)nclusters + raw) : next_task();
+        }
+        __syncwarp();
+      }
+      t = bcast(t_after);
+      tk = load_task(tasks, t);
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA): whole warp walks, lane 0 waits and issues =====================
+    if (rank == 0) {
+      uint32_t it = 0, tcount = 0;
+      int t = 0;
+      if (lane == 0) t = next_task();
+      t = bcast(t);
+      GTask tk = load_task(tasks, t);
+      for (; t >= 0; ++tcount) {
+        int t_after = -1;
+        const int announce = min(tk.nkb, kStages) - 1;   // the producer publishes the next task at this k-block
+        const bool a_mn = (tk.flags & TF_A_MN) != 0, b_mn = (tk.flags & TF_B_MN) != 0;
+        const uint32_t idesc = make_idesc(BM, tk.bn, a_mn, b_mn);
+        const uint32_t acc = tcount & 1;
+        const uint32_t tmem_d = tmem_base + acc * kAccCols;
+        if (lane == 0) {
+          mbar_wait(tmem_empty_bar(acc), ((tcount >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator
+          tc_fence_after();
+          if (tl) { tl[8 * t + 1] = gtimer(); tl[8 * t + 7] = clock64(); }
+        }
+        __syncwarp();
+        for (int i = 0; i < tk.nkb; ++i, ++it) {
+          const int s = (int)(it % kStages);
+          const uint32_t sa = base + s * STAGE_BYTES, sb = sa + A_BYTES;
+          if (elect_one()) {
+            mbar_wait(full_bar(s), (it / kStages) & 1);
+            tc_fence_after();
+            if (tl && t == 0 && i < 64) tl[8 * ntasks + 64 + i] = gtimer();
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t da = a_mn ? desc_mn_major(sa + k * 1024) : desc_k_major(sa + k * 32);
+              const uint64_t db = b_mn ? desc_mn_major(sb + k * 1024) : desc_k_major(sb + k * 32);
+              umma_tf32_pair(tmem_d, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit_pair(empty_bar(s));     // frees the smem slot in both CTAs once these MMAs have read it
+            if (i == announce) t_after = next_task();
+          }
+          __syncwarp();
+        }
+        if (elect_one()) {
+          umma_commit_pair(tmem_full_bar(acc)); // accumulator complete (both CTAs)
+          if (tl) { tl[8 * t + 2] = gtimer(); tl[8 * t + 7] = clock64() - tl[8 * t + 7]; }
+        }
+        t = bcast(t_after);
+        tk = load_task(tasks, t);
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..9 of both CTAs) =====================
+    const int e = warp - 2;                 // epilogue warp index
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = e >> 2;                // this warp takes chunks half, half + 2, ...
+    const uint32_t out_buf = epi_base + e * EPI_WARP_BYTES;      // 2 x 4 KB staging for the bulk stores
+    const uint32_t aux_buf = out_buf + 2 * CHUNK_BYTES;          // 4 KB aux tile
+    const uint32_t tmem_empty_leader0 = mapa(tmem_empty_bar(0), 0), tmem_empty_leader1 = mapa(tmem_empty_bar(1), 0);
+    uint32_t tcount = 0, aux_uses = 0, stores = 0;
+    auto next_task_warp = [&]() -> int {
+      int t = 0;
+      if (lane == 0) t = next_task();
+      return __shfl_sync(0xffffffffu, t, 0);
+    };
+    int t = next_task_warp();
+    GTask tk = load_task(tasks, t);
+    for (; t >= 0; ++tcount) {
+      const int t_after = next_task_warp();
+      const GTask tk_after = load_task(tasks, t_after);
+      const GProblem* p = &params.p[tk.problem];
+      const int BN = tk.bn, N = tk.N, act = tk.act;
+      const bool reduce = (tk.flags & TF_REDUCE) != 0, use_aux = (tk.flags & TF_AUX) != 0, round_out = (tk.flags & TF_ROUND) != 0;
+      const float* __restrict__ bias = p->bias;
+      float* __restrict__ colsum = (tk.flags & TF_COLSUM) ? p->colsum : nullptr;
+      const int row0 = tk.m_blk * BM + (int)rank * BM_CTA + q * 32;    // first output row of this warp
+      const int n0 = tk.n_blk * BN;
+      const int nchunks = (row0 < tk.M) ? min(BN / 32, (N - n0 + 31) / 32) : 0;   // warp-uniform
+      const uint32_t acc = tcount & 1;
+      if (use_aux && half < nchunks && elect_one()) {           // first aux tile: in flight during the main loop
+        mbar_arrive_expect_tx(aux_bar(e), CHUNK_BYTES);
+        tma_load_2d(aux_buf, &p->map_aux, aux_bar(e), n0 + half * 32, row0);
+      }
+      mbar_wait(tmem_full_bar(acc), (tcount >> 1) & 1);
+      tc_fence_after();
+      if (tl && rank == 0 && warp == 2 && lane == 0) tl[8 * t + 3] = gtimer();
+#pragma unroll 1
+      for (int c = half; c < nchunks; c += 2) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + acc * kAccCols + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+        float x[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+        if (use_aux) {
+          mbar_wait(aux_bar(e), aux_uses & 1);
+          ++aux_uses;
+          float h[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 hv = lds128(aux_buf + swz(lane, j));
+            h[4 * j] = hv.x; h[4 * j + 1] = hv.y; h[4 * j + 2] = hv.z; h[4 * j + 3] = hv.w;
+          }
+          __syncwarp();                                          // every lane has read the tile: refill it
+          if (c + 2 < nchunks && elect_one()) {
+            mbar_arrive_expect_tx(aux_bar(e), CHUNK_BYTES);
+            tma_load_2d(aux_buf, &p->map_aux, aux_bar(e), n0 + (c + 2) * 32, row0);
+          }
+          switch (act) {
+            case ACT_RELU:
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] = h[j] > 0.0f ? x[j] : 0.0f;
+              break;
+            case ACT_SOFTPLUS:
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] *= 1.0f - __expf(-h[j]);
+              break;
+            case ACT_SIGMOID:
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] *= h[j] * (1.0f - h[j]);
+              break;
+            default: break;
+          }
+        } else if (!reduce) {
+          if (bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int col = n0 + c * 32 + j * 4;
+              if (col < N) {                                     // bias rows are padded to 4 floats
+                const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + col));
+                x[4 * j] += bv.x; x[4 * j + 1] += bv.y; x[4 * j + 2] += bv.z; x[4 * j + 3] += bv.w;
+              }
+            }
+          }
+          switch (act) {
+            case ACT_RELU:
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.0f);
+              break;
+            case ACT_SOFTPLUS:
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.0f) + __logf(1.0f + __expf(-fabsf(x[j])));
+              break;
+            case ACT_SIGMOID:
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] = __fdividef(1.0f, 1.0f + __expf(-x[j]));
+              break;
+            default: break;
+          }
+        }
+        if (round_out) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = round_tf32(x[j]);
+        }
+        if (n0 + c * 32 + 32 > N) {        // TMA clips stores in 16-byte units: the pad columns N..roundup4(N) get zeros
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = (n0 + c * 32 + j < N) ? x[j] : 0.0f;
+        }
+        // staging buffer (stores & 1) was handed to the bulk store two chunks ago: wait until that store has read it
+        if (elect_one()) bulk_wait_read<1>();
+        __syncwarp();
+        const uint32_t ob = out_buf + (stores & 1) * CHUNK_BYTES;
+        ++stores;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sts128(ob + swz(lane, j), x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (elect_one()) {
+          if (reduce) tma_reduce_add_2d(&p->map_c, ob, n0 + c * 32, row0);
+          else tma_store_2d(&p->map_c, ob, n0 + c * 32, row0);
+          bulk_commit();
+        }
+        if (colsum != nullptr) {
+          // bias gradient of the layer below = column sums of this dgrad output: lane <-> column, 32 conflict-free
+          // reads of the staged tile (rows past M hold exact zeros), one fp32 RED per column and warp
+          float cs = 0.0f;
+#pragma unroll
+          for (int r = 0; r < 32; ++r) {
+            float v1;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v1) : "r"(ob + swz(r, lane >> 2) + (uint32_t)(lane & 3) * 4u));
+            cs += v1;
+          }
+          const int col = n0 + c * 32 + lane;
+          if (col < N) atomicAdd(colsum + col, cs);
+        }
+      }
+      // every tcgen05.ld of this accumulator has completed (wait::ld): hand it back to the MMA issuer
+      tc_fence_before();
+      __syncwarp();
+      if (elect_one()) {
+        mbar_arrive_cluster_relaxed(acc ? tmem_empty_leader1 : tmem_empty_leader0, 0u);
+        if (tk.signal_ctr >= 0) {
+          bulk_wait_complete();            // this warp's stores are performed, then publish (release, gpu scope)
+          fence_proxy_async_all();
+          red_release_gpu_add(counters + tk.signal_ctr, 1u);
+        }
+      }
+      if (tl && rank == 0 && warp == 2 && lane == 0) tl[8 * t + 4] = gtimer();
+      t = t_after;
+      tk = tk_after;
+    }
+    if (elect_one()) bulk_wait_read<0>();   // shared memory must outlive the reads of the bulk stores
+  }
+  tc_fence_before();
+  cluster_sync_all();     // the peer's smem / barriers stay valid until every MMA and every TMA of the pair is done
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, kTmemCols);
+  }
+  // self-cleaning: the last cluster to leave rewinds the queue and the row-block counters this launch used, so the
+  // next launch (next step / next graph replay) needs no memset
+  __shared__ uint32_t s_last;
+  if (threadIdx.x == 0) {
+    uint32_t last = 0;
+    if (rank == 0) {
+      __threadfence();
+      last = (atomicAdd(queue + 1, 1u) == (gridDim.x >> 1) - 1) ? 1u : 0u;
+    }
+    s_last = last;
+  }
+  __syncthreads();
+  if (s_last) {
+    for (int i = threadIdx.x; i < reset_count; i += kThreads) counters[reset_first + i] = 0u;
+    if (threadIdx.x == 0) { queue[0] = 0u; queue[1] = 0u; }
+    __threadfence();
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor map: dim0 (contiguous) x dim1 with row pitch `ld` floats, box {32, box_rows}
+bool make_map(CUtensorMap* map, const float* ptr, int64_t dim0, int64_t dim1, int64_t ld, int box_rows, bool atom32,
+              char* err, int errlen) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { snprintf(err, errlen, "cuTensorMapEncodeTiled entry point not available"); return false; }
+  cuuint64_t dims[2] = {(cuuint64_t)dim0, (cuuint64_t)dim1};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(err, errlen, "cuTensorMapEncodeTiled failed (%d) ptr=%p dims=%lld x %lld ld=%lld box_rows=%d", (int)r,
+             (const void*)ptr, (long long)dim0, (long long)dim1, (long long)ld, box_rows);
+    return false;
+  }
+  return true;
+}
+
+// MN-major operand [dim_k rows, dim_mn contiguous] as a 3-D tensor {32, dim_k, ceil(dim_mn / 32)}: element (x, k, c) =
+// ptr[k * ld + 32 c + x].  The last chunk's x >= dim_mn - 32 c reads the first floats of the next row (or up to 124 B
+// past the last row: every buffer of the library carries that slack); those lanes only feed output rows / columns
+// past M / N, which the epilogue masks and the TMA store clips.  Rows k >= dim_k and chunks past the end are zero-filled.
+bool make_map_mn(CUtensorMap* map, const float* ptr, int64_t dim_mn, int64_t dim_k, int64_t ld, int chunks, char* err,
+                 int errlen) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { snprintf(err, errlen, "cuTensorMapEncodeTiled entry point not available"); return false; }
+  cuuint64_t dims[3] = {32u, (cuuint64_t)dim_k, (cuuint64_t)((dim_mn + 31) / 32)};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 4, 128u};
+  cuuint32_t box[3] = {32u, 32u, (cuuint32_t)chunks};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(err, errlen, "cuTensorMapEncodeTiled (3-D) failed (%d) ptr=%p mn=%lld k=%lld ld=%lld chunks=%d", (int)r,
+             (const void*)ptr, (long long)dim_mn, (long long)dim_k, (long long)ld, chunks);
+    return false;
+  }
+  return true;
+}
+
+}  // namespace
+
+// ---- group plan: the problems / tasks of a handle, cut into launch sites ---------------------------------------------
+constexpr int kSiteProblemsSmall = 2, kSiteProblemsLarge = 24;
+
+struct GroupSite { int first_problem = 0, n_problems = 0, first_task = 0, n_tasks = 0; };
+
+struct GroupPlan {
+  std::vector<GProblem> problems;
+  std::vector<GTask> tasks;          // .problem is relative to the site's first problem once the site is closed
+  std::vector<GroupSite> sites;
+  bool open = false;
+  GTask* d_tasks = nullptr;
+  uint32_t* d_counters = nullptr;    // row-block completion counters of the step (not owned; self-cleaning)
+  int n_counters = 0;
+  bool uploaded = false;
+};
+
+GroupPlan* group_create() { return new GroupPlan(); }
+
+void group_destroy(GroupPlan* g) {
+  if (!g) return;
+  if (g->d_tasks) cudaFree(g->d_tasks);
+  delete g;
+}
+
+// opens a launch site: the problems / tasks added until group_end() run as ONE kernel launch
+int group_begin(GroupPlan* g) {
+  GroupSite st;
+  st.first_problem = (int)g->problems.size();
+  st.first_task = (int)g->tasks.size();
+  g->sites.push_back(st);
+  g->open = true;
+  return (int)g->sites.size() - 1;
+}
+
+bool group_end(GroupPlan* g, char* err, int errlen) {
+  GroupSite& st = g->sites.back();
+  st.n_problems = (int)g->problems.size() - st.first_problem;
+  st.n_tasks = (int)g->tasks.size() - st.first_task;
+  g->open = false;
+  if (st.n_problems > kSiteProblemsLarge) {
+    snprintf(err, errlen, "a launch site holds %d contractions, at most %d fit the kernel parameter", st.n_problems, kSiteProblemsLarge);
+    return false;
+  }
+  for (int i = 0; i < st.n_tasks; ++i) g->tasks[st.first_task + i].problem -= st.first_problem;
+  return true;
+}
+
+int group_site_tasks(const GroupPlan* g, int site) { return g->sites[site].n_tasks; }
+
+bool tc_supported(int kind, const GemmArgs& a) {
+  if (!a.A || !a.B || !a.C) return false;
+  if ((reinterpret_cast<uintptr_t>(a.A) & 15) || (reinterpret_cast<uintptr_t>(a.B) & 15) ||
+      (reinterpret_cast<uintptr_t>(a.C) & 15))
+    return false;
+  if ((a.lda & 3) || (a.ldb & 3) || (a.ldc & 3)) return false;
+  if (a.aux && ((reinterpret_cast<uintptr_t>(a.aux) & 15) || (a.ldaux & 3))) return false;
+  if (a.bias && (reinterpret_cast<uintptr_t>(a.bias) & 15)) return false;
+  // every contraction whose batch extent fills a tile row block runs here, including the n_z-wide ones (heads,
+  // decoder input layer): those are HBM-bound and the TMA pipeline streams the one large operand exactly once;
+  // out-of-range rows / columns of the narrow operand are zero-filled by TMA at no HBM cost
+  const int batch = (kind == 2) ? a.K : a.M;
+  return batch >= 32;
+}
+
+int group_tile_width(int N) {
+  const int tiles_n = (N + 255) / 256;
+  return std::min(256, (((N + tiles_n - 1) / tiles_n) + 63) / 64 * 64);
+}
+
+// adds the contraction to the plan; returns its problem index or -1 (err filled)
+int group_add_problem(GroupPlan* g, int kind, const GemmArgs& a, char* err, int errlen) {
+  GProblem p;
+  memset(&p, 0, sizeof p);
+  const int BN = group_tile_width(a.N);
+  bool ok = true;
+  switch (kind) {
+    case 0:    // NN: A [M,K] K-major ; B [K,N] MN-major
+      ok = make_map(&p.map_a, a.A, a.K, a.M, a.lda, BM_CTA, false, err, errlen) &&
+           make_map_mn(&p.map_b, a.B, a.N, a.K, a.ldb, BN / 64, err, errlen);
+      p.a_mn = 0; p.b_mn = 1;
+      break;
+    case 1:    // NT: A [M,K] K-major ; B [N,K] K-major
+      ok = make_map(&p.map_a, a.A, a.K, a.M, a.lda, BM_CTA, false, err, errlen) &&
+           make_map(&p.map_b, a.B, a.K, a.N, a.ldb, BN / 2, false, err, errlen);
+      p.a_mn = 0; p.b_mn = 0;
+      break;
+    default:   // TN: A [K,M] MN-major ; B [K,N] MN-major
+      ok = make_map_mn(&p.map_a, a.A, a.M, a.K, a.lda, BM_CTA / 32, err, errlen) &&
+           make_map_mn(&p.map_b, a.B, a.N, a.K, a.ldb, BN / 64, err, errlen);
+      p.a_mn = 1; p.b_mn = 1;
+      break;
+  }
+  ok = ok && make_map(&p.map_c, a.C, a.N, a.M, a.ldc, 32, false, err, errlen);
+  const bool has_aux = kind != 2 && a.aux != nullptr;
+  if (ok && has_aux) ok = make_map(&p.map_aux, a.aux, a.N, a.M, a.ldaux, 32, false, err, errlen);
+  else if (ok) p.map_aux = p.map_c;
+  if (!ok) return -1;
+  p.M = a.M; p.N = a.N; p.K = a.K; p.BN = BN;
+  p.reduce = (kind == 2) ? 1 : 0;
+  p.act = a.act; p.round_out = a.round_out; p.has_aux = has_aux ? 1 : 0;
+  p.bias = (kind == 0) ? a.bias : nullptr;
+  p.colsum = (kind != 2) ? a.bias_grad : nullptr;   // NN / NT: bias_grad = where the column sums of C go
+  g->problems.push_back(p);
+  g->uploaded = false;
+  return (int)g->problems.size() - 1;
+}
+
+int group_problem_tiles_m(const GroupPlan* g, int prob) { return (g->problems[prob].M + BM - 1) / BM; }
+int group_problem_tiles_n(const GroupPlan* g, int prob) { const GProblem& p = g->problems[prob]; return (p.N + p.BN - 1) / p.BN; }
+int group_problem_kblocks(const GroupPlan* g, int prob) { return (g->problems[prob].K + BK - 1) / BK; }
+
+int group_add_task(GroupPlan* g, int prob, int m_blk, int n_blk, int kb0, int nkb, int wait_ctr, int wait_cnt,
+                   int wait_val, int wait2_ctr, int wait2_val, int signal_ctr) {
+  const GProblem& p = g->problems[prob];
+  GTask t;
+  memset(&t, 0, sizeof t);
+  t.problem = prob; t.m_blk = m_blk; t.n_blk = n_blk; t.kb0 = kb0; t.nkb = nkb;
+  t.wait_ctr = wait_ctr; t.wait_cnt = wait_cnt; t.wait_val = wait_val;
+  t.wait2_ctr = wait2_ctr; t.wait2_val = wait2_val; t.signal_ctr = signal_ctr;
+  t.bn = p.BN;
+  t.flags = (p.a_mn ? TF_A_MN : 0) | (p.b_mn ? TF_B_MN : 0) | (p.reduce ? TF_REDUCE : 0) | (p.has_aux ? TF_AUX : 0) |
+            (p.round_out ? TF_ROUND : 0) | (p.colsum ? TF_COLSUM : 0);
+  t.act = p.act; t.M = p.M; t.N = p.N;
+  g->tasks.push_back(t);
+  g->uploaded = false;
+  return (int)g->tasks.size() - 1;
+}
+
+int group_num_tasks(const GroupPlan* g) { return (int)g->tasks.size(); }
+
+void group_set_counters(GroupPlan* g, uint32_t* d_counters, int n) { g->d_counters = d_counters; g->n_counters = n; }
+
+bool group_upload(GroupPlan* g, char* err, int errlen) {
+  if (g->uploaded) return true;
+  if (g->d_tasks) { cudaFree(g->d_tasks); g->d_tasks = nullptr; }
+  if (g->tasks.empty()) { g->uploaded = true; return true; }
+  cudaError_t e = cudaMalloc(&g->d_tasks, g->tasks.size() * sizeof(GTask));
+  if (e == cudaSuccess) e = cudaMemcpy(g->d_tasks, g->tasks.data(), g->tasks.size() * sizeof(GTask), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    static bool attr_done = false;
+    if (!attr_done) {
+      e = cudaFuncSetAttribute(gemm_group_kernel<kSiteProblemsSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(gemm_group_kernel<kSiteProblemsLarge>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+      attr_done = (e == cudaSuccess);
+    }
+  }
+  if (e != cudaSuccess) { snprintf(err, errlen, "group upload failed: %s", cudaGetErrorString(e)); return false; }
+  g->uploaded = true;
+  return true;
+}
+
+namespace {
+void launch_site(const GroupPlan* g, int site, uint32_t* queue, int reset_first, int reset_count, unsigned long long* tl,
+                 cudaStream_t s) {
+  const GroupSite& st = g->sites[site];
+  if (st.n_tasks <= 0) return;
+  const int clusters = std::min(st.n_tasks, kNumSMs / 2);
+  if (st.n_problems <= kSiteProblemsSmall) {
+    GParams<kSiteProblemsSmall> prm;
+    memcpy(prm.p, g->problems.data() + st.first_problem, (size_t)st.n_problems * sizeof(GProblem));
+    gemm_group_kernel<kSiteProblemsSmall><<<2 * clusters, kThreads, SMEM_BYTES, s>>>(
+        prm, g->d_tasks + st.first_task, st.n_tasks, g->d_counters, queue, reset_first, reset_count, tl);
+  } else {
+    GParams<kSiteProblemsLarge> prm;
+    memcpy(prm.p, g->problems.data() + st.first_problem, (size_t)st.n_problems * sizeof(GProblem));
+    gemm_group_kernel<kSiteProblemsLarge><<<2 * clusters, kThreads, SMEM_BYTES, s>>>(
+        prm, g->d_tasks + st.first_task, st.n_tasks, g->d_counters, queue, reset_first, reset_count, tl);
+  }
+}
+}  // namespace
+
+// launches a site; the grid is one CTA pair per TPC at most.  `queue` = two zero-initialised words owned by this
+// launch site (task-queue head, clusters-left count; the kernel rewinds them and the counters
+// [reset_first, +reset_count) when its last cluster leaves)
+void group_launch(const GroupPlan* g, int site, uint32_t* queue, int reset_first, int reset_count, cudaStream_t s) {
+  launch_site(g, site, queue, reset_first, reset_count, nullptr, s);
+}
+
+// debug only (VAEASSOC_TC_TIMELINE): one more run of the range with %globaltimer stamps per task; prints, relative to
+// the first cluster's entry (ns): producer start, MMA start, MMA done, epilogue start, epilogue end, cluster
+void group_debug_timeline(const GroupPlan* g, int site, uint32_t* queue, int reset_first, int reset_count, cudaStream_t s) {
+  const int first = g->sites[site].first_task, count = g->sites[site].n_tasks;
+  if (count <= 0) return;
+  unsigned long long* dev = nullptr;
+  if (cudaMalloc(&dev, (size_t)count * 64 + 192 * 8) != cudaSuccess) return;
+  cudaMemsetAsync(dev, 0, (size_t)count * 64 + 192 * 8, s);
+  const int clusters = std::min(count, kNumSMs / 2);
+  launch_site(g, site, queue, reset_first, reset_count, dev, s);
+  cudaStreamSynchronize(s);
+  std::vector<unsigned long long> h((size_t)count * 8 + 192);
+  cudaMemcpy(h.data(), dev, (size_t)count * 64 + 192 * 8, cudaMemcpyDeviceToHost);
+  cudaFree(dev);
+  unsigned long long t0 = ~0ull, t1 = 0;
+  for (int i = 0; i < count; ++i) { t0 = std::min(t0, h[8 * i + 6]); t1 = std::max(t1, h[8 * i + 4]); }
+  fprintf(stderr, "[group timeline] %d tasks on %d clusters, %.1f us from first entry to last epilogue end\n", count, clusters,
+          (t1 - t0) * 1e-3);
+  {
+    const int nk = std::min(g->tasks[first].nkb, 64);
+    fprintf(stderr, "  task 0 k-blocks (us): leader issue | peer issue | full seen by MMA\n   ");
+    for (int i = 0; i < nk; ++i)
+      fprintf(stderr, " %d: %.2f|%.2f|%.2f", i, (h[8 * count + i] - t0) * 1e-3, (h[8 * count + 128 + i] - t0) * 1e-3,
+              (h[8 * count + 64 + i] - t0) * 1e-3);
+    fprintf(stderr, "\n");
+  }
+  const int show = getenv("VAEASSOC_TC_TIMELINE_ALL") ? count : std::min(count, 12);
+  for (int k = 0; k < show; ++k) {
+    const int i = (k < show / 2 || show == count) ? k : count - (show - k);
+    const GTask& tk = g->tasks[first + i];
+    fprintf(stderr, "  task %4d prob %2d (%2d,%2d) nkb %3d cl %2llu entry %6.2f | prod %6.2f mma %6.2f..%6.2f (%llu cyc) epi %6.2f..%6.2f us\n", i,
+            tk.problem, tk.m_blk, tk.n_blk, tk.nkb, h[8 * i + 5], (h[8 * i + 6] - t0) * 1e-3, (h[8 * i + 0] - t0) * 1e-3,
+            (h[8 * i + 1] - t0) * 1e-3, (h[8 * i + 2] - t0) * 1e-3, h[8 * i + 7], (h[8 * i + 3] - t0) * 1e-3, (h[8 * i + 4] - t0) * 1e-3);
+  }
+}
+
+}  // namespace vaeassoc

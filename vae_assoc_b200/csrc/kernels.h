@@ -35,14 +35,33 @@ void launch_colsum(const float* X, int64_t ld, int rows, int cols, float* out, c
 bool skinny_supported(int kind /*0 NN,1 NT,2 TN*/, const GemmArgs& a);
 void launch_gemm_skinny(int kind, const GemmArgs& a, cudaStream_t s);
 
-// tcgen05 / TMA path (gemm_tc.cu).  Returns false if the shape cannot be served (caller falls back to SIMT
-// *kernels of this library*, never to a CPU or a vendor library).
-struct TcPlan;   // opaque: tensor maps + grid for one GEMM call site, built once at handle creation
-TcPlan* tc_plan_create(int kind /*0 NN,1 NT,2 TN*/, const GemmArgs& a, char* err, int errlen);
-void tc_plan_destroy(TcPlan* p);
-void launch_gemm_tc(const TcPlan* p, cudaStream_t s);
-void tc_debug_timeline(TcPlan* p, cudaStream_t s);   // debug: per-CTA phase stamps to stderr
-bool tc_supported(int kind, const GemmArgs& a);
+// tcgen05 / TMA path (gemm_group.cu): a persistent kernel that executes a list of 256 x BN tile tasks drawn from
+// several contractions ("problems"), ordered by dependency and linked by row-block completion counters.  A plan owns
+// the problems / tasks of one handle; a launch runs a contiguous task range.  Shapes the path cannot serve fall back
+// to the SIMT *kernels of this library*, never to a CPU or a vendor library.
+struct GroupPlan;
+bool tc_supported(int kind /*0 NN,1 NT,2 TN*/, const GemmArgs& a);
+GroupPlan* group_create();
+void group_destroy(GroupPlan* g);
+int group_add_problem(GroupPlan* g, int kind, const GemmArgs& a, char* err, int errlen);   // problem index or -1
+int group_problem_tiles_m(const GroupPlan* g, int prob);
+int group_problem_tiles_n(const GroupPlan* g, int prob);
+int group_problem_kblocks(const GroupPlan* g, int prob);      // k-blocks of 32
+// operands ready when counters[wait_ctr .. +wait_cnt) >= wait_val (and counters[wait2_ctr] >= wait2_val); every
+// epilogue warp (16 per tile) bumps counters[signal_ctr] once the tile is globally visible; -1 / 0 = none
+int group_add_task(GroupPlan* g, int prob, int m_blk, int n_blk, int kb0, int nkb, int wait_ctr, int wait_cnt,
+                   int wait_val, int wait2_ctr, int wait2_val, int signal_ctr);
+int group_num_tasks(const GroupPlan* g);
+// a launch site = the problems / tasks added between group_begin() and group_end(): ONE kernel launch (<= 24 problems)
+int group_begin(GroupPlan* g);
+bool group_end(GroupPlan* g, char* err, int errlen);
+int group_site_tasks(const GroupPlan* g, int site);
+void group_set_counters(GroupPlan* g, uint32_t* d_counters, int n);
+bool group_upload(GroupPlan* g, char* err, int errlen);
+void group_launch(const GroupPlan* g, int site, uint32_t* queue, int reset_first, int reset_count, cudaStream_t s);
+void group_debug_timeline(const GroupPlan* g, int site, uint32_t* queue, int reset_first, int reset_count,
+                          cudaStream_t s);   // debug: per-task %globaltimer stamps to stderr
+constexpr int kGroupSignalsPerTile = 16;   // epilogue warps of a CTA pair
 
 // ------------------------------------------------------------------------------------------------------
 // conv / transposed-conv layers of the hidden_conv=True modality as im2col -> GEMM -> col2im (conv.cu)
