@@ -101,6 +101,9 @@ struct Mod {               // one modality (dense variant)
         *dh2 = nullptr, *dh1 = nullptr, *gstat = nullptr, *lat_loss = nullptr, *rec_loss = nullptr,
         *partials = nullptr;
   int recon_blocks = 0;
+  // relu sign masks of h1, h2, g1, g2 (one bit per element, [B, ceil(width / 32)] words): written by the tcgen05 forward
+  // epilogues, read by the dgrad epilogues in place of the fp32 activation tile
+  uint32_t *mh1 = nullptr, *mh2 = nullptr, *mg1 = nullptr, *mg2 = nullptr;
   // ---- hidden_conv=True variant (vae_assoc.py:169-199,249-291; deconv.py) -------------------------------------
   bool conv = false;
   int s0 = 0, s1 = 0, s2 = 0, s3 = 0;        // encoder spatial sizes 28 -> 14 -> 7 -> 3
@@ -379,6 +382,10 @@ void alloc_buffers(Ctx* c) {
     d.lat_loss = c->dalloc<float>(B);    d.rec_loss = c->dalloc<float>(B);
     d.partials = c->dalloc<float>((int64_t)kMaxPartialBlocks * kCostSlots);
     d.P = c->dalloc<float>(4 * d.ni);    d.inv_std = c->dalloc<float>(d.ni);
+    if (!d.conv) {
+      d.mh1 = c->dalloc<uint32_t>(B * ((d.r1 + 31) / 32)); d.mg1 = c->dalloc<uint32_t>(B * ((d.r1 + 31) / 32));
+      d.mh2 = c->dalloc<uint32_t>(B * ((d.r2 + 31) / 32)); d.mg2 = c->dalloc<uint32_t>(B * ((d.r2 + 31) / 32));
+    }
     if (d.conv) {
       const int64_t n1 = B * d.s1 * d.s1, n2 = B * d.s2 * d.s2, n3 = B * d.s3 * d.s3;       // encoder rows
       const int64_t m1 = B * d.t1 * d.t1, m2 = B * d.t2 * d.t2, m3 = B * d.t3 * d.t3;       // decoder rows (per input pixel)
@@ -674,6 +681,16 @@ void build_ops(Ctx* c) {
       if (w_off >= 0) a.B = c->p_tf32 + w_off;
       return tf32 && tc_supported(kind, a);
     };
+    if (f == ACT_RELU && tc(KIND_NN, f_e1, d.W1) && tc(KIND_NN, f_e2, d.W2) && tc(KIND_NN, f_d1, d.V1) && tc(KIND_NN, f_d2, d.V2) &&
+        tc(KIND_NT, d_o, d.Vo) && tc(KIND_NT, d_d2, d.V2) && tc(KIND_NT, d_hd, d.Wh) && tc(KIND_NT, d_e2, d.W2) &&
+        !getenv("VAEASSOC_NO_MASK")) {
+      // relu' needs one bit per element: producers (forward) and consumers (dgrad) are all tcgen05 tasks
+      const int64_t w1 = (d.r1 + 31) / 32, w2 = (d.r2 + 31) / 32;
+      f_e1.mask_out = d.mh1; f_e1.ldmask = w1;  d_e2.mask_in = d.mh1; d_e2.ldmask = w1;
+      f_e2.mask_out = d.mh2; f_e2.ldmask = w2;  d_hd.mask_in = d.mh2; d_hd.ldmask = w2;
+      f_d1.mask_out = d.mg1; f_d1.ldmask = w1;  d_d2.mask_in = d.mg1; d_d2.ldmask = w1;
+      f_d2.mask_out = d.mg2; f_d2.ldmask = w2;  d_o.mask_in = d.mg2;  d_o.ldmask = w2;
+    }
     const bool r_h1 = tc(KIND_NN, f_e2, d.W2) || tc(KIND_TN, w_e2, -1);
     const bool r_h2 = tc(KIND_NN, f_hd, d.Wh) || tc(KIND_TN, w_hd, -1);
     const bool r_g1 = tc(KIND_NN, f_d2, d.V2) || tc(KIND_TN, w_d2, -1);

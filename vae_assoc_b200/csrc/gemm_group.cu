@@ -23,9 +23,11 @@
 //              task index through a 4-slot ring (shared memory of both CTAs, mbarrier full / empty) to every role
 //   warp 1     leader CTA: MMA issuer; accumulators double-buffered in TMEM (2 x 256 columns) so the epilogue of
 //              task i overlaps the main loop of task i+1; `tcgen05.commit` multicasts to both CTAs
-//   warps 2-9  epilogue: tcgen05.ld (thread = row, 32 columns) -> bias / activation / act'(aux tile via TMA) ->
-//              swizzled smem staging -> TMA store (NN, NT) or TMA reduce-add (TN); then release the accumulator
-//              and, once the stores are complete, bump the task's counter (release, gpu scope)
+//   warps 2-9  epilogue: tcgen05.ld (thread = row, 32 columns) -> bias / activation / act'(aux tile via TMA, three
+//              boxes in flight per warp, processed in place) -> swizzled smem box -> coalesced 128-bit global stores
+//              (NN, NT: 8 lanes per 128-byte row segment) or TMA reduce-add (TN); then release the accumulator and
+//              bump the task's counter (red.release.gpu).  Nothing in the chunk loop waits on a fresh global / TMA
+//              round trip: bias values and aux boxes are requested before the accumulator is complete
 // Operands are fp32 in HBM, rounded to tf32 by their producers.  TMA zero-fills loads past M / N / K and clips
 // stores (in 16-byte units: columns N..roundup4(N) receive zeros), so only 16-byte row pitches are required.
 //
@@ -63,9 +65,11 @@ constexpr int A_BYTES = BM_CTA * BK * 4;          // 16 KB
 constexpr int B_BYTES_MAX = 128 * BK * 4;         // BN/2 <= 128 columns
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES_MAX;
 constexpr int CHUNK_BYTES = 32 * 32 * 4;          // one 32 x 32 fp32 epilogue box
-constexpr int EPI_WARP_BYTES = 3 * CHUNK_BYTES;   // 2 output staging buffers + 1 aux tile per epilogue warp
+constexpr int kEpiBufs = 3;                       // rotating boxes per epilogue warp: aux tile in, result out (in place)
+constexpr int EPI_WARP_BYTES = kEpiBufs * CHUNK_BYTES;
 constexpr int kAccCols = 256;                     // TMEM columns per accumulator
 constexpr int kTmemCols = 2 * kAccCols;
+constexpr int kTL = 16;                          // debug timeline: 64-bit stamps per task
 constexpr int kSched = 8;                        // depth of the task-index ring
 constexpr int SMEM_BYTES = kStages * STAGE_BYTES + kEpiWarps * EPI_WARP_BYTES + 512 /*barriers, task ring*/ + 1024 /*align*/;
 static_assert(SMEM_BYTES <= 232448, "more than the 227 KB a CTA may opt into");
@@ -287,6 +291,11 @@ struct alignas(64) GProblem {
   int pad0, pad1;
   const float* bias;
   float* colsum;             // epilogue adds the column sums of its output tile here (bias gradient), or null
+  float* c_ptr;              // output matrix for the direct (non-TMA) stores of the NN / NT epilogue
+  long long ldc;             // its row pitch in floats (multiple of 4)
+  uint32_t* mask_out;        // relu forward: bit (row, col) = output > 0, 32 columns per word, or null
+  const uint32_t* mask_in;   // relu dgrad: the same words replace the aux tile, or null
+  long long ldmask;          // words per mask row
 };
 static_assert(sizeof(GProblem) % 64 == 0, "tensor maps must stay 64-byte aligned inside the array");
 
@@ -299,11 +308,11 @@ struct alignas(16) GTask {
   int wait2_ctr, wait2_val;           // a second counter (or -1)
   int signal_ctr;                     // bumped by each of the 16 epilogue warps when the tile is globally visible, or -1
   int bn;                             // tile width of the problem
-  int flags;                          // bit 0 a_mn, 1 b_mn, 2 reduce, 3 has_aux, 4 round_out, 5 colsum
+  int flags;                          // bit 0 a_mn, 1 b_mn, 2 reduce, 3 has_aux, 4 round_out, 5 colsum, 6 mask_out, 7 mask_in
   int act, M, N;
 };
 static_assert(sizeof(GTask) == 64, "GTask is loaded as four 16-byte words");
-enum { TF_A_MN = 1, TF_B_MN = 2, TF_REDUCE = 4, TF_AUX = 8, TF_ROUND = 16, TF_COLSUM = 32 };
+enum { TF_A_MN = 1, TF_B_MN = 2, TF_REDUCE = 4, TF_AUX = 8, TF_ROUND = 16, TF_COLSUM = 32, TF_MASK_OUT = 64, TF_MASK_IN = 128 };
 
 namespace {
 
@@ -366,10 +375,11 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const GTask* __res
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
   auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
-  auto aux_bar = [&](int e) { return bar_base + 8u * (2 * kStages + 4 + e); };
-  auto sched_full_bar = [&](int r) { return bar_base + 8u * (2 * kStages + 4 + kEpiWarps + r); };
-  auto sched_empty_bar = [&](int r) { return bar_base + 8u * (2 * kStages + 4 + kEpiWarps + kSched + r); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4 + kEpiWarps + 2 * kSched);
+  auto aux_bar = [&](int e, int b) { return bar_base + 8u * (2 * kStages + 4 + kEpiBufs * e + b); };
+  constexpr int kAuxBars = kEpiBufs * kEpiWarps;
+  auto sched_full_bar = [&](int r) { return bar_base + 8u * (2 * kStages + 4 + kAuxBars + r); };
+  auto sched_empty_bar = [&](int r) { return bar_base + 8u * (2 * kStages + 4 + kAuxBars + kSched + r); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4 + kAuxBars + 2 * kSched);
   auto sched_task = [&](int r) { return tmem_slot + 8u + 4u * r; };
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
@@ -382,7 +392,8 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const GTask* __res
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), 2 * kEpiWarps); }
-    for (int e = 0; e < kEpiWarps; ++e) mbar_init(aux_bar(e), 1);
+    for (int e = 0; e < kEpiWarps; ++e)
+      for (int b = 0; b < kEpiBufs; ++b) mbar_init(aux_bar(e, b), 1);
     for (int r = 0; r < kSched; ++r) { mbar_init(sched_full_bar(r), 1); mbar_init(sched_empty_bar(r), kSchedConsumers); }
     fence_barrier_init();
   }
@@ -447,7 +458,7 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const GTask* __res
           if (tk.wait2_ctr >= 0) wait_counter(counters + tk.wait2_ctr, (uint32_t)tk.wait2_val);
           fence_proxy_async_all();           // the producing tasks' TMA stores -> our TMA loads
         }
-        if (tl && rank == 0) { tl[8 * t + 0] = gtimer(); tl[8 * t + 5] = blockIdx.x >> 1; tl[8 * t + 6] = t_entry; }
+        if (tl && rank == 0) { tl[kTL * t + 0] = gtimer(); tl[kTL * t + 5] = blockIdx.x >> 1; tl[kTL * t + 6] = t_entry; }
       }
       __syncwarp();
       int t_after = -1;
@@ -459,7 +470,7 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const GTask* __res
         const int k0 = (tk.kb0 + i) * BK;
         if (elect_one()) {
           mbar_wait(empty_bar(s), ((it / kStages) & 1) ^ 1);
-          if (tl && t == 0 && i < 64) tl[8 * ntasks + (rank ? 128 : 0) + i] = gtimer();
+          if (tl && t == 0 && i < 64) tl[kTL * ntasks + (rank ? 128 : 0) + i] = gtimer();
           if (rank == 0) mbar_arrive_expect_tx(full_bar(s), stage_tx);
           // MN-major operands: one 3-D box {32 mn, 32 k, chunks} lands as [chunk][k][32 mn] (see make_map_mn)
           if (a_mn) tma_load_3d_pair(sa, &p->map_a, full_leader, 0, k0, m0 >> 5);
@@ -492,7 +503,7 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const GTask* __res
         if (lane == 0) {
           mbar_wait(tmem_empty_bar(acc), ((tcount >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator
           tc_fence_after();
-          if (tl) { tl[8 * t + 1] = gtimer(); tl[8 * t + 7] = clock64(); }
+          if (tl) { tl[kTL * t + 1] = gtimer(); tl[kTL * t + 7] = clock64(); }
         }
         __syncwarp();
         for (int i = 0; i < tk.nkb; ++i, ++it) {
@@ -501,7 +512,7 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const GTask* __res
           if (elect_one()) {
             mbar_wait(full_bar(s), (it / kStages) & 1);
             tc_fence_after();
-            if (tl && t == 0 && i < 64) tl[8 * ntasks + 64 + i] = gtimer();
+            if (tl && t == 0 && i < 64) tl[kTL * ntasks + 64 + i] = gtimer();
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint64_t da = a_mn ? desc_mn_major(sa + k * 1024) : desc_k_major(sa + k * 32);
@@ -515,7 +526,7 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const GTask* __res
         }
         if (elect_one()) {
           umma_commit_pair(tmem_full_bar(acc)); // accumulator complete (both CTAs)
-          if (tl) { tl[8 * t + 2] = gtimer(); tl[8 * t + 7] = clock64() - tl[8 * t + 7]; }
+          if (tl) { tl[kTL * t + 2] = gtimer(); tl[kTL * t + 7] = clock64() - tl[kTL * t + 7]; }
         }
         t = bcast(t_after);
         tk = load_task(tasks, t);
@@ -526,10 +537,9 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const GTask* __res
     const int e = warp - 2;                 // epilogue warp index
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int half = e >> 2;                // this warp takes chunks half, half + 2, ...
-    const uint32_t out_buf = epi_base + e * EPI_WARP_BYTES;      // 2 x 4 KB staging for the bulk stores
-    const uint32_t aux_buf = out_buf + 2 * CHUNK_BYTES;          // 4 KB aux tile
+    const uint32_t ebuf = epi_base + e * EPI_WARP_BYTES;         // kEpiBufs rotating 32 x 32 boxes
     const uint32_t tmem_empty_leader0 = mapa(tmem_empty_bar(0), 0), tmem_empty_leader1 = mapa(tmem_empty_bar(1), 0);
-    uint32_t tcount = 0, aux_uses = 0, stores = 0;
+    uint32_t tcount = 0, cidx = 0, aux_phase = 0;               // cidx: chunks processed so far (box = cidx % 3)
     auto next_task_warp = [&]() -> int {
       int t = 0;
       if (lane == 0) t = next_task();
@@ -548,34 +558,67 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const GTask* __res
       const int row0 = tk.m_blk * BM + (int)rank * BM_CTA + q * 32;    // first output row of this warp
       const int n0 = tk.n_blk * BN;
       const int nchunks = (row0 < tk.M) ? min(BN / 32, (N - n0 + 31) / 32) : 0;   // warp-uniform
+      const int nmine = nchunks > half ? (nchunks - half + 1) >> 1 : 0;            // chunks half, half + 2, ... of this warp
       const uint32_t acc = tcount & 1;
-      if (use_aux && half < nchunks && elect_one()) {           // first aux tile: in flight during the main loop
-        mbar_arrive_expect_tx(aux_bar(e), CHUNK_BYTES);
-        tma_load_2d(aux_buf, &p->map_aux, aux_bar(e), n0 + half * 32, row0);
+      // everything the chunk loop needs from global memory is requested NOW, while the main loop of this task runs
+      // (a fresh L2 round trip costs ~1.5 us while the operand streams of 148 SMs are in flight): the bias values of all
+      // chunks of this warp (lane <-> column), the relu mask words of this lane's row, and up to three aux boxes
+      const uint32_t* __restrict__ mask_in = (tk.flags & TF_MASK_IN) ? p->mask_in : nullptr;
+      uint32_t* __restrict__ mask_out = (tk.flags & TF_MASK_OUT) ? p->mask_out : nullptr;
+      float bv0 = 0.0f, bv1 = 0.0f, bv2 = 0.0f, bv3 = 0.0f;
+      if (bias != nullptr) {
+        const int col = n0 + half * 32 + lane;
+        if (0 < nmine && col < N) bv0 = __ldg(bias + col);
+        if (1 < nmine && col + 64 < N) bv1 = __ldg(bias + col + 64);
+        if (2 < nmine && col + 128 < N) bv2 = __ldg(bias + col + 128);
+        if (3 < nmine && col + 192 < N) bv3 = __ldg(bias + col + 192);
+      }
+      uint32_t mw0 = 0u, mw1 = 0u, mw2 = 0u, mw3 = 0u;
+      if (mask_in != nullptr && row0 + lane < tk.M) {
+        const uint32_t* mrow = mask_in + (size_t)(row0 + lane) * (size_t)p->ldmask + (n0 >> 5) + half;
+        if (0 < nmine) mw0 = __ldg(mrow);
+        if (1 < nmine) mw1 = __ldg(mrow + 2);
+        if (2 < nmine) mw2 = __ldg(mrow + 4);
+        if (3 < nmine) mw3 = __ldg(mrow + 6);
+      }
+      if (use_aux && nmine > 0 && elect_one()) {
+        bulk_wait_read<0>();               // a reduce-add of the previous task may still be reading these boxes
+#pragma unroll
+        for (int i = 0; i < kEpiBufs; ++i) {
+          if (i < nmine) {
+            const uint32_t b = (cidx + i) % kEpiBufs;
+            mbar_arrive_expect_tx(aux_bar(e, b), CHUNK_BYTES);
+            tma_load_2d(ebuf + b * CHUNK_BYTES, &p->map_aux, aux_bar(e, b), n0 + (half + 2 * i) * 32, row0);
+          }
+        }
       }
       mbar_wait(tmem_full_bar(acc), (tcount >> 1) & 1);
       tc_fence_after();
-      if (tl && rank == 0 && warp == 2 && lane == 0) tl[8 * t + 3] = gtimer();
+      if (tl && rank == 0 && warp == 2 && lane == 0) tl[kTL * t + 3] = gtimer();
 #pragma unroll 1
-      for (int c = half; c < nchunks; c += 2) {
+      for (int i = 0; i < nmine; ++i, ++cidx) {
+        const int c = half + 2 * i;
+        const uint32_t b = cidx % kEpiBufs;
+        const uint32_t ob = ebuf + b * CHUNK_BYTES;
         uint32_t v[32];
         tmem_ld32(tmem_base + acc * kAccCols + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
         float x[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
-        if (use_aux) {
-          mbar_wait(aux_bar(e), aux_uses & 1);
-          ++aux_uses;
+        if (tl && rank == 0 && warp == 2 && lane == 0 && i == 0) tl[kTL * t + 9] = gtimer();
+        const float b_cur = i == 0 ? bv0 : i == 1 ? bv1 : i == 2 ? bv2 : bv3;
+        if (mask_in != nullptr) {          // relu': one bit per element, already in registers
+          const uint32_t mw = i == 0 ? mw0 : i == 1 ? mw1 : i == 2 ? mw2 : mw3;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = ((mw >> j) & 1u) ? x[j] : 0.0f;
+        } else if (use_aux) {
+          mbar_wait(aux_bar(e, b), (aux_phase >> b) & 1u);
+          aux_phase ^= 1u << b;
           float h[32];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 hv = lds128(aux_buf + swz(lane, j));
+            const float4 hv = lds128(ob + swz(lane, j));
             h[4 * j] = hv.x; h[4 * j + 1] = hv.y; h[4 * j + 2] = hv.z; h[4 * j + 3] = hv.w;
-          }
-          __syncwarp();                                          // every lane has read the tile: refill it
-          if (c + 2 < nchunks && elect_one()) {
-            mbar_arrive_expect_tx(aux_bar(e), CHUNK_BYTES);
-            tma_load_2d(aux_buf, &p->map_aux, aux_bar(e), n0 + (c + 2) * 32, row0);
           }
           switch (act) {
             case ACT_RELU:
@@ -595,13 +638,7 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const GTask* __res
         } else if (!reduce) {
           if (bias != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int col = n0 + c * 32 + j * 4;
-              if (col < N) {                                     // bias rows are padded to 4 floats
-                const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + col));
-                x[4 * j] += bv.x; x[4 * j + 1] += bv.y; x[4 * j + 2] += bv.z; x[4 * j + 3] += bv.w;
-              }
-            }
+            for (int j = 0; j < 32; ++j) x[j] += __shfl_sync(0xffffffffu, b_cur, j);
           }
           switch (act) {
             case ACT_RELU:
@@ -623,23 +660,50 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const GTask* __res
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[j] = round_tf32(x[j]);
         }
-        if (n0 + c * 32 + 32 > N) {        // TMA clips stores in 16-byte units: the pad columns N..roundup4(N) get zeros
+        if (n0 + c * 32 + 32 > N) {        // the pad columns N..roundup4(N) of the row pitch receive zeros
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[j] = (n0 + c * 32 + j < N) ? x[j] : 0.0f;
         }
-        // staging buffer (stores & 1) was handed to the bulk store two chunks ago: wait until that store has read it
-        if (elect_one()) bulk_wait_read<1>();
+        if (tl && rank == 0 && warp == 2 && lane == 0 && i == 0) tl[kTL * t + 11] = gtimer();
+        if (mask_out != nullptr) {
+          uint32_t mw = 0u;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mw |= (x[j] > 0.0f ? 1u : 0u) << j;
+          if (row0 + lane < tk.M) mask_out[(size_t)(row0 + lane) * (size_t)p->ldmask + (n0 >> 5) + c] = mw;
+        }
+        // box b was last handed to a bulk reduce-add three chunks ago (if at all): wait until that one has read it.
+        // (In the aux case the lane overwrites exactly the 128 bytes it has just read: in place, no hazard.)
+        if (tl && rank == 0 && warp == 2 && lane == 0 && i == 0) tl[kTL * t + 12] = gtimer();
+        if (elect_one()) bulk_wait_read<kEpiBufs - 1>();
         __syncwarp();
-        const uint32_t ob = out_buf + (stores & 1) * CHUNK_BYTES;
-        ++stores;
+        if (tl && rank == 0 && warp == 2 && lane == 0 && i == 0) tl[kTL * t + 13] = gtimer();
 #pragma unroll
         for (int j = 0; j < 8; ++j) sts128(ob + swz(lane, j), x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (elect_one()) {
-          if (reduce) tma_reduce_add_2d(&p->map_c, ob, n0 + c * 32, row0);
-          else tma_store_2d(&p->map_c, ob, n0 + c * 32, row0);
-          bulk_commit();
+        if (tl && rank == 0 && warp == 2 && lane == 0 && i == 0) tl[kTL * t + 14] = gtimer();
+        if (reduce) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (elect_one()) {
+            tma_reduce_add_2d(&p->map_c, ob, n0 + c * 32, row0);
+            bulk_commit();
+          }
+        } else {
+          // transposed read-back: 8 lanes cover one 128-byte row segment, 4 rows per instruction -> coalesced 128-bit
+          // stores; rows >= M and columns >= roundup4(N) are clipped here (the TMA loads zero-filled them)
+          __syncwarp();
+          const int rr = lane >> 3, jj = lane & 7;
+          const int col = n0 + c * 32 + jj * 4;
+          if (col < ((N + 3) & ~3)) {
+            float* dst = p->c_ptr + (size_t)(row0 + rr) * (size_t)p->ldc + col;
+            const size_t step = 4 * (size_t)p->ldc;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              if (row0 + rr + 4 * k < tk.M) {
+                const float4 o = lds128(ob + swz(rr + 4 * k, jj));
+                asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + k * step), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+              }
+            }
+          }
         }
         if (colsum != nullptr) {
           // bias gradient of the layer below = column sums of this dgrad output: lane <-> column, 32 conflict-free
@@ -654,19 +718,28 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const GTask* __res
           const int col = n0 + c * 32 + lane;
           if (col < N) atomicAdd(colsum + col, cs);
         }
+        if (tl && rank == 0 && warp == 2 && lane == 0 && i == 0) tl[kTL * t + 10] = gtimer();
+        if (use_aux && i + kEpiBufs < nmine) {
+          __syncwarp();                    // every lane has finished with box b: refill it with the aux tile 3 chunks ahead
+          if (elect_one()) {
+            mbar_arrive_expect_tx(aux_bar(e, b), CHUNK_BYTES);
+            tma_load_2d(ob, &p->map_aux, aux_bar(e, b), n0 + (c + 2 * kEpiBufs) * 32, row0);
+          }
+        }
       }
-      // every tcgen05.ld of this accumulator has completed (wait::ld): hand it back to the MMA issuer
+      // every tcgen05.ld of this accumulator has completed (wait::ld): hand it back to the MMA issuer; the global
+      // stores of all lanes are ordered before the elected lane's release by the warp barrier
+      if (tl && rank == 0 && warp == 2 && lane == 0) tl[kTL * t + 8] = gtimer();
       tc_fence_before();
       __syncwarp();
       if (elect_one()) {
         mbar_arrive_cluster_relaxed(acc ? tmem_empty_leader1 : tmem_empty_leader0, 0u);
         if (tk.signal_ctr >= 0) {
-          bulk_wait_complete();            // this warp's stores are performed, then publish (release, gpu scope)
-          fence_proxy_async_all();
+          if (reduce) { bulk_wait_complete(); fence_proxy_async_all(); }   // bulk reduce-adds performed, then publish
           red_release_gpu_add(counters + tk.signal_ctr, 1u);
         }
       }
-      if (tl && rank == 0 && warp == 2 && lane == 0) tl[8 * t + 4] = gtimer();
+      if (tl && rank == 0 && warp == 2 && lane == 0) tl[kTL * t + 4] = gtimer();
       t = t_after;
       tk = tk_after;
     }
@@ -854,7 +927,8 @@ int group_add_problem(GroupPlan* g, int kind, const GemmArgs& a, char* err, int 
       break;
   }
   ok = ok && make_map(&p.map_c, a.C, a.N, a.M, a.ldc, 32, false, err, errlen);
-  const bool has_aux = kind != 2 && a.aux != nullptr;
+  const bool mask_in = kind != 2 && a.mask_in != nullptr && a.act == ACT_RELU && a.aux != nullptr;
+  const bool has_aux = kind != 2 && a.aux != nullptr && !mask_in;
   if (ok && has_aux) ok = make_map(&p.map_aux, a.aux, a.N, a.M, a.ldaux, 32, false, err, errlen);
   else if (ok) p.map_aux = p.map_c;
   if (!ok) return -1;
@@ -863,6 +937,10 @@ int group_add_problem(GroupPlan* g, int kind, const GemmArgs& a, char* err, int 
   p.act = a.act; p.round_out = a.round_out; p.has_aux = has_aux ? 1 : 0;
   p.bias = (kind == 0) ? a.bias : nullptr;
   p.colsum = (kind != 2) ? a.bias_grad : nullptr;   // NN / NT: bias_grad = where the column sums of C go
+  p.c_ptr = a.C; p.ldc = a.ldc;
+  p.mask_in = mask_in ? a.mask_in : nullptr;
+  p.mask_out = (kind == 0 && a.act == ACT_RELU && !a.aux) ? a.mask_out : nullptr;
+  p.ldmask = a.ldmask;
   g->problems.push_back(p);
   g->uploaded = false;
   return (int)g->problems.size() - 1;
@@ -882,7 +960,8 @@ int group_add_task(GroupPlan* g, int prob, int m_blk, int n_blk, int kb0, int nk
   t.wait2_ctr = wait2_ctr; t.wait2_val = wait2_val; t.signal_ctr = signal_ctr;
   t.bn = p.BN;
   t.flags = (p.a_mn ? TF_A_MN : 0) | (p.b_mn ? TF_B_MN : 0) | (p.reduce ? TF_REDUCE : 0) | (p.has_aux ? TF_AUX : 0) |
-            (p.round_out ? TF_ROUND : 0) | (p.colsum ? TF_COLSUM : 0);
+            (p.round_out ? TF_ROUND : 0) | (p.colsum ? TF_COLSUM : 0) | (p.mask_out ? TF_MASK_OUT : 0) |
+            (p.mask_in ? TF_MASK_IN : 0);
   t.act = p.act; t.M = p.M; t.N = p.N;
   g->tasks.push_back(t);
   g->uploaded = false;
@@ -946,33 +1025,35 @@ void group_debug_timeline(const GroupPlan* g, int site, uint32_t* queue, int res
   const int first = g->sites[site].first_task, count = g->sites[site].n_tasks;
   if (count <= 0) return;
   unsigned long long* dev = nullptr;
-  if (cudaMalloc(&dev, (size_t)count * 64 + 192 * 8) != cudaSuccess) return;
-  cudaMemsetAsync(dev, 0, (size_t)count * 64 + 192 * 8, s);
+  if (cudaMalloc(&dev, (size_t)count * kTL * 8 + 192 * 8) != cudaSuccess) return;
+  cudaMemsetAsync(dev, 0, (size_t)count * kTL * 8 + 192 * 8, s);
   const int clusters = std::min(count, kNumSMs / 2);
   launch_site(g, site, queue, reset_first, reset_count, dev, s);
   cudaStreamSynchronize(s);
-  std::vector<unsigned long long> h((size_t)count * 8 + 192);
-  cudaMemcpy(h.data(), dev, (size_t)count * 64 + 192 * 8, cudaMemcpyDeviceToHost);
+  std::vector<unsigned long long> h((size_t)count * kTL + 192);
+  cudaMemcpy(h.data(), dev, (size_t)count * kTL * 8 + 192 * 8, cudaMemcpyDeviceToHost);
   cudaFree(dev);
   unsigned long long t0 = ~0ull, t1 = 0;
-  for (int i = 0; i < count; ++i) { t0 = std::min(t0, h[8 * i + 6]); t1 = std::max(t1, h[8 * i + 4]); }
+  for (int i = 0; i < count; ++i) { t0 = std::min(t0, h[kTL * i + 6]); t1 = std::max(t1, h[kTL * i + 4]); }
   fprintf(stderr, "[group timeline] %d tasks on %d clusters, %.1f us from first entry to last epilogue end\n", count, clusters,
           (t1 - t0) * 1e-3);
   {
     const int nk = std::min(g->tasks[first].nkb, 64);
     fprintf(stderr, "  task 0 k-blocks (us): leader issue | peer issue | full seen by MMA\n   ");
     for (int i = 0; i < nk; ++i)
-      fprintf(stderr, " %d: %.2f|%.2f|%.2f", i, (h[8 * count + i] - t0) * 1e-3, (h[8 * count + 128 + i] - t0) * 1e-3,
-              (h[8 * count + 64 + i] - t0) * 1e-3);
+      fprintf(stderr, " %d: %.2f|%.2f|%.2f", i, (h[kTL * count + i] - t0) * 1e-3, (h[kTL * count + 128 + i] - t0) * 1e-3,
+              (h[kTL * count + 64 + i] - t0) * 1e-3);
     fprintf(stderr, "\n");
   }
   const int show = getenv("VAEASSOC_TC_TIMELINE_ALL") ? count : std::min(count, 12);
   for (int k = 0; k < show; ++k) {
     const int i = (k < show / 2 || show == count) ? k : count - (show - k);
     const GTask& tk = g->tasks[first + i];
-    fprintf(stderr, "  task %4d prob %2d (%2d,%2d) nkb %3d cl %2llu entry %6.2f | prod %6.2f mma %6.2f..%6.2f (%llu cyc) epi %6.2f..%6.2f us\n", i,
-            tk.problem, tk.m_blk, tk.n_blk, tk.nkb, h[8 * i + 5], (h[8 * i + 6] - t0) * 1e-3, (h[8 * i + 0] - t0) * 1e-3,
-            (h[8 * i + 1] - t0) * 1e-3, (h[8 * i + 2] - t0) * 1e-3, h[8 * i + 7], (h[8 * i + 3] - t0) * 1e-3, (h[8 * i + 4] - t0) * 1e-3);
+    fprintf(stderr, "  task %4d prob %2d (%2d,%2d) nkb %3d cl %2llu entry %6.2f | prod %6.2f mma %6.2f..%6.2f (%llu cyc) epi %6.2f..%6.2f us | ld0 %6.2f chunk0 %6.2f loop %6.2f | math %6.2f mask %6.2f wait %6.2f sts %6.2f\n", i,
+            tk.problem, tk.m_blk, tk.n_blk, tk.nkb, h[kTL * i + 5], (h[kTL * i + 6] - t0) * 1e-3, (h[kTL * i + 0] - t0) * 1e-3,
+            (h[kTL * i + 1] - t0) * 1e-3, (h[kTL * i + 2] - t0) * 1e-3, h[kTL * i + 7], (h[kTL * i + 3] - t0) * 1e-3, (h[kTL * i + 4] - t0) * 1e-3,
+            (h[kTL * i + 9] - t0) * 1e-3, (h[kTL * i + 10] - t0) * 1e-3, (h[kTL * i + 8] - t0) * 1e-3,
+            (h[kTL * i + 11] - t0) * 1e-3, (h[kTL * i + 12] - t0) * 1e-3, (h[kTL * i + 13] - t0) * 1e-3, (h[kTL * i + 14] - t0) * 1e-3);
   }
 }
 

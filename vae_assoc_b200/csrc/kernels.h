@@ -23,6 +23,11 @@ struct GemmArgs {
   int act = 0;          // Act code: forward activation, or which act' to apply in dgrad
   int round_out = 0;    // round stored outputs to tf32 (they feed a tcgen05 kind::tf32 GEMM)
   int splitk = 1;       // TN only
+  // relu layers on the tcgen05 path: the forward epilogue also writes one bit per output (activation > 0), 32 columns
+  // per word, row pitch ldmask words; the dgrad epilogue reads these words instead of the fp32 activation tile (`aux`)
+  uint32_t* mask_out = nullptr;
+  const uint32_t* mask_in = nullptr;
+  int64_t ldmask = 0;
 };
 
 void launch_gemm_nn_simt(const GemmArgs& a, cudaStream_t s);
