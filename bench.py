@@ -34,6 +34,43 @@ def ref_archs(n_z=4):
     return [img, jnt]
 
 
+def conv_archs(n_z=4):
+    """BASELINE.json configs[3]: the commented-out conv image arch of vae_assoc_ujichar_img_jnt.py:72-80 (recog 16/64,
+    gener 64/16, hidden_conv=True: conv encoder + deconv.py decoder) next to the dense joint arch."""
+    img = dict(scope="image", hidden_conv=True, n_hidden_recog_1=16, n_hidden_recog_2=64, n_hidden_gener_1=64,
+               n_hidden_gener_2=16, n_input=784, n_z=n_z)
+    return [img, ref_archs(n_z)[1]]
+
+
+def scaled_archs(n_z=64, width=2048):
+    """BASELINE.json configs[4]: 4 x 2048 hidden layers per modality (2 encoder + 2 decoder layers through the
+    reference's own arch dict), latent 64."""
+    a = ref_archs(n_z)
+    for na in a:
+        for k in ("n_hidden_recog_1", "n_hidden_recog_2", "n_hidden_gener_1", "n_hidden_gener_2"):
+            na[k] = width
+    return a
+
+
+CONFIGS = {
+    # name: (archs builder, default pairs per GPU, workload description)
+    "ref": (ref_archs, 8192, "assoc-VAE reference arch (img 784-500-500, jnt 147-200-200, n_z 4, relu, w [50,1], lambda 8, lr 1e-3)"),
+    "conv": (conv_archs, 4096, "assoc-VAE with the hidden_conv=True image modality (conv encoder 16/32/64, deconv.py decoder "
+                               "64/32/16/1 + dense 784x784) and the dense joint modality, n_z 4, relu, w [50,1], lambda 8"),
+    "scaled": (scaled_archs, 16384, "scaled assoc-VAE (both modalities 2048-2048 hidden, n_z 64, relu, w [50,1], lambda 8)"),
+}
+
+
+def dense_flops_per_sample(archs):
+    """2*K*N per GEMM row; forward + wgrad of every layer + dgrad of every layer but the two input layers."""
+    tot = 0
+    for na in archs:
+        ni, r1, r2, nz = na["n_input"], na["n_hidden_recog_1"], na["n_hidden_recog_2"], na["n_z"]
+        fwd = 2 * (ni * r1 + r1 * r2 + r2 * 2 * nz + nz * r1 + r1 * r2 + r2 * ni)
+        tot += 3 * fwd - 2 * ni * r1
+    return tot
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -90,7 +127,7 @@ class ClockSampler(object):
                     reasons=sorted(reasons), samples=len(sm))
 
 
-def cpu_reference_run(batch, steps, warmup, threads=None):
+def cpu_reference_run(batch, steps, warmup, threads=None, archs=None):
     """CPU restatement (torch fp32, all host threads) of the reference graph at its op granularity; NOT TensorFlow
     (not installable here).  Returns (samples_per_s, ms_per_step, cores)."""
     import torch
@@ -98,7 +135,7 @@ def cpu_reference_run(batch, steps, warmup, threads=None):
     from oracle import vae_assoc_oracle as vo
     cores = threads or os.cpu_count() or 1
     torch.set_num_threads(cores)
-    archs = vo.reference_archs(4)
+    archs = archs or vo.reference_archs(4)
     params = vo.init_params(archs, 0)
     model = torch_twin.TorchAssocVAE(archs, [True, False], "relu", [50.0, 1.0], 8.0, 1e-3, batch, params, dtype=torch.float32)
     X = [torch.tensor(x, dtype=torch.float32) for x in synth.synth_batch(archs, [True, False], 0, 1, 0, batch)]
@@ -117,7 +154,9 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=8192, help="pairs per GPU per step")
+    ap.add_argument("--config", default="ref", choices=sorted(CONFIGS), help="ref = BASELINE configs[1]/[2] (the metric's "
+                    "workload), conv = configs[3], scaled = configs[4]")
+    ap.add_argument("--batch", type=int, default=0, help="pairs per GPU per step (default: the config's)")
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
@@ -126,22 +165,26 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    workload = ("assoc-VAE reference arch (img 784-500-500, jnt 147-200-200, n_z 4, relu, w [50,1], lambda 8, lr 1e-3), "
-                "%d pairs per GPU per step" % args.batch)
+    mk_archs, default_batch, desc = CONFIGS[args.config]
+    if args.batch <= 0:
+        args.batch = default_batch
+    archs = mk_archs()
+    workload = "%s, %d pairs per GPU per step" % (desc, args.batch)
 
     if args.impl == "reference":
         if rank != 0:
             return
         # each step = a bounded sample (same per-GPU batch) so that the run ends within minutes
         steps = min(args.steps, 10); warm = min(args.warmup, 2)
-        sps, ms, cores = cpu_reference_run(args.batch, steps, warm)
+        cpu_batch = min(args.batch, 8192 if args.config == "ref" else 2048)     # bounded sample of the per-GPU batch
+        sps, ms, cores = cpu_reference_run(cpu_batch, steps, warm, archs=archs)
         line = dict(impl="reference", metric="paired samples/sec/train step", value=sps, unit="samples/s",
                     n_gpus=args.gpus, steps=steps, warmup=warm, ms_per_step=ms, higher_is_better=True, scaling="weak",
                     vs_baseline=None, dtype="fp32", data="synthetic",
-                    config=dict(workload=workload, global_batch=args.batch, note="CPU restatement (torch fp32) of the "
+                    config=dict(workload=workload, name=args.config, global_batch=args.batch, note="CPU restatement (torch fp32) of the "
                                 "reference graph, not TensorFlow (not installable here); one process, host cores only"),
                     cpu_baseline=dict(value=sps, unit="samples/s", cores=cores, kind="port",
-                                      sample="%d steps of %d pairs after %d warm-up" % (steps, args.batch, warm)),
+                                      sample="%d steps of %d pairs after %d warm-up" % (steps, cpu_batch, warm)),
                     e2e=dict(value=sps, unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
         print(json.dumps(line))
         return
@@ -156,7 +199,7 @@ def main():
 
     B = args.batch
     Bg = B * world
-    model = vae_assoc.AssocVariationalAutoEncoder(ref_archs(), [True, False], transfer_fct=vae_assoc.relu,
+    model = vae_assoc.AssocVariationalAutoEncoder(archs, [True, False], transfer_fct=vae_assoc.relu,
                                                   weights=[50, 1], assoc_lambda=8, learning_rate=1e-3, batch_size=B,
                                                   precision=args.precision, seed=0, use_graph=not args.no_graph,
                                                   global_batch=Bg, global_row0=rank * B)
@@ -165,7 +208,7 @@ def main():
 
     # device-resident pool of distinct synthetic batches, larger than L2 (126 MB) so that no step re-reads a
     # cached input: 16 x 30.5 MB at B = 8192
-    bytes_per_batch = B * 931 * 4
+    bytes_per_batch = B * sum(na["n_input"] for na in archs) * 4
     pool_n = max(4, int(np.ceil(2.2 * 126e6 / bytes_per_batch)))
     pool_n = min(pool_n, 512)
     pool = [model.synth_batch((k * world + rank) * B, B) for k in range(pool_n)]
@@ -277,12 +320,17 @@ def main():
                     share_of_step=top["ms"] / eager_ms,
                     note="tcgen05 kind::tf32 nominal peak is half the bf16 figure used as `peak`"
                     if top.get("bound") == "tensor" else "")
-    step_tflops = FLOP_PER_SAMPLE * B / (ms_step * 1e-3) / 1e12
+    # algorithmic FLOPs of one step = sum over the contractions of the schedule (2*M*N*K each); for the dense configs this
+    # is SURVEY 8d's per-sample figure x B (7 744 400 x B at the reference arch)
+    step_flops = sum(f for (_, f, _) in acc.values())
+    if args.config != "conv":
+        assert abs(step_flops - dense_flops_per_sample(archs) * B) <= 1e-6 * step_flops, (step_flops, dense_flops_per_sample(archs) * B)
+    step_tflops = step_flops / (ms_step * 1e-3) / 1e12
 
     line = dict(metric="paired samples/sec/train step", value=value, unit="samples/s", n_gpus=world, steps=args.steps,
                 warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype=args.precision, data="synthetic",
-                config=dict(workload=workload, global_batch=Bg, per_gpu_batch=B, parallelism="dp%d" % world,
+                config=dict(workload=workload, name=args.config, global_batch=Bg, per_gpu_batch=B, parallelism="dp%d" % world,
                             l2="inputs rotate through a device pool of %d distinct batches (%.0f MB > 126 MB L2)"
                                % (pool_n, pool_n * bytes_per_batch / 1e6),
                             graph=not args.no_graph),
@@ -294,10 +342,11 @@ def main():
                 kernels=kernels[:40])
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sps, cms, cores = cpu_reference_run(B, 5, 1)
+        cpu_batch = min(B, 8192 if args.config == "ref" else 2048)
+        sps, cms, cores = cpu_reference_run(cpu_batch, 5, 1, archs=archs)
         line["cpu_baseline"] = dict(value=sps, unit="samples/s", cores=cores, kind="port", ms_per_step=cms,
                                     sample="5 steps of %d pairs after 1 warm-up, torch-CPU fp32 restatement "
-                                           "(not TensorFlow)" % B)
+                                           "(not TensorFlow)" % cpu_batch)
     if rank == 0:
         print(json.dumps(line))
     model.close()

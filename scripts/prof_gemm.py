@@ -21,7 +21,9 @@ for name, kind, M, N, K, A, lda, Bm, ldb, Cm, ldc in cases:
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        rc = model._lib.vaeassoc_debug_gemm(model._h, kind, 1, M, N, K, p(A), lda, p(Bm), ldb, p(Cm), ldc, None, None, None, 0, 0, 0)
+        bias = torch.randn(1024, device=dev) if kind == 0 else None       # forward form: bias + relu + tf32 rounding epilogue
+        rc = model._lib.vaeassoc_debug_gemm(model._h, kind, 1, M, N, K, p(A), lda, p(Bm), ldb, p(Cm), ldc,
+                                            p(bias) if kind == 0 else None, None, None, 0, 1 if kind == 0 else 0, 1 if kind == 0 else 0)
         e1.record(); torch.cuda.synchronize()
         assert rc == 0
     print(name, M, N, K, "%.1f us incl. plan+launch+sync" % (1e3 * e0.elapsed_time(e1)), "%.1f TFLOP/s" % (2.0 * M * N * K / (e0.elapsed_time(e1) * 1e-3) / 1e12))

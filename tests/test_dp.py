@@ -114,5 +114,7 @@ def test_dp_nccl_matches_single_gpu(tmp_path, precision):
     np.testing.assert_allclose(got["costs"], costs, rtol=2e-5)
     for i, p in enumerate(model.get_params()):
         d = np.linalg.norm(got["p%d" % i].astype(np.float64) - p) / max(np.linalg.norm(p), 1e-30)
-        assert d < 1e-4, (i, d)
+        # tf32 + relu: the shards' bias-gradient atomics / split-K order differ from the one-GPU run and Adam amplifies the
+        # last-bit differences on near-zero gradients (see rel_l2 in test_gpu_parity.py); measured 1.9e-4 on the biases
+        assert d < (1e-4 if precision == "fp32" else 5e-4), (i, d)
     model.close()

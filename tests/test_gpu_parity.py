@@ -335,3 +335,21 @@ def test_train_loop_matches_reference_semantics(va):
     per_epoch = [hist[(e + 1) * (n_train // 64) - 1] for e in range(3)]
     assert per_epoch[2] < per_epoch[0]
     model.close()
+
+
+def test_dynamic_task_queue_mode_matches(va, monkeypatch):
+    """Data-parallel runs take every tile task (the first one included) from the atomic queue, so that the persistent
+    kernel never depends on all of its clusters being resident next to an NCCL kernel (csrc/gemm_group.cu).  The mode
+    is forced here on one GPU: same costs as the static-first-task mode, to accumulation order."""
+    archs = vo.reference_archs(4)
+    batch = 2048
+    X = [x.astype(np.float32) for x in synth.synth_batch(archs, [True, False], 0, 1, 0, batch)]
+    costs = {}
+    for mode in ("static", "dynamic"):
+        if mode == "dynamic":
+            monkeypatch.setenv("VAEASSOC_DYNAMIC_FIRST", "1")
+        model = va.AssocVariationalAutoEncoder(archs, [True, False], transfer_fct="relu", weights=[50, 1], assoc_lambda=8,
+                                               learning_rate=1e-3, batch_size=batch, precision="tf32", seed=0, eps_seed=3)
+        costs[mode] = [float(model.partial_fit(X)) for _ in range(6)]
+        model.close()
+    np.testing.assert_allclose(costs["dynamic"], costs["static"], rtol=2e-5)

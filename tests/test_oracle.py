@@ -145,3 +145,23 @@ def test_deconv_same_is_shifted_relative_to_torch_default():
                 for kx in range(5):
                     full[0, iy * 2 + ky, ix * 2 + kx] += w[ky, kx] @ y[0, iy, ix]
     np.testing.assert_allclose(out, full[:, 1:7, 1:7], rtol=1e-12)
+
+
+def test_latents_1k_golden_prefix():
+    """tests/golden/latents_1k.npz (1000-step oracle run, `python -m oracle.make_golden_1k`): the first 10 steps are
+    re-run here and must reproduce the frozen costs and latent codes exactly (the full run takes minutes)."""
+    from oracle import make_golden_1k as g1k
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "latents_1k.npz"))
+    assert gold["costs"].shape == (g1k.STEPS,) and np.isfinite(gold["costs"]).all()
+    archs, params, data, eps = g1k.case()
+    o = vo.OracleAssocVAE(archs, [True, False], "relu", [50.0, 1.0], 8.0, 1e-3, g1k.BATCH, params=params)
+    probe = [x.astype(np.float64) for x in g1k.batch_of(data, 0)]
+    for t in range(10):
+        c = o.partial_fit([x.astype(np.float64) for x in g1k.batch_of(data, t)], eps(t).astype(np.float64))
+        np.testing.assert_allclose(c, gold["costs"][t], rtol=1e-12)
+        if t + 1 in (1, 10):
+            z = o.transform(probe)
+            np.testing.assert_allclose(z[0], gold["z_img_%d" % (t + 1)], rtol=1e-10, atol=1e-12)
+            np.testing.assert_allclose(z[1], gold["z_jnt_%d" % (t + 1)], rtol=1e-10, atol=1e-12)
+    # training made progress: the cost after 1000 steps is far below the initial one
+    assert gold["costs"][-1] < 0.6 * gold["costs"][0]

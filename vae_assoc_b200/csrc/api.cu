@@ -164,6 +164,7 @@ struct vaeassoc_ctx {
   struct Seg { int site = 0, reset_first = 0, reset_count = 0; };
   Seg seg_enc, seg_dec, seg_bwd_dec, seg_bwd_enc;     // fused segments of the train step (dense modalities, tf32)
   bool fused = false;
+  bool force_dynamic = false;                         // VAEASSOC_DYNAMIC_FIRST: the data-parallel task-queue mode on one GPU (tests)
   std::vector<Op> ops_colsum_dec, ops_colsum_enc;     // bias gradients that no GEMM epilogue produces (d a, d heads)
   // graphs
   cudaGraphExec_t graph_train = nullptr, graph_grad = nullptr, graph_a1 = nullptr, graph_a2 = nullptr,
@@ -238,9 +239,13 @@ void build_layout(Ctx* c) {
     Mod& d = c->mods[m];
     d.cfg = c->cfg.mod[m];
     d.conv = d.cfg.hidden_conv != 0;
-    d.ni = d.cfg.n_input; d.nip = (int)round_up(d.ni, 4);
-    d.r1 = d.cfg.n_hidden_recog_1; d.r1p = (int)round_up(d.r1, 4);
-    d.r2 = d.cfg.n_hidden_recog_2; d.r2p = (int)round_up(d.r2, 4);
+    // row pitches: dense modalities round to 32 floats so that every row starts on a 128-byte line (one L2 line per
+    // 32-float TMA box row / epilogue row segment instead of two); the conv modality keeps dense NHWC images (4 floats)
+    int al = d.conv ? 4 : 32;
+    if (const char* e = getenv("VAEASSOC_PITCH_ALIGN")) { const int v = atoi(e); if (!d.conv && v >= 4 && v % 4 == 0) al = v; }
+    d.ni = d.cfg.n_input; d.nip = (int)round_up(d.ni, al);
+    d.r1 = d.cfg.n_hidden_recog_1; d.r1p = (int)round_up(d.r1, al);
+    d.r2 = d.cfg.n_hidden_recog_2; d.r2p = (int)round_up(d.r2, al);
     d.nz = nz; d.nh = 2 * nz; d.nhp = (int)round_up(d.nh, 4);
     if (d.ni <= 0 || d.r1 <= 0 || d.r2 <= 0) fail("modality %d: layer sizes must be positive", m);
     if (d.conv) {
@@ -449,12 +454,12 @@ Op make_gemm(Ctx* c, const char* name, int m, int kind, GemmArgs a, int64_t w_of
       const GemmArgs b = a;
       op.launches = 2;
       op.run = [cc, site, b](cudaStream_t s) {
-        group_launch(cc->gplan, site, cc->gsync + cc->n_ctr + 2 * site, 0, 0, s);
+        group_launch(cc->gplan, site, cc->gsync + cc->n_ctr + 2 * site, 0, 0, cc->comm != nullptr || cc->force_dynamic, s);
         launch_colsum(b.B, b.ldb, b.K, b.N, b.bias_grad, s);
       };
     } else {
       op.run = [cc, site](cudaStream_t s) {
-        group_launch(cc->gplan, site, cc->gsync + cc->n_ctr + 2 * site, 0, 0, s);
+        group_launch(cc->gplan, site, cc->gsync + cc->n_ctr + 2 * site, 0, 0, cc->comm != nullptr || cc->force_dynamic, s);
       };
     }
     return op;
@@ -872,7 +877,7 @@ void build_segments(Ctx* c) {
 }
 
 void launch_seg(Ctx* c, const Ctx::Seg& sg, cudaStream_t s) {
-  group_launch(c->gplan, sg.site, c->gsync + c->n_ctr + 2 * sg.site, sg.reset_first, sg.reset_count, s);
+  group_launch(c->gplan, sg.site, c->gsync + c->n_ctr + 2 * sg.site, sg.reset_first, sg.reset_count, c->comm != nullptr || c->force_dynamic, s);
   c->launches += 1;
 }
 
@@ -1202,6 +1207,7 @@ int vaeassoc_create(const vaeassoc_config* cfg, vaeassoc_handle* out) {
     CUDA_OK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CUDA_OK(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
+    c->force_dynamic = getenv("VAEASSOC_DYNAMIC_FIRST") != nullptr;
     for (int i = 0; i < 2; ++i) {
       CUDA_OK(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
       CUDA_OK(cudaEventCreateWithFlags(&c->ev_consumed[i], cudaEventDisableTiming));
@@ -1616,6 +1622,7 @@ int vaeassoc_comm_init(vaeassoc_handle h, const char* nccl_lib_path, const void*
   const int r = g_nccl.CommInitRank(&comm, world, id, rank);
   if (r != 0) fail("ncclCommInitRank failed: %s", g_nccl.GetErrorString(r));
   h->comm = comm; h->rank = rank; h->world = world;
+  destroy_graphs(h);     // the captured launches bake in the task-queue mode (see group_launch)
   API_END(h)
 }
 
@@ -1626,6 +1633,7 @@ int vaeassoc_comm_destroy(vaeassoc_handle h) {
     CUDA_OK(cudaStreamSynchronize(h->comm_stream));
     g_nccl.CommDestroy(h->comm);
     h->comm = nullptr; h->world = 1; h->rank = 0;
+    destroy_graphs(h);
   }
   API_END(h)
 }
@@ -1659,7 +1667,7 @@ int vaeassoc_debug_gemm(vaeassoc_handle h, int kind, int use_tc, int M, int N, i
                          kind == KIND_TN ? std::min(per * 8, kb - r0 * 8) : kb, -1, 0, 0, -1, 0, -1);
     group_set_counters(plan, h->gsync, h->n_ctr);
     if (!group_end(plan, err, sizeof err) || !group_upload(plan, err, sizeof err)) { group_destroy(plan); fail("%s", err); }
-    group_launch(plan, dsite, h->gsync + h->n_ctr + 2 * (h->max_sites - 1), 0, 0, h->stream);
+    group_launch(plan, dsite, h->gsync + h->n_ctr + 2 * (h->max_sites - 1), 0, 0, h->comm != nullptr || h->force_dynamic, h->stream);
     if (kind == KIND_TN && bias_grad) launch_colsum(B, ldb, K, N, bias_grad, h->stream);
     CUDA_OK(cudaStreamSynchronize(h->stream));
     if (getenv("VAEASSOC_TC_TIMELINE"))

@@ -218,6 +218,29 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// asynchronous form: the registers are valid only after tmem_ld_wait(v); the wait names them as in/out operands so
+// that the compiler keeps every use behind it
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                 "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),
+                 "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
+                 "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
+}
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
@@ -250,6 +273,12 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -316,10 +345,14 @@ enum { TF_A_MN = 1, TF_B_MN = 2, TF_REDUCE = 4, TF_AUX = 8, TF_ROUND = 16, TF_CO
 
 namespace {
 
+// polls with RELAXED loads: an acquire load is LDG.STRONG + CCTL.IVALL (invalidate the whole L1) per iteration, and a
+// producer lane spinning on it every ~100 ns slowed every shared-memory / shuffle / store instruction of the epilogue
+// warps on the same SM by 5x (measured: 1.4 us per 32x32 chunk instead of 0.27).  The caller issues ONE
+// fence.acq_rel.gpu after its last counter has been observed.
 __device__ __forceinline__ void wait_counter(const uint32_t* ctr, uint32_t need) {
   const long long t0 = clock64();
-  while (ld_acquire_gpu(ctr) < need) {
-    __nanosleep(64);
+  while (ld_relaxed_gpu(ctr) < need) {
+    __nanosleep(100);
     if (clock64() - t0 > 4000000000ll) __trap();    // ~2 s: a scheduling bug must not hang the GPU
   }
 }
@@ -364,7 +397,7 @@ template <int NP>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_group_kernel(const __grid_constant__ GParams<NP> params, const GTask* __restrict__ tasks, int ntasks,
                   uint32_t* __restrict__ counters, uint32_t* __restrict__ queue, int reset_first, int reset_count,
-                  unsigned long long* __restrict__ tl) {
+                  int dynamic_first, unsigned long long* __restrict__ tl) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t epi_base = base + kStages * STAGE_BYTES;
@@ -432,12 +465,21 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const GTask* __res
       ++published;
       return t;
     };
-    // first task = the cluster's index (no atomic, no cluster starts with two); the next ones come from the queue,
-    // popped at the start of the running task and published once its first stages are in flight
+    // first task = the cluster's index (no atomic round trip at launch); the next ones come from the queue, popped at
+    // the start of the running task and published once its first stages are in flight.  The static first task assumes
+    // that every cluster becomes resident without waiting for another kernel: when a collective that waits on a peer
+    // GPU may hold SMs (data parallel runs), `dynamic_first` makes the first task come from the queue as well, so that
+    // the smallest unfinished task is always held by a RUNNING cluster whatever share of the SMs this launch gets.
     const int nclusters = (int)(gridDim.x >> 1);
-    int t = ((int)(blockIdx.x >> 1) < ntasks) ? (int)(blockIdx.x >> 1) : -1;
+    const uint32_t queue_base = dynamic_first ? 0u : (uint32_t)nclusters;
+    int t = -1;
     if (lane == 0) {
-      if (rank == 0) publish((uint32_t)(t >= 0 ? t : ntasks)); else t = next_task();
+      if (rank == 0) {
+        const uint32_t first = dynamic_first ? atomicAdd(queue, 1u) : (uint32_t)(blockIdx.x >> 1);
+        t = publish(first);
+      } else {
+        t = next_task();
+      }
     }
     t = bcast(t);
     GTask tk = load_task(tasks, t);
@@ -456,7 +498,8 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const GTask* __res
         if (tk.wait_cnt > 0 || tk.wait2_ctr >= 0) {
           for (int c = 0; c < tk.wait_cnt; ++c) wait_counter(counters + tk.wait_ctr + c, (uint32_t)tk.wait_val);
           if (tk.wait2_ctr >= 0) wait_counter(counters + tk.wait2_ctr, (uint32_t)tk.wait2_val);
-          fence_proxy_async_all();           // the producing tasks' TMA stores -> our TMA loads
+          fence_acq_rel_gpu();               // pairs with the producers' red.release.gpu
+          fence_proxy_async_all();           // their generic-proxy stores -> our TMA (async proxy) loads
         }
         if (tl && rank == 0) { tl[kTL * t + 0] = gtimer(); tl[kTL * t + 5] = blockIdx.x >> 1; tl[kTL * t + 6] = t_entry; }
       }
@@ -478,7 +521,7 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const GTask* __res
           if (b_mn) tma_load_3d_pair(sb, &p->map_b, full_leader, 0, k0, nb0 >> 5);
           else tma_load_2d_pair(sb, &p->map_b, full_leader, k0, nb0);
           if (i == announce)                 // the next task: known to every role while this one streams
-            t_after = (rank == 0) ? publish((uint32_t)nclusters + raw) : next_task();
+            t_after = (rank == 0) ? publish(queue_base + raw) : next_task();
         }
         __syncwarp();
       }
@@ -539,7 +582,7 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const GTask* __res
     const int half = e >> 2;                // this warp takes chunks half, half + 2, ...
     const uint32_t ebuf = epi_base + e * EPI_WARP_BYTES;         // kEpiBufs rotating 32 x 32 boxes
     const uint32_t tmem_empty_leader0 = mapa(tmem_empty_bar(0), 0), tmem_empty_leader1 = mapa(tmem_empty_bar(1), 0);
-    uint32_t tcount = 0, cidx = 0, aux_phase = 0;               // cidx: chunks processed so far (box = cidx % 3)
+    uint32_t tcount = 0, cidx = 0, aux_phase = 0, red_pending = 0;   // cidx: chunks processed so far (box = cidx % 3)
     auto next_task_warp = [&]() -> int {
       int t = 0;
       if (lane == 0) t = next_task();
@@ -594,23 +637,47 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const GTask* __res
       }
       mbar_wait(tmem_full_bar(acc), (tcount >> 1) & 1);
       tc_fence_after();
-      if (tl && rank == 0 && warp == 2 && lane == 0) tl[kTL * t + 3] = gtimer();
+      if (tl && rank == 0 && warp == 2 && lane == 0) { tl[kTL * t + 3] = gtimer(); tl[kTL * t + 15] = (unsigned long long)clock64(); }
+      // a bulk reduce-add of an earlier task may still be reading one of the boxes: drain those reads once, here,
+      // instead of polling in every chunk (reduce tasks themselves keep the per-chunk wait below)
+      if (!reduce && red_pending) {
+        if (!use_aux && elect_one()) bulk_wait_read<0>();      // (the aux branch above has already waited)
+        __syncwarp();
+        red_pending = 0;
+      }
+      const bool interior_rows = row0 + 32 <= tk.M;
+      const uint32_t sts_base = ebuf + (uint32_t)lane * 128u, sts_x = (uint32_t)(lane & 7);
+      const int rr = lane >> 3, jj = lane & 7;
+      // read-back offsets of the transposed copy: row rr + 4k, 16-byte column jj; (rr + 4k) & 7 = rr + 4 (k & 1)
+      const uint32_t rb_even = (uint32_t)rr * 128u + ((uint32_t)(jj ^ rr) << 4);
+      const uint32_t rb_odd = (uint32_t)rr * 128u + ((uint32_t)(jj ^ (rr + 4)) << 4);
+      // accumulator bits of this lane's row, transformed in place.  The TMEM read of chunk i + 1 is issued as soon as
+      // chunk i sits in shared memory, so that it overlaps the copy-out of chunk i (8 warps reading TMEM at once get
+      // ~32 B/clk: ~1000 cycles per 4 KB chunk)
+      uint32_t v[32];
+      const uint32_t tmem_row = tmem_base + acc * kAccCols + ((uint32_t)(q * 32) << 16);
+      if (nmine > 0) tmem_ld32_issue(tmem_row + (uint32_t)(half * 32), v);
 #pragma unroll 1
       for (int i = 0; i < nmine; ++i, ++cidx) {
         const int c = half + 2 * i;
         const uint32_t b = cidx % kEpiBufs;
         const uint32_t ob = ebuf + b * CHUNK_BYTES;
-        uint32_t v[32];
-        tmem_ld32(tmem_base + acc * kAccCols + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-        float x[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
-        if (tl && rank == 0 && warp == 2 && lane == 0 && i == 0) tl[kTL * t + 9] = gtimer();
-        const float b_cur = i == 0 ? bv0 : i == 1 ? bv1 : i == 2 ? bv2 : bv3;
-        if (mask_in != nullptr) {          // relu': one bit per element, already in registers
+        tmem_ld_wait(v);
+        if (tl && rank == 0 && warp == 2 && lane == 0 && i == 0) tl[kTL * t + 9] = (unsigned long long)clock64();
+        if (mask_in != nullptr) {
+          // relu': one bit per element, already in registers; the tf32 rounding (round-to-nearest, ties away = add half
+          // an ulp to the magnitude, truncate) is folded into the same AND
           const uint32_t mw = i == 0 ? mw0 : i == 1 ? mw1 : i == 2 ? mw2 : mw3;
+          if (round_out) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = ((mw >> j) & 1u) ? x[j] : 0.0f;
+            for (int j = 0; j < 32; ++j) {
+              const uint32_t keep = (uint32_t)((int32_t)(mw << (31 - j)) >> 31);
+              v[j] = (v[j] + 0x1000u) & (keep & 0xffffe000u);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] &= (uint32_t)((int32_t)(mw << (31 - j)) >> 31);
+          }
         } else if (use_aux) {
           mbar_wait(aux_bar(e, b), (aux_phase >> b) & 1u);
           aux_phase ^= 1u << b;
@@ -620,66 +687,88 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const GTask* __res
             const float4 hv = lds128(ob + swz(lane, j));
             h[4 * j] = hv.x; h[4 * j + 1] = hv.y; h[4 * j + 2] = hv.z; h[4 * j + 3] = hv.w;
           }
-          switch (act) {
-            case ACT_RELU:
+          if (act == ACT_RELU) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) x[j] = h[j] > 0.0f ? x[j] : 0.0f;
-              break;
-            case ACT_SOFTPLUS:
+            for (int j = 0; j < 32; ++j) v[j] = h[j] > 0.0f ? v[j] : 0u;
+          } else if (act == ACT_SOFTPLUS) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) x[j] *= 1.0f - __expf(-h[j]);
-              break;
-            case ACT_SIGMOID:
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * (1.0f - __expf(-h[j])));
+          } else if (act == ACT_SIGMOID) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) x[j] *= h[j] * (1.0f - h[j]);
-              break;
-            default: break;
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * (h[j] * (1.0f - h[j])));
+          }
+          if (round_out) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = (v[j] + 0x1000u) & 0xffffe000u;
           }
         } else if (!reduce) {
           if (bias != nullptr) {
+            const float b_cur = i == 0 ? bv0 : i == 1 ? bv1 : i == 2 ? bv2 : bv3;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] += __shfl_sync(0xffffffffu, b_cur, j);
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __shfl_sync(0xffffffffu, b_cur, j));
           }
-          switch (act) {
-            case ACT_RELU:
+          if (act == ACT_RELU) {
+            // on the bits: negative floats are negative integers, so max(., 0) is the relu; with rounding, the half ulp
+            // is added first (a negative value stays negative, +0 .. half an ulp round to 0)
+            if (round_out) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.0f);
-              break;
-            case ACT_SOFTPLUS:
+              for (int j = 0; j < 32; ++j) v[j] = (uint32_t)max((int32_t)(v[j] + 0x1000u), 0) & 0xffffe000u;
+            } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.0f) + __logf(1.0f + __expf(-fabsf(x[j])));
-              break;
-            case ACT_SIGMOID:
+              for (int j = 0; j < 32; ++j) v[j] = (uint32_t)max((int32_t)v[j], 0);
+            }
+          } else {
+            if (act == ACT_SOFTPLUS) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) x[j] = __fdividef(1.0f, 1.0f + __expf(-x[j]));
-              break;
-            default: break;
+              for (int j = 0; j < 32; ++j) {
+                const float xv = __uint_as_float(v[j]);
+                v[j] = __float_as_uint(fmaxf(xv, 0.0f) + __logf(1.0f + __expf(-fabsf(xv))));
+              }
+            } else if (act == ACT_SIGMOID) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__fdividef(1.0f, 1.0f + __expf(-__uint_as_float(v[j]))));
+            }
+            if (round_out) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = (v[j] + 0x1000u) & 0xffffe000u;
+            }
           }
         }
-        if (round_out) {
+        const bool interior_cols = n0 + c * 32 + 32 <= N;
+        if (!interior_cols) {              // the pad columns N..roundup4(N) of the row pitch receive zeros
 #pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = round_tf32(x[j]);
+          for (int j = 0; j < 32; ++j) v[j] = (n0 + c * 32 + j < N) ? v[j] : 0u;
         }
-        if (n0 + c * 32 + 32 > N) {        // the pad columns N..roundup4(N) of the row pitch receive zeros
-#pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = (n0 + c * 32 + j < N) ? x[j] : 0.0f;
-        }
-        if (tl && rank == 0 && warp == 2 && lane == 0 && i == 0) tl[kTL * t + 11] = gtimer();
+        if (tl && rank == 0 && warp == 2 && lane == 0 && i == 0) tl[kTL * t + 11] = (unsigned long long)clock64();
         if (mask_out != nullptr) {
-          uint32_t mw = 0u;
+          // bit j = (output j > 0); relu outputs are >= +0, so "bits != 0": sign of the negated bits, shifted in from
+          // the right, two independent chains of 16
+          uint32_t wl = 0u, wh = 0u;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) mw |= (x[j] > 0.0f ? 1u : 0u) << j;
-          if (row0 + lane < tk.M) mask_out[(size_t)(row0 + lane) * (size_t)p->ldmask + (n0 >> 5) + c] = mw;
+          for (int j = 15; j >= 0; --j) {
+            wl = __funnelshift_l(0u - v[j], wl, 1);
+            wh = __funnelshift_l(0u - v[j + 16], wh, 1);
+          }
+          if (interior_rows || row0 + lane < tk.M)
+            mask_out[(size_t)(row0 + lane) * (size_t)p->ldmask + (n0 >> 5) + c] = (wh << 16) | wl;
         }
-        // box b was last handed to a bulk reduce-add three chunks ago (if at all): wait until that one has read it.
-        // (In the aux case the lane overwrites exactly the 128 bytes it has just read: in place, no hazard.)
-        if (tl && rank == 0 && warp == 2 && lane == 0 && i == 0) tl[kTL * t + 12] = gtimer();
-        if (elect_one()) bulk_wait_read<kEpiBufs - 1>();
-        __syncwarp();
-        if (tl && rank == 0 && warp == 2 && lane == 0 && i == 0) tl[kTL * t + 13] = gtimer();
+        if (tl && rank == 0 && warp == 2 && lane == 0 && i == 0) tl[kTL * t + 12] = (unsigned long long)clock64();
+        if (reduce) {
+          // box b was handed to a bulk reduce-add three chunks ago: wait until that one has read it
+          if (elect_one()) bulk_wait_read<kEpiBufs - 1>();
+          __syncwarp();
+        }
+        if (tl && rank == 0 && warp == 2 && lane == 0 && i == 0) tl[kTL * t + 13] = (unsigned long long)clock64();
+        // (in the aux case the lane overwrites exactly the 128 bytes it has just read: in place, no hazard)
+        {
+          const uint32_t sb = sts_base + b * CHUNK_BYTES;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) sts128(ob + swz(lane, j), x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
-        if (tl && rank == 0 && warp == 2 && lane == 0 && i == 0) tl[kTL * t + 14] = gtimer();
+          for (int j = 0; j < 8; ++j)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sb + (((uint32_t)j ^ sts_x) << 4)), "r"(v[4 * j]),
+                         "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3]) : "memory");
+        }
+        if (tl && rank == 0 && warp == 2 && lane == 0 && i == 0) tl[kTL * t + 14] = (unsigned long long)clock64();
+        if (i + 1 < nmine) tmem_ld32_issue(tmem_row + (uint32_t)((c + 2) * 32), v);
         if (reduce) {
           fence_proxy_async_smem();
           __syncwarp();
@@ -687,19 +776,26 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const GTask* __res
             tma_reduce_add_2d(&p->map_c, ob, n0 + c * 32, row0);
             bulk_commit();
           }
+          red_pending = 1;
         } else {
           // transposed read-back: 8 lanes cover one 128-byte row segment, 4 rows per instruction -> coalesced 128-bit
-          // stores; rows >= M and columns >= roundup4(N) are clipped here (the TMA loads zero-filled them)
+          // stores; rows >= M and columns >= roundup4(N) are clipped (the TMA loads zero-filled them)
           __syncwarp();
-          const int rr = lane >> 3, jj = lane & 7;
           const int col = n0 + c * 32 + jj * 4;
-          if (col < ((N + 3) & ~3)) {
-            float* dst = p->c_ptr + (size_t)(row0 + rr) * (size_t)p->ldc + col;
-            const size_t step = 4 * (size_t)p->ldc;
+          float* dst = p->c_ptr + (size_t)(row0 + rr) * (size_t)p->ldc + col;
+          const size_t step = 4 * (size_t)p->ldc;
+          if (interior_rows && interior_cols) {
+            float4 o[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = lds128(ob + ((k & 1) ? rb_odd : rb_even) + (uint32_t)k * 512u);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + k * step), "f"(o[k].x), "f"(o[k].y), "f"(o[k].z), "f"(o[k].w) : "memory");
+          } else if (col < ((N + 3) & ~3)) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
               if (row0 + rr + 4 * k < tk.M) {
-                const float4 o = lds128(ob + swz(rr + 4 * k, jj));
+                const float4 o = lds128(ob + ((k & 1) ? rb_odd : rb_even) + (uint32_t)k * 512u);
                 asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + k * step), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
               }
             }
@@ -708,17 +804,22 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const GTask* __res
         if (colsum != nullptr) {
           // bias gradient of the layer below = column sums of this dgrad output: lane <-> column, 32 conflict-free
           // reads of the staged tile (rows past M hold exact zeros), one fp32 RED per column and warp
-          float cs = 0.0f;
+          float cs0 = 0.0f, cs1 = 0.0f, cs2 = 0.0f, cs3 = 0.0f;
+          const uint32_t cb = ob + (uint32_t)(lane & 3) * 4u;
+          const uint32_t cj = (uint32_t)(lane >> 2);
 #pragma unroll
-          for (int r = 0; r < 32; ++r) {
-            float v1;
-            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v1) : "r"(ob + swz(r, lane >> 2) + (uint32_t)(lane & 3) * 4u));
-            cs += v1;
+          for (int r = 0; r < 32; r += 4) {
+            float a0, a1, a2, a3;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a0) : "r"(cb + (uint32_t)r * 128u + ((cj ^ (uint32_t)(r & 7)) << 4)));
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a1) : "r"(cb + (uint32_t)(r + 1) * 128u + ((cj ^ (uint32_t)((r + 1) & 7)) << 4)));
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a2) : "r"(cb + (uint32_t)(r + 2) * 128u + ((cj ^ (uint32_t)((r + 2) & 7)) << 4)));
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a3) : "r"(cb + (uint32_t)(r + 3) * 128u + ((cj ^ (uint32_t)((r + 3) & 7)) << 4)));
+            cs0 += a0; cs1 += a1; cs2 += a2; cs3 += a3;
           }
           const int col = n0 + c * 32 + lane;
-          if (col < N) atomicAdd(colsum + col, cs);
+          if (col < N) atomicAdd(colsum + col, (cs0 + cs1) + (cs2 + cs3));
         }
-        if (tl && rank == 0 && warp == 2 && lane == 0 && i == 0) tl[kTL * t + 10] = gtimer();
+        if (tl && rank == 0 && warp == 2 && lane == 0 && i == 0) tl[kTL * t + 10] = (unsigned long long)clock64();
         if (use_aux && i + kEpiBufs < nmine) {
           __syncwarp();                    // every lane has finished with box b: refill it with the aux tile 3 chunks ahead
           if (elect_one()) {
@@ -993,8 +1094,8 @@ bool group_upload(GroupPlan* g, char* err, int errlen) {
 }
 
 namespace {
-void launch_site(const GroupPlan* g, int site, uint32_t* queue, int reset_first, int reset_count, unsigned long long* tl,
-                 cudaStream_t s) {
+void launch_site(const GroupPlan* g, int site, uint32_t* queue, int reset_first, int reset_count, int dynamic_first,
+                 unsigned long long* tl, cudaStream_t s) {
   const GroupSite& st = g->sites[site];
   if (st.n_tasks <= 0) return;
   const int clusters = std::min(st.n_tasks, kNumSMs / 2);
@@ -1002,12 +1103,12 @@ void launch_site(const GroupPlan* g, int site, uint32_t* queue, int reset_first,
     GParams<kSiteProblemsSmall> prm;
     memcpy(prm.p, g->problems.data() + st.first_problem, (size_t)st.n_problems * sizeof(GProblem));
     gemm_group_kernel<kSiteProblemsSmall><<<2 * clusters, kThreads, SMEM_BYTES, s>>>(
-        prm, g->d_tasks + st.first_task, st.n_tasks, g->d_counters, queue, reset_first, reset_count, tl);
+        prm, g->d_tasks + st.first_task, st.n_tasks, g->d_counters, queue, reset_first, reset_count, dynamic_first, tl);
   } else {
     GParams<kSiteProblemsLarge> prm;
     memcpy(prm.p, g->problems.data() + st.first_problem, (size_t)st.n_problems * sizeof(GProblem));
     gemm_group_kernel<kSiteProblemsLarge><<<2 * clusters, kThreads, SMEM_BYTES, s>>>(
-        prm, g->d_tasks + st.first_task, st.n_tasks, g->d_counters, queue, reset_first, reset_count, tl);
+        prm, g->d_tasks + st.first_task, st.n_tasks, g->d_counters, queue, reset_first, reset_count, dynamic_first, tl);
   }
 }
 }  // namespace
@@ -1015,8 +1116,9 @@ void launch_site(const GroupPlan* g, int site, uint32_t* queue, int reset_first,
 // launches a site; the grid is one CTA pair per TPC at most.  `queue` = two zero-initialised words owned by this
 // launch site (task-queue head, clusters-left count; the kernel rewinds them and the counters
 // [reset_first, +reset_count) when its last cluster leaves)
-void group_launch(const GroupPlan* g, int site, uint32_t* queue, int reset_first, int reset_count, cudaStream_t s) {
-  launch_site(g, site, queue, reset_first, reset_count, nullptr, s);
+void group_launch(const GroupPlan* g, int site, uint32_t* queue, int reset_first, int reset_count, int dynamic_first,
+                  cudaStream_t s) {
+  launch_site(g, site, queue, reset_first, reset_count, dynamic_first, nullptr, s);
 }
 
 // debug only (VAEASSOC_TC_TIMELINE): one more run of the range with %globaltimer stamps per task; prints, relative to
@@ -1028,7 +1130,7 @@ void group_debug_timeline(const GroupPlan* g, int site, uint32_t* queue, int res
   if (cudaMalloc(&dev, (size_t)count * kTL * 8 + 192 * 8) != cudaSuccess) return;
   cudaMemsetAsync(dev, 0, (size_t)count * kTL * 8 + 192 * 8, s);
   const int clusters = std::min(count, kNumSMs / 2);
-  launch_site(g, site, queue, reset_first, reset_count, dev, s);
+  launch_site(g, site, queue, reset_first, reset_count, 0, dev, s);
   cudaStreamSynchronize(s);
   std::vector<unsigned long long> h((size_t)count * kTL + 192);
   cudaMemcpy(h.data(), dev, (size_t)count * kTL * 8 + 192 * 8, cudaMemcpyDeviceToHost);
@@ -1049,11 +1151,12 @@ void group_debug_timeline(const GroupPlan* g, int site, uint32_t* queue, int res
   for (int k = 0; k < show; ++k) {
     const int i = (k < show / 2 || show == count) ? k : count - (show - k);
     const GTask& tk = g->tasks[first + i];
-    fprintf(stderr, "  task %4d prob %2d (%2d,%2d) nkb %3d cl %2llu entry %6.2f | prod %6.2f mma %6.2f..%6.2f (%llu cyc) epi %6.2f..%6.2f us | ld0 %6.2f chunk0 %6.2f loop %6.2f | math %6.2f mask %6.2f wait %6.2f sts %6.2f\n", i,
+    fprintf(stderr, "  task %4d prob %2d (%2d,%2d) nkb %3d cl %2llu entry %6.2f | prod %6.2f mma %6.2f..%6.2f (%llu cyc) epi %6.2f..%6.2f us | ld0 %6.0f chunk0 %6.0f loop %6.2f | math %6.0f mask %6.0f wait %6.0f sts %6.0f\n", i,
             tk.problem, tk.m_blk, tk.n_blk, tk.nkb, h[kTL * i + 5], (h[kTL * i + 6] - t0) * 1e-3, (h[kTL * i + 0] - t0) * 1e-3,
             (h[kTL * i + 1] - t0) * 1e-3, (h[kTL * i + 2] - t0) * 1e-3, h[kTL * i + 7], (h[kTL * i + 3] - t0) * 1e-3, (h[kTL * i + 4] - t0) * 1e-3,
-            (h[kTL * i + 9] - t0) * 1e-3, (h[kTL * i + 10] - t0) * 1e-3, (h[kTL * i + 8] - t0) * 1e-3,
-            (h[kTL * i + 11] - t0) * 1e-3, (h[kTL * i + 12] - t0) * 1e-3, (h[kTL * i + 13] - t0) * 1e-3, (h[kTL * i + 14] - t0) * 1e-3);
+(double)(long long)(h[kTL * i + 9] - h[kTL * i + 15]), (double)(long long)(h[kTL * i + 10] - h[kTL * i + 15]), (h[kTL * i + 8] - t0) * 1e-3,
+            (double)(long long)(h[kTL * i + 11] - h[kTL * i + 15]), (double)(long long)(h[kTL * i + 12] - h[kTL * i + 15]),
+            (double)(long long)(h[kTL * i + 13] - h[kTL * i + 15]), (double)(long long)(h[kTL * i + 14] - h[kTL * i + 15]));
   }
 }
 

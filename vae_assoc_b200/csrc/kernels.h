@@ -63,7 +63,10 @@ bool group_end(GroupPlan* g, char* err, int errlen);
 int group_site_tasks(const GroupPlan* g, int site);
 void group_set_counters(GroupPlan* g, uint32_t* d_counters, int n);
 bool group_upload(GroupPlan* g, char* err, int errlen);
-void group_launch(const GroupPlan* g, int site, uint32_t* queue, int reset_first, int reset_count, cudaStream_t s);
+// dynamic_first: every task (the first one included) comes from the atomic queue -- required whenever a kernel that
+// waits on a peer GPU (NCCL) may hold SMs while this launch is resident
+void group_launch(const GroupPlan* g, int site, uint32_t* queue, int reset_first, int reset_count, int dynamic_first,
+                  cudaStream_t s);
 void group_debug_timeline(const GroupPlan* g, int site, uint32_t* queue, int reset_first, int reset_count,
                           cudaStream_t s);   // debug: per-task %globaltimer stamps to stderr
 constexpr int kGroupSignalsPerTile = 16;   // epilogue warps of a CTA pair
