@@ -162,6 +162,9 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     args = ap.parse_args()
 
+    # stdout carries exactly ONE JSON line: NCCL's banner ("NCCL version ...", printed to stdout when the image sets
+    # NCCL_DEBUG=VERSION) goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -247,13 +250,15 @@ def main():
     barrier()
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     launches = model.launch_count() - l0
-    if rank == 0 and ms_total < 400.0:
-        # keep the same work running until the 100 ms sampler has seen the region (these steps are not timed)
-        t_more = time.time()
-        while len(sampler.lines) < 3 and time.time() - t_more < 2.0:
-            for k in range(20):
-                model.partial_fit_async(pool[k % pool_n])
-            model.synchronize()
+    if ms_total < 400.0:
+        # keep the same work running until the 100 ms clock sampler has seen it (these steps are not timed).  EVERY rank
+        # runs the same number of extra steps (the count derives from the rank-reduced time): under data parallelism a
+        # step contains two all-reduces, and a rank that stepped alone would wait for its peers forever
+        n_extra = int(min(5000, max(20, 600.0 / max(ms_total / args.steps, 1e-3))))
+        for k in range(n_extra):
+            model.partial_fit_async(pool[k % pool_n])
+        model.synchronize()
+        barrier()
     clocks = sampler.stop() if rank == 0 else None
     last_cost = float(model.last_cost())
     ms_step = ms_total / args.steps
