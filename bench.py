@@ -160,11 +160,14 @@ def main():
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="diagnostics: only the HBM-resident timing loop")
     args = ap.parse_args()
 
-    # stdout carries exactly ONE JSON line: NCCL's banner ("NCCL version ...", printed to stdout when the image sets
-    # NCCL_DEBUG=VERSION) goes to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # stdout carries exactly ONE JSON line: everything else a library prints there (NCCL's "NCCL version ..." banner comes
+    # from C code) is sent to stderr by pointing file descriptor 1 at stderr; the JSON line goes to the saved descriptor
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -189,7 +192,7 @@ def main():
                     cpu_baseline=dict(value=sps, unit="samples/s", cores=cores, kind="port",
                                       sample="%d steps of %d pairs after %d warm-up" % (steps, cpu_batch, warm)),
                     e2e=dict(value=sps, unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-        print(json.dumps(line))
+        json_out.write(json.dumps(line) + "\n"); json_out.flush()
         return
 
     import torch
@@ -263,6 +266,14 @@ def main():
     last_cost = float(model.last_cost())
     ms_step = ms_total / args.steps
     value = Bg * args.steps / (ms_total * 1e-3)
+
+    if args.quick:
+        if rank == 0:
+            json_out.write(json.dumps(dict(value=value, ms_per_step=ms_step, n_gpus=world, quick=True)) + "\n"); json_out.flush()
+        model.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- end to end: pinned host batches -> H2D -> step -> D2H of the cost, every step --------------------------
     host_n = 4
@@ -353,7 +364,7 @@ def main():
                                     sample="5 steps of %d pairs after 1 warm-up, torch-CPU fp32 restatement "
                                            "(not TensorFlow)" % cpu_batch)
     if rank == 0:
-        print(json.dumps(line))
+        json_out.write(json.dumps(line) + "\n"); json_out.flush()
     model.close()
     if world > 1:
         dist.destroy_process_group()

@@ -153,6 +153,8 @@ struct vaeassoc_ctx {
   std::vector<std::vector<Op>> ops_loss_mod, ops_bwd_dec_mod, ops_bwd_enc_mod;   // per-modality: run concurrently
   cudaStream_t side[VAEASSOC_MAX_MODALITIES - 1] = {nullptr, nullptr, nullptr};   // modality m > 0 runs on side[m-1]
   cudaEvent_t ev_fork = nullptr, ev_join[VAEASSOC_MAX_MODALITIES - 1] = {nullptr, nullptr, nullptr};
+  cudaStream_t aux_stream = nullptr;      // small kernels off the critical path (gradient memset, cost finalize)
+  cudaEvent_t ev_aux_fork = nullptr, ev_aux_join = nullptr;
   cudaStream_t wstream[VAEASSOC_MAX_MODALITIES] = {nullptr, nullptr, nullptr, nullptr};   // wgrad branch of modality m
   cudaEvent_t ev_wfork[VAEASSOC_MAX_MODALITIES] = {nullptr, nullptr, nullptr, nullptr},
               ev_wjoin[VAEASSOC_MAX_MODALITIES] = {nullptr, nullptr, nullptr, nullptr};
@@ -164,6 +166,7 @@ struct vaeassoc_ctx {
   struct Seg { int site = 0, reset_first = 0, reset_count = 0; };
   Seg seg_enc, seg_dec, seg_bwd_dec, seg_bwd_enc;     // fused segments of the train step (dense modalities, tf32)
   bool fused = false;
+  int dp_single = -1;                                 // VAEASSOC_DP_SINGLE=0/1; default (-1): one all-reduce per step iff fused
   bool force_dynamic = false;                         // VAEASSOC_DYNAMIC_FIRST: the data-parallel task-queue mode on one GPU (tests)
   std::vector<Op> ops_colsum_dec, ops_colsum_enc;     // bias gradients that no GEMM epilogue produces (d a, d heads)
   // graphs
@@ -966,8 +969,12 @@ void join_colsums(Ctx* c, std::vector<Op>& ops, cudaStream_t s) {
 // segment A1: zero grads, forward, losses, decoder backward   (gradient bucket 0 complete at its end)
 void enqueue_a1(Ctx* c, cudaStream_t s) {
   const int M = c->cfg.n_modalities;
-  CUDA_OK(cudaMemsetAsync(c->g, 0, (size_t)(c->n_flat + 32) * sizeof(float), s));
   if (c->fused) {
+    // the gradient buffer is first touched by the decoder backward: its memset runs as a parallel branch of the forward
+    CUDA_OK(cudaEventRecord(c->ev_aux_fork, s));
+    CUDA_OK(cudaStreamWaitEvent(c->aux_stream, c->ev_aux_fork, 0));
+    CUDA_OK(cudaMemsetAsync(c->g, 0, (size_t)(c->n_flat + 32) * sizeof(float), c->aux_stream));
+    CUDA_OK(cudaEventRecord(c->ev_aux_join, c->aux_stream));
     // four launches of the persistent tile kernel carry every dense layer of both modalities (csrc/gemm_group.cu)
     launch_seg(c, c->seg_enc, s);
     run_ops(c, c->ops_latent_fwd, s);
@@ -975,11 +982,13 @@ void enqueue_a1(Ctx* c, cudaStream_t s) {
     fork_modalities(c, s);
     for (int m = 0; m < M; ++m) run_ops(c, c->ops_loss_mod[m], mod_stream(c, m, s));
     join_modalities(c, s);
+    CUDA_OK(cudaStreamWaitEvent(s, c->ev_aux_join, 0));
     fork_colsums(c, c->ops_colsum_dec, s);
     launch_seg(c, c->seg_bwd_dec, s);
     join_colsums(c, c->ops_colsum_dec, s);
     return;
   }
+  CUDA_OK(cudaMemsetAsync(c->g, 0, (size_t)(c->n_flat + 32) * sizeof(float), s));
   fork_modalities(c, s);
   for (int m = 0; m < M; ++m) run_ops(c, c->ops_enc_mod[m], mod_stream(c, m, s));
   join_modalities(c, s);
@@ -996,9 +1005,17 @@ void enqueue_a1(Ctx* c, cudaStream_t s) {
 void enqueue_a2(Ctx* c, cudaStream_t s, int advance) {
   run_ops(c, c->ops_latent_bwd, s);
   if (c->fused) {
+    // the cost reduction (block partials of the loss kernels -> cost slot, step counter) runs next to the encoder backward
+    CUDA_OK(cudaEventRecord(c->ev_aux_fork, s));
+    CUDA_OK(cudaStreamWaitEvent(c->aux_stream, c->ev_aux_fork, 0));
+    launch_finalize(finalize_args(c, advance), c->aux_stream);
+    c->launches += 1;
+    CUDA_OK(cudaEventRecord(c->ev_aux_join, c->aux_stream));
     fork_colsums(c, c->ops_colsum_enc, s);
     launch_seg(c, c->seg_bwd_enc, s);
     join_colsums(c, c->ops_colsum_enc, s);
+    CUDA_OK(cudaStreamWaitEvent(s, c->ev_aux_join, 0));
+    return;
   } else {
     fork_modalities(c, s);
     for (int m = 0; m < c->cfg.n_modalities; ++m) run_bwd_ops(c, m, c->ops_bwd_enc_mod[m], mod_stream(c, m, s));
@@ -1122,7 +1139,30 @@ void run_step(Ctx* c, bool with_adam) {
     }
     return;
   }
+  if (c->dp_single >= 0 ? c->dp_single != 0 : c->fused) {
+    // one all-reduce of the whole flat gradient buffer (+ cost slot) on the compute stream after the backward pass: half
+    // the NCCL launches and no cross-stream events.  The persistent tile kernels occupy every SM, so the bucket-0
+    // all-reduce of the two-bucket schedule below cannot run next to the encoder backward; its 24 NVLS CTAs only take
+    // SMs away from the tile kernel while they wait for the slowest rank.  Measured at 8 ranks, 8192 pairs per rank:
+    // 0.413 ms per step against 0.653 ms with the two overlapped buckets (0.320 ms on one GPU)
+    if (c->cfg.use_graph) { CUDA_OK(cudaGraphLaunch(c->graph_a1, s)); c->launches += c->graph_a1_nodes; }
+    else enqueue_a1(c, s);
+    if (c->cfg.use_graph && with_adam) { CUDA_OK(cudaGraphLaunch(c->graph_a2, s)); c->launches += c->graph_a2_nodes; }
+    else enqueue_a2(c, s, with_adam ? 1 : 0);
+    allreduce(c, c->g, c->n_flat + 32, s);
+    c->launches += 1;
+    if (with_adam) {
+      if (c->cfg.use_graph) { CUDA_OK(cudaGraphLaunch(c->graph_adam, s)); c->launches += c->graph_adam_nodes; }
+      else enqueue_adam(c, s);
+    } else {
+      launch_publish_cost(c->g + c->n_flat, c->last_cost, s);
+      c->launches += 1;
+    }
+    return;
+  }
   // data parallel: bucket 0 (decoders) is all-reduced on the comm stream while the encoder backward runs
+  // (capturing the NCCL kernels into one whole-step graph was tried and hung at communicator teardown / on the
+  // synchronous partial_fit path with NCCL 2.28.9: the collectives stay eager launches between three graphs)
   if (c->cfg.use_graph) { CUDA_OK(cudaGraphLaunch(c->graph_a1, s)); c->launches += c->graph_a1_nodes; }
   else enqueue_a1(c, s);
   CUDA_OK(cudaEventRecord(c->ev_bucket, s));
@@ -1208,6 +1248,7 @@ int vaeassoc_create(const vaeassoc_config* cfg, vaeassoc_handle* out) {
     CUDA_OK(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     c->force_dynamic = getenv("VAEASSOC_DYNAMIC_FIRST") != nullptr;
+    if (const char* e = getenv("VAEASSOC_DP_SINGLE")) c->dp_single = atoi(e) != 0 ? 1 : 0;
     for (int i = 0; i < 2; ++i) {
       CUDA_OK(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
       CUDA_OK(cudaEventCreateWithFlags(&c->ev_consumed[i], cudaEventDisableTiming));
@@ -1222,6 +1263,9 @@ int vaeassoc_create(const vaeassoc_config* cfg, vaeassoc_handle* out) {
       CUDA_OK(cudaEventCreateWithFlags(&c->ev_wjoin[i], cudaEventDisableTiming));
     }
     CUDA_OK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CUDA_OK(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreateWithFlags(&c->ev_aux_fork, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&c->ev_aux_join, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&c->ev_bucket, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming));
     build_layout(c);
@@ -1260,6 +1304,9 @@ int vaeassoc_destroy(vaeassoc_handle h) {
     if (h->ev_wjoin[i]) cudaEventDestroy(h->ev_wjoin[i]);
   }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
+  if (h->ev_aux_fork) cudaEventDestroy(h->ev_aux_fork);
+  if (h->ev_aux_join) cudaEventDestroy(h->ev_aux_join);
   if (h->ev_bucket) cudaEventDestroy(h->ev_bucket);
   if (h->ev_comm) cudaEventDestroy(h->ev_comm);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
