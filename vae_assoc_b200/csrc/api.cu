@@ -166,7 +166,7 @@ struct vaeassoc_ctx {
   struct Seg { int site = 0, reset_first = 0, reset_count = 0; };
   Seg seg_enc, seg_dec, seg_bwd_dec, seg_bwd_enc;     // fused segments of the train step (dense modalities, tf32)
   bool fused = false;
-  int dp_single = -1;                                 // VAEASSOC_DP_SINGLE=0/1; default (-1): one all-reduce per step iff fused
+  int dp_single = -1;                                 // VAEASSOC_DP_SINGLE=0/1; default (-1): one all-reduce per step iff fused and world > 4
   bool force_dynamic = false;                         // VAEASSOC_DYNAMIC_FIRST: the data-parallel task-queue mode on one GPU (tests)
   std::vector<Op> ops_colsum_dec, ops_colsum_enc;     // bias gradients that no GEMM epilogue produces (d a, d heads)
   // graphs
@@ -1139,12 +1139,13 @@ void run_step(Ctx* c, bool with_adam) {
     }
     return;
   }
-  if (c->dp_single >= 0 ? c->dp_single != 0 : c->fused) {
+  if (c->dp_single >= 0 ? c->dp_single != 0 : (c->fused && c->world > 4)) {
     // one all-reduce of the whole flat gradient buffer (+ cost slot) on the compute stream after the backward pass: half
     // the NCCL launches and no cross-stream events.  The persistent tile kernels occupy every SM, so the bucket-0
     // all-reduce of the two-bucket schedule below cannot run next to the encoder backward; its 24 NVLS CTAs only take
     // SMs away from the tile kernel while they wait for the slowest rank.  Measured at 8 ranks, 8192 pairs per rank:
-    // 0.413 ms per step against 0.653 ms with the two overlapped buckets (0.320 ms on one GPU)
+    // 0.413 ms per step against 0.653 ms with the two overlapped buckets (0.320 ms on one GPU).  With 2 and 4 ranks the
+    // overlapped buckets are still slightly ahead (0.366 / 0.374 ms against 0.380 at 2 ranks), hence world > 4
     if (c->cfg.use_graph) { CUDA_OK(cudaGraphLaunch(c->graph_a1, s)); c->launches += c->graph_a1_nodes; }
     else enqueue_a1(c, s);
     if (c->cfg.use_graph && with_adam) { CUDA_OK(cudaGraphLaunch(c->graph_a2, s)); c->launches += c->graph_a2_nodes; }

@@ -999,16 +999,23 @@ bool tc_supported(int kind, const GemmArgs& a) {
   return batch >= 32;
 }
 
-int group_tile_width(int N) {
-  const int tiles_n = (N + 255) / 256;
-  return std::min(256, (((N + tiles_n - 1) / tiles_n) + 63) / 64 * 64);
+// tile width of a contraction with `batch_rows` batch rows (M of the row-wise forms, K of the weight gradient).  With
+// many row blocks the widest tile wins (fewest operand bytes per FLOP: the main loops are bound by the L2 -> SM fabric).
+// With few row blocks (B = 100: ONE) a 256-wide tile leaves 70 of the 74 CTA pairs idle and its epilogue (4 chunks per
+// warp, ~5.5 us) sits on the layer-to-layer critical path: narrower tiles spread the columns over more pairs and cut the
+// epilogue to 1-2 chunks per warp.
+int group_tile_width(int N, int batch_rows) {
+  const int row_blocks = (batch_rows + BM - 1) / BM;
+  const int max_bn = row_blocks >= 16 ? 256 : (row_blocks >= 4 ? 128 : 64);
+  const int tiles_n = (N + max_bn - 1) / max_bn;
+  return std::min(max_bn, (((N + tiles_n - 1) / tiles_n) + 63) / 64 * 64);
 }
 
 // adds the contraction to the plan; returns its problem index or -1 (err filled)
 int group_add_problem(GroupPlan* g, int kind, const GemmArgs& a, char* err, int errlen) {
   GProblem p;
   memset(&p, 0, sizeof p);
-  const int BN = group_tile_width(a.N);
+  const int BN = getenv("VAEASSOC_WIDE_TILES") ? group_tile_width(a.N, 1 << 20) : group_tile_width(a.N, kind == 2 ? a.K : a.M);
   bool ok = true;
   switch (kind) {
     case 0:    // NN: A [M,K] K-major ; B [K,N] MN-major
