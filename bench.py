@@ -330,9 +330,14 @@ def main():
     kernels.sort(key=lambda k: -k["ms"])
     top = kernels[0]
     eager_ms = sum(k["ms"] for k in kernels)
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch of the four fused segments, from the committed ncu --set full
+    # capture of this workload (profiles/r1_group_final_ncu.md); other workloads / kernels: not captured -> null
+    ncu_traffic = {"seg_fwd_enc": 41.2e6, "seg_fwd_dec": 27.1e6, "seg_bwd_dec": 119.0e6, "seg_bwd_enc": 123.6e6}
+    traffic = ncu_traffic.get(top["name"]) if (args.config == "ref" and B == 8192 and args.precision == "tf32") else None
     roofline = dict(bound=top.get("bound", "hbm"), kernel=top["name"], achieved=top.get("achieved"),
                     peak=pk["tensor"] if top.get("bound") == "tensor" else pk["hbm"], unit=top.get("unit"),
-                    frac=top.get("frac"), traffic=None, peak_source=pk["src"],
+                    frac=top.get("frac"), traffic=traffic, traffic_unit="bytes per launch (DRAM read + write, ncu)",
+                    peak_source=pk["src"],
                     share_of_step=top["ms"] / eager_ms,
                     note="tcgen05 kind::tf32 nominal peak is half the bf16 figure used as `peak`"
                     if top.get("bound") == "tensor" else "")
