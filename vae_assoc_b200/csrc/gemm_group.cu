@@ -71,7 +71,9 @@ constexpr int kAccCols = 256;                     // TMEM columns per accumulato
 constexpr int kTmemCols = 2 * kAccCols;
 constexpr int kTL = 16;                          // debug timeline: 64-bit stamps per task
 constexpr int kSched = 8;                        // depth of the task-index ring
-constexpr int SMEM_BYTES = kStages * STAGE_BYTES + kEpiWarps * EPI_WARP_BYTES + 512 /*barriers, task ring*/ + 1024 /*align*/;
+constexpr int kBiasStrip = 128;                  // bytes per epilogue warp: the 32 bias values of the current chunk
+constexpr int SMEM_BYTES = kStages * STAGE_BYTES + kEpiWarps * EPI_WARP_BYTES + 512 /*barriers, task ring*/ +
+                           kEpiWarps * kBiasStrip + 1024 /*align*/;
 static_assert(SMEM_BYTES <= 232448, "more than the 227 KB a CTA may opt into");
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------
@@ -397,11 +399,14 @@ template <int NP>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_group_kernel(const __grid_constant__ GParams<NP> params, const GTask* __restrict__ tasks, int ntasks,
                   uint32_t* __restrict__ counters, uint32_t* __restrict__ queue, int reset_first, int reset_count,
-                  int dynamic_first, unsigned long long* __restrict__ tl) {
+                  int mode, unsigned long long* __restrict__ tl) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t epi_base = base + kStages * STAGE_BYTES;
   const uint32_t bar_base = epi_base + kEpiWarps * EPI_WARP_BYTES;
+  const uint32_t strip_base = bar_base + 512u;
+  const int dynamic_first = mode & 1;
+  const bool bias_smem = (mode & 2) != 0, tma_store = (mode & 4) != 0;
   // barriers: full[s] (leader CTA only), empty[s], tmem_full[2], tmem_empty[2] (leader CTA only), aux[epilogue warp],
   // sched_full[kSched], sched_empty[kSched] (leader CTA only); then the TMEM slot and the task-index ring
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -640,7 +645,7 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const GTask* __res
       if (tl && rank == 0 && warp == 2 && lane == 0) { tl[kTL * t + 3] = gtimer(); tl[kTL * t + 15] = (unsigned long long)clock64(); }
       // a bulk reduce-add of an earlier task may still be reading one of the boxes: drain those reads once, here,
       // instead of polling in every chunk (reduce tasks themselves keep the per-chunk wait below)
-      if (!reduce && red_pending) {
+      if (!reduce && !tma_store && red_pending) {
         if (!use_aux && elect_one()) bulk_wait_read<0>();      // (the aux branch above has already waited)
         __syncwarp();
         red_pending = 0;
@@ -704,8 +709,24 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const GTask* __res
         } else if (!reduce) {
           if (bias != nullptr) {
             const float b_cur = i == 0 ? bv0 : i == 1 ? bv1 : i == 2 ? bv2 : bv3;
+            if (bias_smem) {
+              // 32 bias values of the chunk through a 128-byte strip: 1 store + 8 broadcast 128-bit loads instead of 32 shuffles
+              const uint32_t strip = strip_base + (uint32_t)e * kBiasStrip;
+              __syncwarp();
+              asm volatile("st.shared.f32 [%0], %1;" ::"r"(strip + (uint32_t)lane * 4u), "f"(b_cur) : "memory");
+              __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __shfl_sync(0xffffffffu, b_cur, j));
+              for (int j = 0; j < 8; ++j) {
+                const float4 bq = lds128(strip + (uint32_t)j * 16u);
+                v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + bq.x);
+                v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + bq.y);
+                v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + bq.z);
+                v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + bq.w);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __shfl_sync(0xffffffffu, b_cur, j));
+            }
           }
           if (act == ACT_RELU) {
             // on the bits: negative floats are negative integers, so max(., 0) is the relu; with rounding, the half ulp
@@ -753,8 +774,8 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const GTask* __res
             mask_out[(size_t)(row0 + lane) * (size_t)p->ldmask + (n0 >> 5) + c] = (wh << 16) | wl;
         }
         if (tl && rank == 0 && warp == 2 && lane == 0 && i == 0) tl[kTL * t + 12] = (unsigned long long)clock64();
-        if (reduce) {
-          // box b was handed to a bulk reduce-add three chunks ago: wait until that one has read it
+        if (reduce || tma_store) {
+          // box b was handed to a bulk store / reduce-add three chunks ago: wait until that one has read it
           if (elect_one()) bulk_wait_read<kEpiBufs - 1>();
           __syncwarp();
         }
@@ -769,11 +790,12 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const GTask* __res
         }
         if (tl && rank == 0 && warp == 2 && lane == 0 && i == 0) tl[kTL * t + 14] = (unsigned long long)clock64();
         if (i + 1 < nmine) tmem_ld32_issue(tmem_row + (uint32_t)((c + 2) * 32), v);
-        if (reduce) {
+        if (reduce || tma_store) {
           fence_proxy_async_smem();
           __syncwarp();
           if (elect_one()) {
-            tma_reduce_add_2d(&p->map_c, ob, n0 + c * 32, row0);
+            if (reduce) tma_reduce_add_2d(&p->map_c, ob, n0 + c * 32, row0);
+            else tma_store_2d(&p->map_c, ob, n0 + c * 32, row0);
             bulk_commit();
           }
           red_pending = 1;
@@ -836,7 +858,7 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const GTask* __res
       if (elect_one()) {
         mbar_arrive_cluster_relaxed(acc ? tmem_empty_leader1 : tmem_empty_leader0, 0u);
         if (tk.signal_ctr >= 0) {
-          if (reduce) { bulk_wait_complete(); fence_proxy_async_all(); }   // bulk reduce-adds performed, then publish
+          if (reduce || tma_store) { bulk_wait_complete(); fence_proxy_async_all(); }   // bulk stores performed, then publish
           red_release_gpu_add(counters + tk.signal_ctr, 1u);
         }
       }
@@ -1105,17 +1127,19 @@ void launch_site(const GroupPlan* g, int site, uint32_t* queue, int reset_first,
                  unsigned long long* tl, cudaStream_t s) {
   const GroupSite& st = g->sites[site];
   if (st.n_tasks <= 0) return;
+  static const int env_mode = (getenv("VAEASSOC_EPI_BIAS_SHFL") ? 0 : 2) | (getenv("VAEASSOC_EPI_TMA_STORE") ? 4 : 0);
+  const int mode = (dynamic_first ? 1 : 0) | env_mode;
   const int clusters = std::min(st.n_tasks, kNumSMs / 2);
   if (st.n_problems <= kSiteProblemsSmall) {
     GParams<kSiteProblemsSmall> prm;
     memcpy(prm.p, g->problems.data() + st.first_problem, (size_t)st.n_problems * sizeof(GProblem));
     gemm_group_kernel<kSiteProblemsSmall><<<2 * clusters, kThreads, SMEM_BYTES, s>>>(
-        prm, g->d_tasks + st.first_task, st.n_tasks, g->d_counters, queue, reset_first, reset_count, dynamic_first, tl);
+        prm, g->d_tasks + st.first_task, st.n_tasks, g->d_counters, queue, reset_first, reset_count, mode, tl);
   } else {
     GParams<kSiteProblemsLarge> prm;
     memcpy(prm.p, g->problems.data() + st.first_problem, (size_t)st.n_problems * sizeof(GProblem));
     gemm_group_kernel<kSiteProblemsLarge><<<2 * clusters, kThreads, SMEM_BYTES, s>>>(
-        prm, g->d_tasks + st.first_task, st.n_tasks, g->d_counters, queue, reset_first, reset_count, dynamic_first, tl);
+        prm, g->d_tasks + st.first_task, st.n_tasks, g->d_counters, queue, reset_first, reset_count, mode, tl);
   }
 }
 }  // namespace
