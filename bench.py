@@ -339,8 +339,12 @@ def main():
                     frac=top.get("frac"), traffic=traffic, traffic_unit="bytes per launch (DRAM read + write, ncu)",
                     peak_source=pk["src"],
                     share_of_step=top["ms"] / eager_ms,
-                    note="tcgen05 kind::tf32 nominal peak is half the bf16 figure used as `peak`"
+                    note="peak = measured cuBLAS bf16 (MEASURED_PEAKS.json); this path computes in kind::tf32, whose nominal peak "
+                         "is half of bf16 and whose measured cuBLAS 8192^3 throughput on this pool is 710.7 TFLOP/s "
+                         "(profiles/r1_tf32_peak.json): frac_of_tf32_cublas = achieved / 710.7"
                     if top.get("bound") == "tensor" else "")
+    if top.get("bound") == "tensor" and top.get("achieved"):
+        roofline["frac_of_tf32_cublas"] = top["achieved"] / 710.7
     # algorithmic FLOPs of one step = sum over the contractions of the schedule (2*M*N*K each); for the dense configs this
     # is SURVEY 8d's per-sample figure x B (7 744 400 x B at the reference arch)
     step_flops = sum(f for (_, f, _) in acc.values())
