@@ -1,0 +1,53 @@
+"""Host batching semantics of vae_assoc_b200/dataset.py against the behaviour documented for the reference
+(/root/reference/dataset.py:6-72): one shuffle at construction, split by ratio, sequential batches, a fresh shuffle of
+the CURRENT order at every epoch wrap (the tail that does not fill a batch is dropped), numpy RNG consumed identically."""
+import numpy as np
+
+from vae_assoc_b200 import dataset
+
+
+def _expected_stream(data, batch, n_batches, seed, validation_ratio=.1, test_ratio=.1):
+    """Plain restatement of the documented behaviour on the TRAIN split, physically re-gathering rows."""
+    np.random.seed(seed)
+    perm = np.arange(data.shape[0]); np.random.shuffle(perm)
+    rows = data[perm]
+    n = rows.shape[0]
+    train = rows[:int((1 - validation_ratio - test_ratio) * n)]
+    out, pos = [], 0
+    for _ in range(n_batches):
+        if pos + batch > train.shape[0]:
+            p = np.arange(train.shape[0]); np.random.shuffle(p)
+            train = train[p]; pos = 0
+        out.append(train[pos:pos + batch]); pos += batch
+    return out, train.shape[0]
+
+
+def test_split_sizes_and_batches_match_reference_behaviour():
+    data = np.arange(103 * 3, dtype=np.float32).reshape(103, 3)
+    want, n_train = _expected_stream(data, 16, 23, seed=5)
+    np.random.seed(5)
+    ds = dataset.construct_datasets(data, validation_ratio=.1, test_ratio=.1)
+    assert ds.train._data.shape[0] == n_train == int(0.8 * 103)
+    assert ds.validation._data.shape[0] == int(0.9 * 103) - int(0.8 * 103)
+    assert ds.test._data.shape[0] == 103 - int(0.9 * 103)
+    for k, w in enumerate(want):
+        got, labels = ds.train.next_batch(16)
+        assert labels is None
+        np.testing.assert_array_equal(got, w, err_msg="batch %d" % k)
+    assert ds.train._epochs_completed == 23 // (n_train // 16) - (1 if 23 % (n_train // 16) == 0 else 0)
+    # every split is disjoint and together they are the data
+    allrows = np.concatenate([ds.train._data, ds.validation._data, ds.test._data])
+    assert sorted(map(tuple, allrows)) == sorted(map(tuple, data))
+
+
+def test_labels_travel_with_rows_and_no_shuffle_keeps_order():
+    data = np.arange(40, dtype=np.float32).reshape(20, 2)
+    labels = np.arange(20).reshape(20, 1)
+    ds = dataset.construct_datasets(data, labels, shuffle=False, validation_ratio=.2, test_ratio=.2)
+    x, y = ds.train.next_batch(5)
+    np.testing.assert_array_equal(x, data[:5]); np.testing.assert_array_equal(y, labels[:5])
+    np.random.seed(1)
+    for _ in range(7):
+        x, y = ds.train.next_batch(5)
+        np.testing.assert_array_equal(x[:, 0] // 2, y[:, 0])        # row i carries label i through every reshuffle
+    np.testing.assert_array_equal(ds.train._data[:, 0] // 2, ds.train._labels[:, 0])
