@@ -4,7 +4,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libvaeassoc.so")
+# VAEASSOC_LIB selects a build-time variant of the library (vae_assoc_b200/build.py: build_variant); default = the product
+LIB_PATH = os.environ.get("VAEASSOC_LIB") or os.path.join(HERE, "libvaeassoc.so")
 MAX_MODALITIES = 4
 ABI_VERSION = 1
 

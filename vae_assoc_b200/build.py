@@ -63,6 +63,30 @@ def _compile(src, log):
     return obj, True
 
 
+def build_variant(name, defines, verbose=True):
+    """A build-time variant of the library next to the default one (e.g. `w16`: 16 epilogue warps per CTA in the tile
+    kernel): vae_assoc_b200/libvaeassoc_<name>.so, selected at run time with VAEASSOC_LIB=<path>."""
+    obj_dir = OBJ + "_" + name
+    lib = os.path.join(HERE, "libvaeassoc_%s.so" % name)
+    os.makedirs(obj_dir, exist_ok=True)
+    objs = []
+    for src in SOURCES:
+        obj = os.path.join(obj_dir, os.path.splitext(src)[0] + ".o")
+        cmd = [_nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-c", os.path.join(CSRC, src), "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        with open(os.path.join(obj_dir, src + ".log"), "w") as f:
+            f.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed for %s (%s):\n%s" % (src, name, r.stderr[-4000:]))
+        objs.append(obj)
+    r = subprocess.run([_nvcc(), "-shared", "-o", lib] + objs + ["-cudart", "static", "-ldl", "-lpthread"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n" + r.stderr[-4000:])
+    if verbose:
+        print("[build] linked", lib)
+    return lib
+
+
 def build(force=False, verbose=True):
     os.makedirs(OBJ, exist_ok=True)
     if force:
@@ -82,4 +106,7 @@ def build(force=False, verbose=True):
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv)
+    if "--w16" in sys.argv:
+        build_variant("w16", ["VAEASSOC_EPI_WARPS=16"])
+    else:
+        build(force="--force" in sys.argv)

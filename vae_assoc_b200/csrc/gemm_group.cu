@@ -58,14 +58,16 @@ constexpr int BM_CTA = 128;      // rows of the tile per CTA; UMMA M = 256 over 
 constexpr int BM = 2 * BM_CTA;
 constexpr int BK = 32;           // fp32 elements per stage = one 128-byte swizzle row
 constexpr int UMMA_K = 8;        // tf32: 32 bytes per instruction
-constexpr int kEpiWarps = 8;     // two warps per TMEM lane quarter, each takes every other 32-column chunk
+constexpr int kEpiWarps = VAEASSOC_EPI_WARPS;   // kSlots warps per TMEM lane quarter; slot s takes chunks s, s + kSlots, ...
+constexpr int kSlots = kEpiWarps / 4;
+static_assert(kEpiWarps % 4 == 0 && kSlots >= 1 && kSlots <= 4, "epilogue warps come in groups of four (one per TMEM lane quarter)");
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kStages = 4;
 constexpr int A_BYTES = BM_CTA * BK * 4;          // 16 KB
 constexpr int B_BYTES_MAX = 128 * BK * 4;         // BN/2 <= 128 columns
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES_MAX;
 constexpr int CHUNK_BYTES = 32 * 32 * 4;          // one 32 x 32 fp32 epilogue box
-constexpr int kEpiBufs = 3;                       // rotating boxes per epilogue warp: aux tile in, result out (in place)
+constexpr int kEpiBufs = kEpiWarps <= 8 ? 3 : 1;  // rotating boxes per epilogue warp: aux tile in, result out (in place)
 constexpr int EPI_WARP_BYTES = kEpiBufs * CHUNK_BYTES;
 constexpr int kAccCols = 256;                     // TMEM columns per accumulator
 constexpr int kTmemCols = 2 * kAccCols;
@@ -584,7 +586,7 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const GTask* __res
     // ===================== epilogue (warps 2..9 of both CTAs) =====================
     const int e = warp - 2;                 // epilogue warp index
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int half = e >> 2;                // this warp takes chunks half, half + 2, ...
+    const int slot = e >> 2;                // this warp takes chunks slot, slot + kSlots, ...
     const uint32_t ebuf = epi_base + e * EPI_WARP_BYTES;         // kEpiBufs rotating 32 x 32 boxes
     const uint32_t tmem_empty_leader0 = mapa(tmem_empty_bar(0), 0), tmem_empty_leader1 = mapa(tmem_empty_bar(1), 0);
     uint32_t tcount = 0, cidx = 0, aux_phase = 0, red_pending = 0;   // cidx: chunks processed so far (box = cidx % 3)
@@ -606,7 +608,7 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const GTask* __res
       const int row0 = tk.m_blk * BM + (int)rank * BM_CTA + q * 32;    // first output row of this warp
       const int n0 = tk.n_blk * BN;
       const int nchunks = (row0 < tk.M) ? min(BN / 32, (N - n0 + 31) / 32) : 0;   // warp-uniform
-      const int nmine = nchunks > half ? (nchunks - half + 1) >> 1 : 0;            // chunks half, half + 2, ... of this warp
+      const int nmine = nchunks > slot ? (nchunks - slot + kSlots - 1) / kSlots : 0;   // chunks slot, slot + kSlots, ... of this warp
       const uint32_t acc = tcount & 1;
       // everything the chunk loop needs from global memory is requested NOW, while the main loop of this task runs
       // (a fresh L2 round trip costs ~1.5 us while the operand streams of 148 SMs are in flight): the bias values of all
@@ -615,19 +617,20 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const GTask* __res
       uint32_t* __restrict__ mask_out = (tk.flags & TF_MASK_OUT) ? p->mask_out : nullptr;
       float bv0 = 0.0f, bv1 = 0.0f, bv2 = 0.0f, bv3 = 0.0f;
       if (bias != nullptr) {
-        const int col = n0 + half * 32 + lane;
+        const int col = n0 + slot * 32 + lane;
+        constexpr int cs = 32 * kSlots;                    // column stride between this warp's chunks
         if (0 < nmine && col < N) bv0 = __ldg(bias + col);
-        if (1 < nmine && col + 64 < N) bv1 = __ldg(bias + col + 64);
-        if (2 < nmine && col + 128 < N) bv2 = __ldg(bias + col + 128);
-        if (3 < nmine && col + 192 < N) bv3 = __ldg(bias + col + 192);
+        if (1 < nmine && col + cs < N) bv1 = __ldg(bias + col + cs);
+        if (2 < nmine && col + 2 * cs < N) bv2 = __ldg(bias + col + 2 * cs);
+        if (3 < nmine && col + 3 * cs < N) bv3 = __ldg(bias + col + 3 * cs);
       }
       uint32_t mw0 = 0u, mw1 = 0u, mw2 = 0u, mw3 = 0u;
       if (mask_in != nullptr && row0 + lane < tk.M) {
-        const uint32_t* mrow = mask_in + (size_t)(row0 + lane) * (size_t)p->ldmask + (n0 >> 5) + half;
+        const uint32_t* mrow = mask_in + (size_t)(row0 + lane) * (size_t)p->ldmask + (n0 >> 5) + slot;
         if (0 < nmine) mw0 = __ldg(mrow);
-        if (1 < nmine) mw1 = __ldg(mrow + 2);
-        if (2 < nmine) mw2 = __ldg(mrow + 4);
-        if (3 < nmine) mw3 = __ldg(mrow + 6);
+        if (1 < nmine) mw1 = __ldg(mrow + kSlots);
+        if (2 < nmine) mw2 = __ldg(mrow + 2 * kSlots);
+        if (3 < nmine) mw3 = __ldg(mrow + 3 * kSlots);
       }
       if (use_aux && nmine > 0 && elect_one()) {
         bulk_wait_read<0>();               // a reduce-add of the previous task may still be reading these boxes
@@ -636,7 +639,7 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const GTask* __res
           if (i < nmine) {
             const uint32_t b = (cidx + i) % kEpiBufs;
             mbar_arrive_expect_tx(aux_bar(e, b), CHUNK_BYTES);
-            tma_load_2d(ebuf + b * CHUNK_BYTES, &p->map_aux, aux_bar(e, b), n0 + (half + 2 * i) * 32, row0);
+            tma_load_2d(ebuf + b * CHUNK_BYTES, &p->map_aux, aux_bar(e, b), n0 + (slot + kSlots * i) * 32, row0);
           }
         }
       }
@@ -661,10 +664,10 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const GTask* __res
       // ~32 B/clk: ~1000 cycles per 4 KB chunk)
       uint32_t v[32];
       const uint32_t tmem_row = tmem_base + acc * kAccCols + ((uint32_t)(q * 32) << 16);
-      if (nmine > 0) tmem_ld32_issue(tmem_row + (uint32_t)(half * 32), v);
+      if (nmine > 0) tmem_ld32_issue(tmem_row + (uint32_t)(slot * 32), v);
 #pragma unroll 1
       for (int i = 0; i < nmine; ++i, ++cidx) {
-        const int c = half + 2 * i;
+        const int c = slot + kSlots * i;
         const uint32_t b = cidx % kEpiBufs;
         const uint32_t ob = ebuf + b * CHUNK_BYTES;
         tmem_ld_wait(v);
@@ -789,7 +792,7 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const GTask* __res
                          "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3]) : "memory");
         }
         if (tl && rank == 0 && warp == 2 && lane == 0 && i == 0) tl[kTL * t + 14] = (unsigned long long)clock64();
-        if (i + 1 < nmine) tmem_ld32_issue(tmem_row + (uint32_t)((c + 2) * 32), v);
+        if (i + 1 < nmine) tmem_ld32_issue(tmem_row + (uint32_t)((c + kSlots) * 32), v);
         if (reduce || tma_store) {
           fence_proxy_async_smem();
           __syncwarp();
@@ -846,7 +849,7 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const GTask* __res
           __syncwarp();                    // every lane has finished with box b: refill it with the aux tile 3 chunks ahead
           if (elect_one()) {
             mbar_arrive_expect_tx(aux_bar(e, b), CHUNK_BYTES);
-            tma_load_2d(ob, &p->map_aux, aux_bar(e, b), n0 + (c + 2 * kEpiBufs) * 32, row0);
+            tma_load_2d(ob, &p->map_aux, aux_bar(e, b), n0 + (c + kSlots * kEpiBufs) * 32, row0);
           }
         }
       }

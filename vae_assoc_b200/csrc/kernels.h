@@ -69,7 +69,10 @@ void group_launch(const GroupPlan* g, int site, uint32_t* queue, int reset_first
                   cudaStream_t s);
 void group_debug_timeline(const GroupPlan* g, int site, uint32_t* queue, int reset_first, int reset_count,
                           cudaStream_t s);   // debug: per-task %globaltimer stamps to stderr
-constexpr int kGroupSignalsPerTile = 16;   // epilogue warps of a CTA pair
+#ifndef VAEASSOC_EPI_WARPS
+#define VAEASSOC_EPI_WARPS 8            // epilogue warps per CTA of the tile kernel (build-time variant: 16)
+#endif
+constexpr int kGroupSignalsPerTile = 2 * VAEASSOC_EPI_WARPS;   // epilogue warps of a CTA pair
 
 // ------------------------------------------------------------------------------------------------------
 // conv / transposed-conv layers of the hidden_conv=True modality as im2col -> GEMM -> col2im (conv.cu)
