@@ -27,12 +27,15 @@ extern "C" {
 #endif
 
 #define VAEASSOC_MAX_MODALITIES 4
-#define VAEASSOC_ABI_VERSION 1
+#define VAEASSOC_ABI_VERSION 2
 
 typedef struct vaeassoc_ctx* vaeassoc_handle;
 
 enum { VAEASSOC_RELU = 0, VAEASSOC_SOFTPLUS = 1 };                 /* transfer_fct, vae_assoc.py:26,502   */
-enum { VAEASSOC_FP32 = 0, VAEASSOC_TF32 = 1 };                     /* SIMT FFMA  |  tcgen05 kind::tf32    */
+/* SIMT FFMA (1e-4 path) | tcgen05 kind::tf32 (2e-3 path) | bf16 operands: NAMED by SURVEY 8b's contract but REJECTED by
+ * vaeassoc_create / vaeassoc_set_precision -- 8-bit mantissas miss the 2e-3 tolerance of the tensor-core path (tf32,
+ * 10 bits, measures 6e-4), so the library refuses instead of silently training at another precision */
+enum { VAEASSOC_FP32 = 0, VAEASSOC_TF32 = 1, VAEASSOC_BF16 = 2 };
 enum { VAEASSOC_PARAMS = 0, VAEASSOC_GRADS = 1, VAEASSOC_ADAM_M = 2, VAEASSOC_ADAM_V = 3 };
 
 /* one entry of `network_architectures` (vae_assoc.py:73-76) plus its `binary` / `weights` items (:31-41) */
@@ -43,6 +46,8 @@ typedef struct {
   int32_t hidden_conv;
   int32_t binary;
   float weight;
+  char scope[32];               /* na["scope"] (vae_assoc.py:168,248: tf.variable_scope(scope)) -> variable names
+                                   "<scope>/Variable_k", "<scope>_1/Variable_k"; empty -> "image","joint","modal2","modal3" */
 } vaeassoc_modality;
 
 /* constructor arguments of AssocVariationalAutoEncoder (vae_assoc.py:26-27) */
@@ -118,8 +123,14 @@ int vaeassoc_partial_fit_host(vaeassoc_handle h, const float* const* x_host, con
                               float* cost_host);
 /* pipelined host form used by train(): uploads batch k+1 on a copy stream while step k computes.
  * `vaeassoc_submit_host` returns as soon as the batch is queued; costs are read back with
- * vaeassoc_cost_history / vaeassoc_cost_read. */
+ * vaeassoc_cost_history / vaeassoc_cost_read.
+ * BUFFER LIFETIME: the H2D copies are asynchronous.  Pageable buffers are staged by the driver before the call returns
+ * and may be reused at once; PINNED (page-locked) buffers are read by DMA after the call returns and must stay
+ * allocated and unmodified until `vaeassoc_upload_wait(h, k)` has returned for this submit's index k (= the number of
+ * submits made before it; vaeassoc_submit_count).  train() and bench.py rotate pinned slots behind that call. */
 int vaeassoc_submit_host(vaeassoc_handle h, const float* const* x_host, const float* eps_host);
+int64_t vaeassoc_submit_count(vaeassoc_handle h);                     /* submits so far = index of the next one */
+int vaeassoc_upload_wait(vaeassoc_handle h, int64_t submit_index);    /* blocks until that submit's H2D completed */
 /* every submit also queues an async D2H of that step's cost into a pinned host ring (4096 entries);
  * this synchronises the stream and returns the costs of submits [first_submit, first_submit + n). */
 int vaeassoc_submit_costs(vaeassoc_handle h, int64_t first_submit, int64_t n, float* dst_host);
@@ -152,6 +163,12 @@ enum {
 };
 int vaeassoc_probe_get(vaeassoc_handle h, int kind, int modality, float* dst_host, int64_t capacity_floats,
                        int64_t* n_written);
+/* relu sign bits of a hidden layer after the most recent tensor-core step (tf32 mode, relu, dense modality): layer
+ * 0 = h1, 1 = h2 (encoder), 2 = g1, 3 = g2 (decoder); bit (row, col) = activation > 0, 32 columns per word,
+ * `*words_per_row` words per row.  These are the masks the dgrad epilogues apply (TF ReluGrad, y > 0); parity tests feed
+ * them to the oracle so that gradients are compared under IDENTICAL masks.  Fails if the layer has no mask. */
+int vaeassoc_probe_mask(vaeassoc_handle h, int layer, int modality, uint32_t* dst_host, int64_t capacity_words,
+                        int64_t* n_written, int64_t* words_per_row);
 
 /* ---- synthetic paired batches: replaces dataset.py:22-43 next_batch + utils.py:142-195 ------------------- */
 /* rows [row0, row0 + n_rows) of the global stream; x_dev[m] dense [n_rows, n_input_m] device */
@@ -167,6 +184,19 @@ int vaeassoc_philox_normal(vaeassoc_handle h, uint32_t seed, uint32_t tag, int64
 int vaeassoc_comm_unique_id(const char* nccl_lib_path, void* id128);           /* rank 0: ncclGetUniqueId   */
 int vaeassoc_comm_init(vaeassoc_handle h, const char* nccl_lib_path, const void* id128, int rank, int world);
 int vaeassoc_comm_destroy(vaeassoc_handle h);
+/* broadcast rank 0's parameters, Adam slots and step count to every rank (replicas must start identical: the
+ * all-reduce only averages gradients); collective -- every rank calls it */
+int vaeassoc_comm_sync_state(vaeassoc_handle h);
+/* ncclCommGetAsyncError: 0 = healthy; on an asynchronous NCCL failure the communicator is aborted (ncclCommAbort),
+ * the handle's error text is set and a non-zero status is returned (also checked by vaeassoc_stream_sync) */
+int vaeassoc_comm_check(vaeassoc_handle h);
+
+/* ---- checkpoints: tf.train.Saver.save / .restore over ALL variables incl. the Adam slots (vae_assoc.py:70,427-463) --
+ * One self-describing binary file ("VAEASSOC" magic, tensor table with the TF-style names, parameters, both Adam
+ * slots, step count).  vaeassoc_load matches tensors by NAME and shape and fails (non-zero, handle unchanged) on a
+ * mismatch.  TensorFlow V1 checkpoints are imported on the Python side (vae_assoc_b200/tf_checkpoint.py). */
+int vaeassoc_save(vaeassoc_handle h, const char* path);
+int vaeassoc_load(vaeassoc_handle h, const char* path);
 
 /* ---- introspection for benchmarks --------------------------------------------------------------------------- */
 /* number of kernels this library launched on the handle since creation (bench.py's gpu_launches) */

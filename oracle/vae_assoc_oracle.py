@@ -397,7 +397,11 @@ class OracleAssocVAE(object):
         return dict(cost=cost, vae_costs=costs, vae_reconstr_losses=rec, vae_latent_losses=lat, assoc_costs=assoc)
 
     # ---- backward (what tf.train.AdamOptimizer.minimize differentiates, vae_assoc.py:373-374) ----
-    def loss_and_grads(self, X, eps, global_batch=None):
+    def loss_and_grads(self, X, eps, global_batch=None, masks=None):
+        """`masks` (optional, dense relu modalities): per modality a dict {"h1","h2","g1","g2"} of boolean [B, width]
+        arrays that REPLACE relu'(.) = 1[h > 0] in the backward pass (TF ReluGrad, y > 0).  The tensor-core parity test
+        reads the masks the CUDA path actually applied (vaeassoc_probe_mask) and passes them here, so that gradients
+        are compared under identical masks and the residual is the kernels' arithmetic alone."""
         M = len(self.network_architectures)
         X = [np.asarray(x, dtype=self.dtype) for x in X]
         eps = np.asarray(eps, dtype=self.dtype)
@@ -406,6 +410,11 @@ class OracleAssocVAE(object):
         fw = self.forward(X, eps)
         ls = self.loss(X, fw, global_batch)
         f, lam = self.transfer_fct, self.assoc_lambda
+
+        def ag(m, name, h):
+            if masks is not None and masks[m] is not None:
+                return np.asarray(masks[m][name], dtype=h.dtype)
+            return act_grad_from_output(f, h)
         grads = [[None] * len(ps) for ps in self.params]
         dz_list = []
         # decoders
@@ -432,9 +441,9 @@ class OracleAssocVAE(object):
             else:
                 da = self._q(t["r_da"], da)
                 G[12] = dc["g2"].T @ da; G[13] = da.sum(0)
-                d = self._q(t["r_dg2"], (da @ self._q(t["d_o"], P[12]).T) * act_grad_from_output(f, dc["g2"]))
+                d = self._q(t["r_dg2"], (da @ self._q(t["d_o"], P[12]).T) * ag(m, "g2", dc["g2"]))
                 G[10] = dc["g1"].T @ d; G[11] = d.sum(0)
-                d = self._q(t["r_dg1"], (d @ self._q(t["d_d2"], P[10]).T) * act_grad_from_output(f, dc["g1"]))
+                d = self._q(t["r_dg1"], (d @ self._q(t["d_d2"], P[10]).T) * ag(m, "g1", dc["g1"]))
                 G[8] = dc["z"].T @ d; G[9] = d.sum(0)
                 dz = d @ self._q(t["d_d1"], P[8]).T
             dz_list.append(dz)
@@ -468,10 +477,10 @@ class OracleAssocVAE(object):
                 dm_, dl_ = self._q(t["r_dhd"], dmu[m]), self._q(t["r_dhd"], dlv[m])
                 G[4] = ec["h2"].T @ dm_; G[5] = dm_.sum(0)
                 G[6] = ec["h2"].T @ dl_; G[7] = dl_.sum(0)
-                d = (dm_ @ self._q(t["d_hd"], P[4]).T + dl_ @ self._q(t["d_hd"], P[6]).T) * act_grad_from_output(f, ec["h2"])
+                d = (dm_ @ self._q(t["d_hd"], P[4]).T + dl_ @ self._q(t["d_hd"], P[6]).T) * ag(m, "h2", ec["h2"])
                 d = self._q(t["r_dh2"], d)
                 G[2] = ec["h1"].T @ d; G[3] = d.sum(0)
-                d = self._q(t["r_dh1"], (d @ self._q(t["d_e2"], P[2]).T) * act_grad_from_output(f, ec["h1"]))
+                d = self._q(t["r_dh1"], (d @ self._q(t["d_e2"], P[2]).T) * ag(m, "h1", ec["h1"]))
                 G[0] = ec["x"].T @ d; G[1] = d.sum(0)
         probes = dict(fw)
         probes.update(ls)

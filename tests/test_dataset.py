@@ -51,3 +51,34 @@ def test_labels_travel_with_rows_and_no_shuffle_keeps_order():
         x, y = ds.train.next_batch(5)
         np.testing.assert_array_equal(x[:, 0] // 2, y[:, 0])        # row i carries label i through every reshuffle
     np.testing.assert_array_equal(ds.train._data[:, 0] // 2, ds.train._labels[:, 0])
+
+
+def test_extract_loaders_follow_reference_order(tmp_path):
+    """utils.extract_images / extract_jnt_fa_parms (/root/reference/utils.py:142-195): scaling, ordering, digit filter,
+    and the Python-2 pickle the reference's files are (protocol 2, latin1)."""
+    import pickle
+    from vae_assoc_b200 import utils
+    rng = np.random.RandomState(3)
+    # keys as in the UJI set: the ordering of images is by the LAST letter, that of the parameters by the whole key
+    imgs = {"b": [rng.randint(0, 256, (28, 28)).astype(np.uint8) for _ in range(3)],
+            "a": [rng.randint(0, 256, (28, 28)).astype(np.uint8) for _ in range(2)],
+            "7": [rng.randint(0, 256, (28, 28)).astype(np.uint8) for _ in range(2)]}
+    fa = {k: [rng.normal(size=147) for _ in v] for k, v in imgs.items()}
+    x = utils.extract_images(data=imgs, only_digits=False)
+    assert x.shape == (7, 784) and x.dtype == np.float32 and 0.0 <= x.min() and x.max() <= 1.0
+    np.testing.assert_allclose(x[0], imgs["7"][0].reshape(-1) / 255.0, rtol=1e-6)       # '7' < 'a' < 'b'
+    np.testing.assert_allclose(x[2], imgs["a"][0].reshape(-1) / 255.0, rtol=1e-6)
+    assert utils.extract_images(data=imgs, only_digits=True).shape == (2, 784)
+    p, mean, std = utils.extract_jnt_fa_parms(data=fa, only_digits=False)
+    assert p.shape == (7, 147)
+    np.testing.assert_allclose(mean, p.mean(0)); np.testing.assert_allclose(std, p.std(0))
+    np.testing.assert_array_equal(p[0], fa["7"][0])
+    assert utils.extract_jnt_trajs(data={"3": [np.ones((5, 7))]}).shape == (1, 35)
+    # from files, as the training script does (vae_assoc_ujichar_img_jnt.py:21-36)
+    fi, ff = tmp_path / "img.pkl", tmp_path / "fa.pkl"
+    fi.write_bytes(pickle.dumps(imgs, protocol=2)); ff.write_bytes(pickle.dumps(fa, protocol=2))
+    np.random.seed(0)
+    ds, m2, s2 = utils.load_paired_datasets(str(fi), str(ff))
+    assert ds.train._data.shape[1] == 931
+    assert ds.train._data.shape[0] + ds.validation._data.shape[0] + ds.test._data.shape[0] == 7
+    np.testing.assert_allclose(m2, mean)

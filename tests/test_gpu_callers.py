@@ -73,6 +73,7 @@ def test_ujichar_script_and_model_viewer_call_patterns(tmp_path):
     viewer_model = vae_assoc.AssocVariationalAutoEncoder([img_network_architecture, jnt_network_architecture],
                                                          binary=[True, False], transfer_fct=tf.nn.relu,
                                                          assoc_lambda=5, learning_rate=0.0001, batch_size=batch_size)
+    assert len(tf.all_variables()) == 86                    # baxter_vae_assoc_writer.py:599 prints this count
     folder, name = os.path.split(fname)
     viewer_model.restore_model(folder, name)
     z_mu = np.zeros((viewer_model.batch_size, n_z))

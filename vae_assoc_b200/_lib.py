@@ -7,10 +7,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # VAEASSOC_LIB selects a build-time variant of the library (vae_assoc_b200/build.py: build_variant); default = the product
 LIB_PATH = os.environ.get("VAEASSOC_LIB") or os.path.join(HERE, "libvaeassoc.so")
 MAX_MODALITIES = 4
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 RELU, SOFTPLUS = 0, 1
-FP32, TF32 = 0, 1
+FP32, TF32, BF16 = 0, 1, 2
 PARAMS, GRADS, ADAM_M, ADAM_V = 0, 1, 2, 3
 (PROBE_Z_MEAN, PROBE_Z_LOG_SIGMA_SQ, PROBE_Z, PROBE_X_RECONSTR_MEAN, PROBE_RECONSTR_LOSS, PROBE_LATENT_LOSS,
  PROBE_VAE_COST, PROBE_ASSOC_COST, PROBE_D_Z_MEAN, PROBE_D_Z_LOG_SIGMA_SQ, PROBE_EPS) = range(11)
@@ -19,7 +19,7 @@ PARAMS, GRADS, ADAM_M, ADAM_V = 0, 1, 2, 3
 class Modality(C.Structure):
     _fields_ = [("n_input", C.c_int32), ("n_hidden_recog_1", C.c_int32), ("n_hidden_recog_2", C.c_int32),
                 ("n_hidden_gener_1", C.c_int32), ("n_hidden_gener_2", C.c_int32), ("hidden_conv", C.c_int32),
-                ("binary", C.c_int32), ("weight", C.c_float)]
+                ("binary", C.c_int32), ("weight", C.c_float), ("scope", C.c_char * 32)]
 
 
 class Config(C.Structure):
@@ -66,18 +66,25 @@ SIGNATURES = {
     "vaeassoc_cost_history": (C.c_int, [Handle, C.c_int64, C.c_int64, C.c_void_p]),
     "vaeassoc_partial_fit_host": (C.c_int, [Handle, FloatPP, C.c_void_p, C.POINTER(C.c_float)]),
     "vaeassoc_submit_host": (C.c_int, [Handle, FloatPP, C.c_void_p]),
+    "vaeassoc_submit_count": (C.c_int64, [Handle]),
+    "vaeassoc_upload_wait": (C.c_int, [Handle, C.c_int64]),
     "vaeassoc_submit_costs": (C.c_int, [Handle, C.c_int64, C.c_int64, C.c_void_p]),
     "vaeassoc_eval_cost": (C.c_int, [Handle, FloatPP, I64P, C.c_void_p, C.POINTER(C.c_float)]),
     "vaeassoc_encode": (C.c_int, [Handle, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "vaeassoc_decode": (C.c_int, [Handle, C.c_int, C.c_void_p, C.c_void_p]),
     "vaeassoc_reconstruct": (C.c_int, [Handle, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "vaeassoc_probe_get": (C.c_int, [Handle, C.c_int, C.c_int, C.c_void_p, C.c_int64, I64P]),
+    "vaeassoc_probe_mask": (C.c_int, [Handle, C.c_int, C.c_int, C.c_void_p, C.c_int64, I64P, I64P]),
     "vaeassoc_synth_batch": (C.c_int, [Handle, C.c_uint32, C.c_uint32, C.c_int64, C.c_int64, FloatPP]),
     "vaeassoc_philox_normal": (C.c_int, [Handle, C.c_uint32, C.c_uint32, C.c_int64, C.c_int64, C.c_int32,
                                          C.c_uint32, C.c_void_p]),
     "vaeassoc_comm_unique_id": (C.c_int, [C.c_char_p, C.c_void_p]),
     "vaeassoc_comm_init": (C.c_int, [Handle, C.c_char_p, C.c_void_p, C.c_int, C.c_int]),
     "vaeassoc_comm_destroy": (C.c_int, [Handle]),
+    "vaeassoc_comm_sync_state": (C.c_int, [Handle]),
+    "vaeassoc_comm_check": (C.c_int, [Handle]),
+    "vaeassoc_save": (C.c_int, [Handle, C.c_char_p]),
+    "vaeassoc_load": (C.c_int, [Handle, C.c_char_p]),
     "vaeassoc_launch_count": (C.c_int64, [Handle]),
     "vaeassoc_debug_gemm": (C.c_int, [Handle, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64,
                                       C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -1,22 +1,72 @@
-"""Checkpoint I/O behind save_model / restore_model (reference: tf.train.Saver over ALL variables including the
-Adam slots, vae_assoc.py:70,427-463).  Own flat format -- a numpy .npz written to exactly the file name the caller
-gave (the reference writes `<fname>` V1 checkpoints; TensorFlow's binary format is not reproduced):
+"""Checkpoint I/O behind save_model / restore_model (reference: tf.train.Saver over ALL variables including the Adam
+slots, vae_assoc.py:70,427-463).
 
-    <tf name>                 parameter            e.g. "image/Variable_2", "image_1/Variable"
-    <tf name>/Adam            first-moment slot    (TF slot naming)
-    <tf name>/Adam_1          second-moment slot
-    beta1_power, beta2_power  TF's two power accumulators (derived from the step count)
-    __step__, __manifest__    Adam step t, and a JSON manifest (roles, shapes, hyper-parameters)
+* save: the library's own self-describing file (`vaeassoc_save`, include/vaeassoc.h: tensor table with the TF-style names
+  `image/Variable_2`, `image_1/Variable` ..., parameters + both Adam slots + step), written to exactly the file name the
+  caller gave.  `save_tf_v1` exports the same variables as a TensorFlow V1 checkpoint instead.
+* load: the format is recognised by its first bytes --
+    "VAEASSOC"   the library's format                      -> vaeassoc_load (matched by name and shape)
+    "PK"         round-1 files (numpy .npz inside .ckpt)   -> read with numpy
+    otherwise    a TensorFlow V1 checkpoint table (what the reference's Saver wrote, e.g. the shipped
+                 model_batchsize64_nz4_lambda8_weight50.ckpt) -> tf_checkpoint.read_v1, variables matched by TF name:
+                 `<scope>/Variable_k` parameters, `<name>/Adam`, `<name>/Adam_1` slots, `beta1_power` -> step count.
 """
 import io
-import json
+import math
 
 import numpy as np
 
+from . import tf_checkpoint
+
 
 def save(model, path):
+    model._check(model._lib.vaeassoc_save(model._h, str(path).encode()))
+
+
+def _apply_named(model, get, has, step):
     names = model.variable_names()
-    roles = model.variable_roles()
+    missing = [n for n in names if not has(n)]
+    if missing:
+        raise KeyError("checkpoint lacks variables %s" % missing[:3])
+    shapes = [tuple(t.shape[:t.ndim]) for t in model._tensors]
+    params = []
+    for n, shp in zip(names, shapes):
+        a = np.asarray(get(n), dtype=np.float32)
+        if tuple(a.shape) != shp:
+            raise ValueError("checkpoint variable %s has shape %s, the model expects %s" % (n, a.shape, shp))
+        params.append(a)
+    model.set_params(params)
+    if all(has(n + "/Adam") and has(n + "/Adam_1") for n in names) and step is not None:
+        model.set_adam_state([np.asarray(get(n + "/Adam"), np.float32) for n in names],
+                             [np.asarray(get(n + "/Adam_1"), np.float32) for n in names], int(step))
+
+
+def load(model, path):
+    with open(path, "rb") as f:
+        head = f.read(8)
+    if head == b"VAEASSOC":
+        model._check(model._lib.vaeassoc_load(model._h, str(path).encode()))
+        return "vaeassoc"
+    if head[:2] == b"PK":
+        with open(path, "rb") as f:
+            data = np.load(io.BytesIO(f.read()), allow_pickle=False)
+        _apply_named(model, lambda n: data[n], lambda n: n in data.files,
+                     int(data["__step__"]) if "__step__" in data.files else None)
+        return "npz"
+    tensors = tf_checkpoint.read_v1(path)
+    step = None
+    if "beta1_power" in tensors:
+        # TF's Adam keeps beta1^t, not t (vae_assoc.py:373: tf.train.AdamOptimizer defaults, beta1 = 0.9)
+        b1p = float(np.asarray(tensors["beta1_power"]).reshape(-1)[0])
+        step = int(round(math.log(b1p) / math.log(0.9))) if 0.0 < b1p < 1.0 else 0
+    _apply_named(model, lambda n: tensors[n], lambda n: n in tensors, step)
+    return "tf_v1"
+
+
+def save_tf_v1(model, path):
+    """Exports every variable a tf.train.Saver would write (parameters, Adam slots, the two beta powers) as a TensorFlow
+    V1 checkpoint, so that a TensorFlow-0.x build of the reference can `restore_model` it."""
+    names = model.variable_names()
     params = model.get_params()
     m, v, step = model.get_adam_state()
     out = {}
@@ -26,26 +76,4 @@ def save(model, path):
         out[n + "/Adam_1"] = vi
     out["beta1_power"] = np.float32(0.9 ** step)
     out["beta2_power"] = np.float32(0.999 ** step)
-    out["__step__"] = np.int64(step)
-    manifest = dict(format="vae_assoc_b200/1", names=names, roles=[[int(a), b] for a, b in roles],
-                    shapes=[list(p.shape) for p in params], batch_size=int(model.batch_size), n_z=int(model.n_z),
-                    learning_rate=float(model.learning_rate), assoc_lambda=float(model.assoc_lambda),
-                    weights=[float(w) for w in model.weights], binary=[bool(b) for b in model.binary])
-    out["__manifest__"] = np.frombuffer(json.dumps(manifest).encode(), dtype=np.uint8)
-    buf = io.BytesIO()
-    np.savez(buf, **out)
-    with open(path, "wb") as f:          # exact file name (np.savez would append ".npz")
-        f.write(buf.getvalue())
-
-
-def load(model, path):
-    with open(path, "rb") as f:
-        data = np.load(io.BytesIO(f.read()), allow_pickle=False)
-    names = model.variable_names()
-    missing = [n for n in names if n not in data.files]
-    if missing:
-        raise KeyError("checkpoint %s lacks variables %s" % (path, missing[:3]))
-    model.set_params([data[n] for n in names])
-    if all((n + "/Adam") in data.files for n in names):
-        model.set_adam_state([data[n + "/Adam"] for n in names], [data[n + "/Adam_1"] for n in names],
-                             int(data["__step__"]))
+    tf_checkpoint.write_v1(path, out)

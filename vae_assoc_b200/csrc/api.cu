@@ -55,6 +55,9 @@ struct NcclApi {
   int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
   int (*CommDestroy)(void*) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommGetAsyncError)(void*, int*) = nullptr;
+  int (*CommAbort)(void*) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
   void load(const char* path) {
     if (lib) return;
@@ -67,13 +70,16 @@ struct NcclApi {
     NCCL_SYM(CommInitRank, "ncclCommInitRank")
     NCCL_SYM(CommDestroy, "ncclCommDestroy")
     NCCL_SYM(AllReduce, "ncclAllReduce")
+    NCCL_SYM(Broadcast, "ncclBroadcast")
+    NCCL_SYM(CommGetAsyncError, "ncclCommGetAsyncError")
+    NCCL_SYM(CommAbort, "ncclCommAbort")
     NCCL_SYM(GetErrorString, "ncclGetErrorString")
 #undef NCCL_SYM
   }
 };
 NcclApi g_nccl;
 std::mutex g_nccl_mutex;
-constexpr int kNcclFloat = 7, kNcclSum = 0;
+constexpr int kNcclFloat = 7, kNcclInt64 = 4, kNcclSum = 0;
 
 // -------------------------------------------------------------------------------------------------------
 // schedule
@@ -131,7 +137,10 @@ struct vaeassoc_ctx {
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
   cudaEvent_t ev_bucket = nullptr, ev_comm = nullptr;
   int64_t submit_count = 0;
+  static constexpr int kUploadRing = 8;
+  cudaEvent_t ev_upload[kUploadRing] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // H2D of submit k done
   std::vector<void*> allocs;
+  std::vector<void*> op_allocs;   // per-op workspaces of the current schedule (split partial sums); rebuilt with the ops
   std::vector<Mod> mods;
   std::vector<vaeassoc_tensor_info> tensors;
   int64_t n_flat = 0;          // floats in the parameter part (multiple of 32)
@@ -166,6 +175,7 @@ struct vaeassoc_ctx {
   struct Seg { int site = 0, reset_first = 0, reset_count = 0; };
   Seg seg_enc, seg_dec, seg_bwd_dec, seg_bwd_enc;     // fused segments of the train step (dense modalities, tf32)
   bool fused = false;
+  bool masks_in_use[VAEASSOC_MAX_MODALITIES] = {false, false, false, false};   // relu sign masks written / read this schedule
   int dp_single = -1;                                 // VAEASSOC_DP_SINGLE=0/1; default (-1): one all-reduce per step iff fused and world > 4
   bool force_dynamic = false;                         // VAEASSOC_DYNAMIC_FIRST: the data-parallel task-queue mode on one GPU (tests)
   std::vector<Op> ops_colsum_dec, ops_colsum_enc;     // bias gradients that no GEMM epilogue produces (d a, d heads)
@@ -176,6 +186,7 @@ struct vaeassoc_ctx {
   // comm
   void* comm = nullptr;
   int rank = 0, world = 1;
+  uint64_t comm_calls = 0;
 
   template <typename T>
   T* dalloc(int64_t n, bool zero = true) {
@@ -186,6 +197,19 @@ struct vaeassoc_ctx {
     if (zero) CUDA_OK(cudaMemset(ptr, 0, bytes));
     allocs.push_back(ptr);
     return reinterpret_cast<T*>(ptr);
+  }
+  // zero-initialised workspace owned by one op of the schedule: ops of different streams never share one
+  float* op_ws(int64_t floats) {
+    if (floats <= 0) return nullptr;
+    void* ptr = nullptr;
+    CUDA_OK(cudaMalloc(&ptr, (size_t)floats * sizeof(float)));
+    CUDA_OK(cudaMemset(ptr, 0, (size_t)floats * sizeof(float)));
+    op_allocs.push_back(ptr);
+    return reinterpret_cast<float*>(ptr);
+  }
+  void free_op_ws() {
+    for (void* p : op_allocs) cudaFree(p);
+    op_allocs.clear();
   }
 };
 
@@ -304,10 +328,18 @@ void build_layout(Ctx* c) {
   // logical tensors in the reference's tf.Variable creation order (vae_assoc.py:93-111: per modality
   // recognition (8 variables, scope "<scope>") then generator (6 variables, name scope "<scope>_1"))
   // default scope names follow the reference script (vae_assoc_ujichar_img_jnt.py:54,64)
+  // scope = na["scope"] (vae_assoc.py:168,248); default names follow the reference script (vae_assoc_ujichar_img_jnt.py:54,64)
   static const char* default_scopes[4] = {"image", "joint", "modal2", "modal3"};
   for (int m = 0; m < M; ++m) {
     const Mod& d = c->mods[m];
-    const char* sc = default_scopes[m];
+    char scbuf[33];
+    memcpy(scbuf, d.cfg.scope, 32); scbuf[32] = 0;
+    const char* sc = scbuf[0] ? scbuf : default_scopes[m];
+    for (int k = 0; k < m; ++k) {
+      char other[33];
+      memcpy(other, c->mods[k].cfg.scope, 32); other[32] = 0;
+      if (!strcmp(sc, other[0] ? other : default_scopes[k])) fail("modalities %d and %d share the variable scope '%s'", k, m, sc);
+    }
     if (d.conv) {
       // conv_2d weights are plain tf.Variables (vae_assoc.py:471-473); deconv2d ones are prettytensor variables
       // 'weights' / 'bias' of layer scopes deconv2d, deconv2d_1, ... (deconv.py:92,110-114)
@@ -456,9 +488,10 @@ Op make_gemm(Ctx* c, const char* name, int m, int kind, GemmArgs a, int64_t w_of
     if (kind == KIND_TN && a.bias_grad) {
       const GemmArgs b = a;
       op.launches = 2;
-      op.run = [cc, site, b](cudaStream_t s) {
+      float* cws = c->op_ws(colsum_ws_floats(b.K, b.N));
+      op.run = [cc, site, b, cws](cudaStream_t s) {
         group_launch(cc->gplan, site, cc->gsync + cc->n_ctr + 2 * site, 0, 0, cc->comm != nullptr || cc->force_dynamic, s);
-        launch_colsum(b.B, b.ldb, b.K, b.N, b.bias_grad, s);
+        launch_colsum(b.B, b.ldb, b.K, b.N, b.bias_grad, cws, s);
       };
     } else {
       op.run = [cc, site](cudaStream_t s) {
@@ -470,13 +503,19 @@ Op make_gemm(Ctx* c, const char* name, int m, int kind, GemmArgs a, int64_t w_of
   if (w_off >= 0) a.B = c->p + w_off;
   if (skinny_supported(kind, a)) {
     op.name += ".sk";
+    a.ws = c->op_ws(gemm_skinny_ws_floats(kind, a));
+    if (kind == KIND_TN) op.launches = 2;
     op.run = [kind, a](cudaStream_t s) { launch_gemm_skinny(kind, a, s); };
     return op;
   }
   switch (kind) {
     case KIND_NN: op.run = [a](cudaStream_t s) { launch_gemm_nn_simt(a, s); }; break;
     case KIND_NT: op.run = [a](cudaStream_t s) { launch_gemm_nt_simt(a, s); }; break;
-    default: op.run = [a](cudaStream_t s) { launch_gemm_tn_simt(a, s); }; break;
+    default:
+      a.ws = c->op_ws(gemm_tn_simt_ws_floats(a));
+      if (a.ws) op.launches = 2;
+      op.run = [a](cudaStream_t s) { launch_gemm_tn_simt(a, s); };
+      break;
   }
   return op;
 }
@@ -530,10 +569,11 @@ Op make_col2im(const char* name, int m, const float* cols, int64_t ldc, int B, i
   op.run = [a](cudaStream_t st) { launch_col2im(a, st); };
   return op;
 }
-Op make_colsum(const char* name, int m, const float* X, int64_t ld, int64_t rows, int cols, float* out) {
+Op make_colsum(Ctx* c, const char* name, int m, const float* X, int64_t ld, int64_t rows, int cols, float* out) {
   Op op; op.name = std::string(name) + "." + std::to_string(m);
   op.bytes = 4.0 * rows * cols;
-  op.run = [=](cudaStream_t st) { launch_colsum(X, ld, (int)rows, cols, out, st); };
+  float* ws = c->op_ws(colsum_ws_floats(rows, cols));
+  op.run = [=](cudaStream_t st) { launch_colsum(X, ld, rows, cols, out, ws, st); };
   return op;
 }
 GemmArgs gemm_plain(int M, int N, int K, const float* A, int64_t lda, int64_t ldb, float* C, int64_t ldc) {
@@ -585,22 +625,22 @@ void build_ops_conv(Ctx* c, int m) {
   bd.push_back(make_gemm(c, "wgrad_out", m, KIND_TN, gemm_wgrad(B, d.ni, d.ni, d.g2, d.nip, d.da, d.nip, G + d.Vo, d.nip, G + d.co), -1, false));
   bd.push_back(make_gemm(c, "dgrad_out", m, KIND_NT, gemm_dgrad(B, d.ni, d.ni, d.da, d.nip, nullptr, d.nip, d.dg2, d.nip, d.g2, d.nip, ACT_SIGMOID), d.Vo, R));
   // deconv4: d4 = dg2 [B,28,28,1]
-  bd.push_back(make_colsum("bgrad_deconv4", m, d.dg2, 1, (int64_t)B * d.ni, 1, G + d.d4));
+  bd.push_back(make_colsum(c, "bgrad_deconv4", m, d.dg2, 1, (int64_t)B * d.ni, 1, G + d.d4));
   bd.push_back(make_im2col("bwd_im2col4", m, d.dg2, B, d.t4, 1, 5, 2, pb_s, d.t3, d.cols4, 28));
   bd.push_back(make_gemm(c, "wgrad_deconv4", m, KIND_TN, gemm_wgrad(m3, 25, d.q3, d.cols4, 28, d.o3, d.q3, G + d.D4, d.q3, nullptr), -1, false));
   { GemmArgs a = gemm_plain(m3, d.q3, 25, d.cols4, 28, d.q3, d.dd3, d.q3); a.aux = d.o3; a.ldaux = d.q3; a.act = ACT_SIGMOID;
     bd.push_back(make_gemm(c, "dgrad_deconv4", m, KIND_NN, a, d.D4, R)); }
-  bd.push_back(make_colsum("bgrad_deconv3", m, d.dd3, d.q3, m3, d.q3, G + d.d3));
+  bd.push_back(make_colsum(c, "bgrad_deconv3", m, d.dd3, d.q3, m3, d.q3, G + d.d3));
   bd.push_back(make_im2col("bwd_im2col3", m, d.dd3, B, d.t3, d.q3, 5, 2, pb_s, d.t2, d.cols3, 25 * d.q3));
   bd.push_back(make_gemm(c, "wgrad_deconv3", m, KIND_TN, gemm_wgrad(m2, 25 * d.q3, d.q2, d.cols3, 25 * d.q3, d.o2, d.q2, G + d.D3, d.q2, nullptr), -1, false));
   { GemmArgs a = gemm_plain(m2, d.q2, 25 * d.q3, d.cols3, 25 * d.q3, d.q2, d.dd2, d.q2); a.aux = d.o2; a.ldaux = d.q2; a.act = ACT_SIGMOID;
     bd.push_back(make_gemm(c, "dgrad_deconv3", m, KIND_NN, a, d.D3, R)); }
-  bd.push_back(make_colsum("bgrad_deconv2", m, d.dd2, d.q2, m2, d.q2, G + d.d2));
+  bd.push_back(make_colsum(c, "bgrad_deconv2", m, d.dd2, d.q2, m2, d.q2, G + d.d2));
   bd.push_back(make_im2col("bwd_im2col2", m, d.dd2, B, d.t2, d.q2, 5, 1, 0, d.t1, d.cols2, 25 * d.q2));
   bd.push_back(make_gemm(c, "wgrad_deconv2", m, KIND_TN, gemm_wgrad(m1, 25 * d.q2, d.q1, d.cols2, 25 * d.q2, d.o1, d.q1, G + d.D2, d.q1, nullptr), -1, false));
   { GemmArgs a = gemm_plain(m1, d.q1, 25 * d.q2, d.cols2, 25 * d.q2, d.q1, d.dd1, d.q1); a.aux = d.o1; a.ldaux = d.q1; a.act = ACT_SIGMOID;
     bd.push_back(make_gemm(c, "dgrad_deconv2", m, KIND_NN, a, d.D2, R)); }
-  bd.push_back(make_colsum("bgrad_deconv1", m, d.dd1, d.q1, m1, d.q1, G + d.d1));
+  bd.push_back(make_colsum(c, "bgrad_deconv1", m, d.dd1, d.q1, m1, d.q1, G + d.d1));
   // deconv1 maps the 1x1 latent "image" to 3x3: its patch matrix is dd1 itself, viewed [B, 9 g1]
   bd.push_back(make_gemm(c, "wgrad_deconv1", m, KIND_TN, gemm_wgrad(B, 9 * d.q1, nz, d.dd1, 9 * d.q1, d.z, nz, G + d.D1, nzp, nullptr), -1, false));
   bd.push_back(make_gemm(c, "dgrad_deconv1", m, KIND_NN, gemm_plain(B, nz, 9 * d.q1, d.dd1, 9 * d.q1, nzp, d.dz, nz), d.D1, false));
@@ -626,6 +666,7 @@ void build_segments(Ctx* c);
 
 void build_ops(Ctx* c) {
   destroy_graphs(c);
+  c->free_op_ws();
   group_destroy(c->gplan);
   c->gplan = group_create();
   c->fused = false;
@@ -660,6 +701,7 @@ void build_ops(Ctx* c) {
 
   for (int m = 0; m < M; ++m) {
     Mod& d = c->mods[m];
+    c->masks_in_use[m] = false;
     if (d.conv) {
       build_ops_conv(c, m);
       add_recon(m, tf32);
@@ -698,6 +740,7 @@ void build_ops(Ctx* c) {
       f_e2.mask_out = d.mh2; f_e2.ldmask = w2;  d_hd.mask_in = d.mh2; d_hd.ldmask = w2;
       f_d1.mask_out = d.mg1; f_d1.ldmask = w1;  d_d2.mask_in = d.mg1; d_d2.ldmask = w1;
       f_d2.mask_out = d.mg2; f_d2.ldmask = w2;  d_o.mask_in = d.mg2;  d_o.ldmask = w2;
+      c->masks_in_use[m] = true;
     }
     const bool r_h1 = tc(KIND_NN, f_e2, d.W2) || tc(KIND_TN, w_e2, -1);
     const bool r_h2 = tc(KIND_NN, f_hd, d.Wh) || tc(KIND_TN, w_hd, -1);
@@ -830,7 +873,8 @@ void build_segments(Ctx* c) {
         // dY comes from an elementwise kernel (loss / latent backward): its column sums need their own launch
         const GemmArgs b = op.gargs;
         Op cs; cs.name = "bgrad_" + op.name; cs.bytes = 4.0 * b.K * b.N;
-        cs.run = [b](cudaStream_t s) { launch_colsum(b.B, b.ldb, b.K, b.N, b.bias_grad, s); };
+        float* cws = c->op_ws(colsum_ws_floats(b.K, b.N));
+        cs.run = [b, cws](cudaStream_t s) { launch_colsum(b.B, b.ldb, b.K, b.N, b.bias_grad, cws, s); };
         return cs;
       }
       return Op();
@@ -1028,6 +1072,7 @@ void enqueue_adam(Ctx* c, cudaStream_t s) {
   launch_adam(adam_args(c), s);
   c->launches += 1;
 }
+void allreduce(Ctx* c, float* buf, int64_t count, cudaStream_t s);
 void enqueue_forward_loss(Ctx* c, cudaStream_t s) {   // evaluate_cost: no gradients
   run_ops(c, c->ops_fwd_enc, s);
   {
@@ -1047,6 +1092,7 @@ void enqueue_forward_loss(Ctx* c, cudaStream_t s) {   // evaluate_cost: no gradi
   run_ops(c, c->ops_fwd_dec, s);
   run_ops(c, c->ops_loss, s);   // also writes d cost/d a (harmless; gradients are not consumed)
   launch_finalize(finalize_args(c, 0), s);
+  if (c->comm && c->world > 1) { allreduce(c, c->g + c->n_flat, 32, s); c->launches += 1; }
   launch_publish_cost(c->g + c->n_flat, c->last_cost, s);
   c->launches += 2;
 }
@@ -1116,9 +1162,24 @@ void stage_inputs(Ctx* c, const float* const* x, const int64_t* ld, const float*
   c->launches += 1;
 }
 
+// ncclCommGetAsyncError -> abort: a failed peer / link must surface as an error of the next call, not as a hang
+void comm_check(Ctx* c) {
+  if (!c->comm) return;
+  int async_err = 0;
+  const int r = g_nccl.CommGetAsyncError(c->comm, &async_err);
+  if (r != 0 || async_err != 0) {
+    const char* what = g_nccl.GetErrorString(r != 0 ? r : async_err);
+    g_nccl.CommAbort(c->comm);
+    c->comm = nullptr; c->world = 1; c->rank = 0;
+    destroy_graphs(c);
+    fail("NCCL asynchronous error: %s -- communicator aborted", what ? what : "unknown");
+  }
+}
+
 void allreduce(Ctx* c, float* buf, int64_t count, cudaStream_t s) {
   const int r = g_nccl.AllReduce(buf, buf, (size_t)count, kNcclFloat, kNcclSum, c->comm, s);
   if (r != 0) fail("ncclAllReduce failed: %s", g_nccl.GetErrorString(r));
+  if ((++c->comm_calls & 63) == 0) comm_check(c);       // cheap host-side poll, every 64 collectives
 }
 
 // the train step proper (inputs already staged)
@@ -1190,6 +1251,13 @@ void check_handle(vaeassoc_handle h) {
   CUDA_OK(cudaSetDevice(h->device));
 }
 
+void check_precision(int precision) {
+  if (precision == VAEASSOC_BF16)
+    fail("precision bf16 is not served: 8-bit mantissa operands miss the 2e-3 tolerance of the tensor-core path "
+         "(tf32 measures 6e-4); use tf32 (tcgen05 kind::tf32) or fp32");
+  if (precision != VAEASSOC_FP32 && precision != VAEASSOC_TF32) fail("precision must be fp32 or tf32");
+}
+
 void validate_config(const vaeassoc_config* cfg) {
   if (!cfg) fail("null config");
   if (cfg->abi_version != VAEASSOC_ABI_VERSION) fail("ABI version mismatch: caller %d, library %d", cfg->abi_version, VAEASSOC_ABI_VERSION);
@@ -1197,7 +1265,7 @@ void validate_config(const vaeassoc_config* cfg) {
   if (cfg->batch_size < 1) fail("batch_size must be >= 1");
   if (cfg->n_z < 1 || cfg->n_z > 1024) fail("n_z must be in [1,1024]");
   if (cfg->transfer_fct != VAEASSOC_RELU && cfg->transfer_fct != VAEASSOC_SOFTPLUS) fail("transfer_fct must be relu or softplus");
-  if (cfg->precision != VAEASSOC_FP32 && cfg->precision != VAEASSOC_TF32) fail("precision must be fp32 or tf32");
+  check_precision(cfg->precision);
   if (cfg->global_batch != 0 && cfg->global_batch < cfg->batch_size) fail("global_batch < batch_size");
 }
 
@@ -1254,6 +1322,7 @@ int vaeassoc_create(const vaeassoc_config* cfg, vaeassoc_handle* out) {
       CUDA_OK(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
       CUDA_OK(cudaEventCreateWithFlags(&c->ev_consumed[i], cudaEventDisableTiming));
     }
+    for (int i = 0; i < Ctx::kUploadRing; ++i) CUDA_OK(cudaEventCreateWithFlags(&c->ev_upload[i], cudaEventDisableTiming));
     for (int i = 0; i < VAEASSOC_MAX_MODALITIES - 1; ++i) {
       CUDA_OK(cudaStreamCreateWithFlags(&c->side[i], cudaStreamNonBlocking));
       CUDA_OK(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
@@ -1290,11 +1359,13 @@ int vaeassoc_destroy(vaeassoc_handle h) {
   destroy_graphs(h);
   group_destroy(h->gplan);
   for (void* p : h->allocs) cudaFree(p);
+  h->free_op_ws();
   if (h->host_cost_ring) cudaFreeHost(h->host_cost_ring);
   for (int i = 0; i < 2; ++i) {
     if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
     if (h->ev_consumed[i]) cudaEventDestroy(h->ev_consumed[i]);
   }
+  for (int i = 0; i < Ctx::kUploadRing; ++i) if (h->ev_upload[i]) cudaEventDestroy(h->ev_upload[i]);
   for (int i = 0; i < VAEASSOC_MAX_MODALITIES - 1; ++i) {
     if (h->side[i]) cudaStreamDestroy(h->side[i]);
     if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
@@ -1327,12 +1398,13 @@ int vaeassoc_set_stream(vaeassoc_handle h, void* cuda_stream) {
 int vaeassoc_stream_sync(vaeassoc_handle h) {
   API_BEGIN(h)
   CUDA_OK(cudaStreamSynchronize(h->stream));
+  comm_check(h);
   API_END(h)
 }
 
 int vaeassoc_set_precision(vaeassoc_handle h, int precision) {
   API_BEGIN(h)
-  if (precision != VAEASSOC_FP32 && precision != VAEASSOC_TF32) fail("precision must be fp32 or tf32");
+  check_precision(precision);
   CUDA_OK(cudaStreamSynchronize(h->stream));
   h->cfg.precision = precision;
   h->shadow_dirty = true;
@@ -1490,6 +1562,7 @@ int vaeassoc_submit_host(vaeassoc_handle h, const float* const* x_host, const fl
   if (h->submit_count >= 2) CUDA_OK(cudaStreamWaitEvent(h->copy_stream, h->ev_consumed[slot], 0));
   upload_host(h, x_host, eps_host, slot, h->copy_stream);
   CUDA_OK(cudaEventRecord(h->ev_copied[slot], h->copy_stream));
+  CUDA_OK(cudaEventRecord(h->ev_upload[h->submit_count % Ctx::kUploadRing], h->copy_stream));
   CUDA_OK(cudaStreamWaitEvent(h->stream, h->ev_copied[slot], 0));
   const float* xd[VAEASSOC_MAX_MODALITIES];
   for (int m = 0; m < h->cfg.n_modalities; ++m) xd[m] = h->mods[m].xin[slot];
@@ -1499,6 +1572,18 @@ int vaeassoc_submit_host(vaeassoc_handle h, const float* const* x_host, const fl
   CUDA_OK(cudaMemcpyAsync(h->host_cost_ring + (h->submit_count % Ctx::kHostRing), h->last_cost, sizeof(float),
                           cudaMemcpyDeviceToHost, h->stream));
   h->submit_count += 1;
+  API_END(h)
+}
+
+int64_t vaeassoc_submit_count(vaeassoc_handle h) { return h ? h->submit_count : -1; }
+
+int vaeassoc_upload_wait(vaeassoc_handle h, int64_t submit_index) {
+  API_BEGIN(h)
+  if (submit_index < 0 || submit_index >= h->submit_count) fail("submit %lld has not been made (%lld so far)", (long long)submit_index, (long long)h->submit_count);
+  // the copy stream is in order: an event of a LATER submit implies this one; the ring holds the last kUploadRing
+  const int64_t oldest = std::max<int64_t>(0, h->submit_count - Ctx::kUploadRing);
+  const int64_t k = std::max(submit_index, oldest);
+  CUDA_OK(cudaEventSynchronize(h->ev_upload[k % Ctx::kUploadRing]));
   API_END(h)
 }
 
@@ -1517,7 +1602,7 @@ int vaeassoc_eval_cost(vaeassoc_handle h, const float* const* x_dev, const int64
   API_BEGIN(h)
   if (!x_dev) fail("x_dev is null");
   for (int m = 0; m < h->cfg.n_modalities; ++m) if (!x_dev[m]) fail("x_dev[%d] is null", m);
-  if (h->comm && h->world > 1) fail("evaluate_cost is a single-process call; use it on a handle without a communicator");
+  // under data parallelism every rank calls this with ITS shard: the shard costs (global scaling baked in) are summed
   stage_inputs(h, x_dev, ld, eps_dev, h->stream);
   refresh_shadow(h, h->stream);
   enqueue_forward_loss(h, h->stream);
@@ -1686,6 +1771,134 @@ int vaeassoc_comm_destroy(vaeassoc_handle h) {
   API_END(h)
 }
 
+int vaeassoc_comm_sync_state(vaeassoc_handle h) {
+  API_BEGIN(h)
+  if (h->comm && h->world > 1) {
+    cudaStream_t s = h->stream;
+    auto bc = [&](void* buf, size_t count, int type) {
+      const int r = g_nccl.Broadcast(buf, buf, count, type, 0, h->comm, s);
+      if (r != 0) fail("ncclBroadcast failed: %s", g_nccl.GetErrorString(r));
+    };
+    bc(h->p, (size_t)h->n_flat, kNcclFloat);
+    bc(h->m, (size_t)h->n_flat, kNcclFloat);
+    bc(h->v, (size_t)h->n_flat, kNcclFloat);
+    bc(h->step_dev, 1, kNcclInt64);
+    h->launches += 4;
+    h->shadow_dirty = true;
+    CUDA_OK(cudaStreamSynchronize(s));
+    comm_check(h);
+  }
+  API_END(h)
+}
+
+int vaeassoc_comm_check(vaeassoc_handle h) {
+  API_BEGIN(h)
+  comm_check(h);
+  API_END(h)
+}
+
+int vaeassoc_probe_mask(vaeassoc_handle h, int layer, int modality, uint32_t* dst_host, int64_t capacity_words,
+                        int64_t* n_written, int64_t* words_per_row) {
+  API_BEGIN(h)
+  if (modality < 0 || modality >= h->cfg.n_modalities) fail("modality %d out of range", modality);
+  if (layer < 0 || layer > 3 || !dst_host) fail("layer must be 0..3 (h1, h2, g1, g2) and dst_host non-null");
+  const Mod& d = h->mods[modality];
+  if (!h->masks_in_use[modality])
+    fail("modality %d keeps no relu masks (they exist for dense relu modalities on the tensor-core path, batch >= 32)", modality);
+  const uint32_t* src = layer == 0 ? d.mh1 : layer == 1 ? d.mh2 : layer == 2 ? d.mg1 : d.mg2;
+  const int64_t wpr = ((layer == 0 || layer == 2 ? d.r1 : d.r2) + 31) / 32;
+  const int64_t n = (int64_t)h->cfg.batch_size * wpr;
+  if (n > capacity_words) fail("mask needs %lld words, capacity %lld", (long long)n, (long long)capacity_words);
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  CUDA_OK(cudaMemcpy(dst_host, src, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  if (n_written) *n_written = n;
+  if (words_per_row) *words_per_row = wpr;
+  API_END(h)
+}
+
+// ---- checkpoint file: "VAEASSOC" | u32 version | u32 n_tensors | i64 step | per tensor { name[48], role[16], i32 ndim,
+// i32 shape[4], i64 count, f32 p[count], f32 m[count], f32 v[count] } -- dense logical tensors in the reference's
+// tf.Variable creation order (what tf.train.Saver would write: every variable plus its two Adam slots, vae_assoc.py:70)
+namespace {
+constexpr char kCkptMagic[8] = {'V', 'A', 'E', 'A', 'S', 'S', 'O', 'C'};
+struct File {
+  FILE* f = nullptr;
+  ~File() { if (f) fclose(f); }
+};
+void get_dense(Ctx* h, const float* base, const vaeassoc_tensor_info& t, std::vector<float>& out) {
+  out.resize((size_t)t.rows * t.cols);
+  CUDA_OK(cudaMemcpy2D(out.data(), (size_t)t.cols * 4, base + t.offset, (size_t)t.ld * 4, (size_t)t.cols * 4, (size_t)t.rows,
+                       cudaMemcpyDeviceToHost));
+}
+void put_dense(Ctx* h, float* base, const vaeassoc_tensor_info& t, const std::vector<float>& in) {
+  CUDA_OK(cudaMemcpy2D(base + t.offset, (size_t)t.ld * 4, in.data(), (size_t)t.cols * 4, (size_t)t.cols * 4, (size_t)t.rows,
+                       cudaMemcpyHostToDevice));
+}
+}  // namespace
+
+int vaeassoc_save(vaeassoc_handle h, const char* path) {
+  API_BEGIN(h)
+  if (!path || !path[0]) fail("empty checkpoint path");
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  File fl; fl.f = fopen(path, "wb");
+  if (!fl.f) fail("cannot open %s for writing", path);
+  const uint32_t version = 1, n = (uint32_t)h->tensors.size();
+  int64_t step = 0;
+  CUDA_OK(cudaMemcpy(&step, h->step_dev, sizeof step, cudaMemcpyDeviceToHost));
+  bool ok = fwrite(kCkptMagic, 1, 8, fl.f) == 8 && fwrite(&version, 4, 1, fl.f) == 1 && fwrite(&n, 4, 1, fl.f) == 1 &&
+            fwrite(&step, 8, 1, fl.f) == 1;
+  std::vector<float> buf;
+  for (const vaeassoc_tensor_info& t : h->tensors) {
+    const int64_t count = t.rows * t.cols;
+    ok = ok && fwrite(t.name, 1, 48, fl.f) == 48 && fwrite(t.role, 1, 16, fl.f) == 16 && fwrite(&t.ndim, 4, 1, fl.f) == 1 &&
+         fwrite(t.shape, 4, 4, fl.f) == 4 && fwrite(&count, 8, 1, fl.f) == 1;
+    for (const float* base : {h->p, h->m, h->v}) {
+      get_dense(h, base, t, buf);
+      ok = ok && fwrite(buf.data(), 4, (size_t)count, fl.f) == (size_t)count;
+    }
+  }
+  if (!ok || fflush(fl.f) != 0) fail("short write to %s", path);
+  API_END(h)
+}
+
+int vaeassoc_load(vaeassoc_handle h, const char* path) {
+  API_BEGIN(h)
+  if (!path || !path[0]) fail("empty checkpoint path");
+  File fl; fl.f = fopen(path, "rb");
+  if (!fl.f) fail("cannot open %s", path);
+  char magic[8]; uint32_t version = 0, n = 0; int64_t step = 0;
+  if (fread(magic, 1, 8, fl.f) != 8 || memcmp(magic, kCkptMagic, 8) != 0) fail("%s is not a libvaeassoc checkpoint", path);
+  if (fread(&version, 4, 1, fl.f) != 1 || fread(&n, 4, 1, fl.f) != 1 || fread(&step, 8, 1, fl.f) != 1 || version != 1)
+    fail("%s: unsupported checkpoint version", path);
+  if (n != h->tensors.size()) fail("%s holds %u tensors, the model has %zu", path, n, h->tensors.size());
+  // read and validate EVERYTHING before the first device write: a mismatch leaves the handle unchanged
+  std::vector<std::vector<float>> data(3 * (size_t)n);
+  for (uint32_t i = 0; i < n; ++i) {
+    const vaeassoc_tensor_info& t = h->tensors[i];
+    char name[48], role[16]; int32_t ndim = 0, shape[4]; int64_t count = 0;
+    if (fread(name, 1, 48, fl.f) != 48 || fread(role, 1, 16, fl.f) != 16 || fread(&ndim, 4, 1, fl.f) != 1 ||
+        fread(shape, 4, 4, fl.f) != 4 || fread(&count, 8, 1, fl.f) != 1)
+      fail("%s: truncated tensor table", path);
+    name[47] = 0;
+    if (strncmp(name, t.name, 48) != 0) fail("%s: tensor %u is '%s', the model expects '%s'", path, i, name, t.name);
+    if (ndim != t.ndim || memcmp(shape, t.shape, sizeof shape) != 0 || count != t.rows * t.cols)
+      fail("%s: shape of '%s' does not match the model", path, name);
+    for (int k = 0; k < 3; ++k) {
+      data[3 * i + k].resize((size_t)count);
+      if (fread(data[3 * i + k].data(), 4, (size_t)count, fl.f) != (size_t)count) fail("%s: truncated data of '%s'", path, name);
+    }
+  }
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  for (uint32_t i = 0; i < n; ++i) {
+    put_dense(h, h->p, h->tensors[i], data[3 * i]);
+    put_dense(h, h->m, h->tensors[i], data[3 * i + 1]);
+    put_dense(h, h->v, h->tensors[i], data[3 * i + 2]);
+  }
+  CUDA_OK(cudaMemcpy(h->step_dev, &step, sizeof step, cudaMemcpyHostToDevice));
+  h->shadow_dirty = true;
+  API_END(h)
+}
+
 int64_t vaeassoc_launch_count(vaeassoc_handle h) { return h ? h->launches : -1; }
 
 int vaeassoc_debug_gemm(vaeassoc_handle h, int kind, int use_tc, int M, int N, int K, const float* A, int64_t lda,
@@ -1716,13 +1929,23 @@ int vaeassoc_debug_gemm(vaeassoc_handle h, int kind, int use_tc, int M, int N, i
     group_set_counters(plan, h->gsync, h->n_ctr);
     if (!group_end(plan, err, sizeof err) || !group_upload(plan, err, sizeof err)) { group_destroy(plan); fail("%s", err); }
     group_launch(plan, dsite, h->gsync + h->n_ctr + 2 * (h->max_sites - 1), 0, 0, h->comm != nullptr || h->force_dynamic, h->stream);
-    if (kind == KIND_TN && bias_grad) launch_colsum(B, ldb, K, N, bias_grad, h->stream);
+    float* cws = nullptr;
+    if (kind == KIND_TN && bias_grad) {
+      const int64_t nws = colsum_ws_floats(K, N);
+      CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&cws), (size_t)nws * 4));
+      CUDA_OK(cudaMemsetAsync(cws, 0, (size_t)nws * 4, h->stream));
+      launch_colsum(B, ldb, K, N, bias_grad, cws, h->stream);
+    }
     CUDA_OK(cudaStreamSynchronize(h->stream));
+    if (cws) cudaFree(cws);
     if (getenv("VAEASSOC_TC_TIMELINE"))
       group_debug_timeline(plan, dsite, h->gsync + h->n_ctr + 2 * (h->max_sites - 1), 0, 0, h->stream);
     group_destroy(plan);
   } else {
-    if (use_tc == 0 && skinny_supported(kind, a)) {
+    const bool sk = use_tc == 0 && skinny_supported(kind, a);
+    const int64_t nws = sk ? gemm_skinny_ws_floats(kind, a) : (kind == KIND_TN ? gemm_tn_simt_ws_floats(a) : 0);
+    if (nws > 0) CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&a.ws), (size_t)nws * 4));
+    if (sk) {
       launch_gemm_skinny(kind, a, h->stream);
     } else {
       switch (kind) {
@@ -1732,6 +1955,7 @@ int vaeassoc_debug_gemm(vaeassoc_handle h, int kind, int use_tc, int M, int N, i
       }
     }
     CUDA_OK(cudaStreamSynchronize(h->stream));
+    if (a.ws) cudaFree(a.ws);
   }
   CUDA_OK(cudaGetLastError());
   API_END(h)

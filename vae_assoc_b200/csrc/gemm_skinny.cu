@@ -91,54 +91,80 @@ __global__ void __launch_bounds__(128) skinny_in_kernel(GemmArgs g) {
 }
 
 // ---- (e)/(f): wgrad C[M,N] += A[K,M]^T . B[K,N] with min(M,N) <= 16, K = batch.  The wide operand is streamed once
-// (thread per wide column, coalesced), the skinny operand's rows are broadcast from shared memory; each CTA reduces
-// ROWS batch rows and issues one fp32 RED per output element.  bias_grad += colsum(B).
+// (thread per wide column, coalesced), the skinny operand's rows are broadcast from shared memory; CTA (x, y) reduces
+// its slab of batch rows and stores the partial sums into the workspace ws[y][S][W] (+ column-sum partials); a second
+// pass adds the slabs in ascending order: deterministic, no fp32 atomics.  bias_grad += colsum(B).
 constexpr int ROWS = 32;
 template <bool SKINNY_M>
-__global__ void __launch_bounds__(128) skinny_wgrad_kernel(GemmArgs g) {
+__global__ void __launch_bounds__(128) skinny_wgrad_kernel(GemmArgs g, int rows_per_cta) {
   __shared__ float sS[ROWS][SK];
   const int S = SKINNY_M ? g.M : g.N;                       // skinny extent
   const int W = SKINNY_M ? g.N : g.M;                       // wide extent
   const float* skinny = SKINNY_M ? g.A : g.B;  const int64_t lds = SKINNY_M ? g.lda : g.ldb;
   const float* wide = SKINNY_M ? g.B : g.A;    const int64_t ldw = SKINNY_M ? g.ldb : g.lda;
-  const int r0 = blockIdx.y * ROWS, r1 = min(g.K, r0 + ROWS);
-  for (int i = threadIdx.x; i < (r1 - r0) * S; i += blockDim.x) {
-    const int r = i / S, s = i - r * S;
-    sS[r][s] = skinny[(int64_t)(r0 + r) * lds + s];
-  }
-  __syncthreads();
+  const int y0 = blockIdx.y * rows_per_cta, y1 = min(g.K, y0 + rows_per_cta);
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
   float acc[SK];
 #pragma unroll
   for (int s = 0; s < SK; ++s) acc[s] = 0.f;
-  float colsum = 0.f;
-  if (w < W) {
-#pragma unroll 8
-    for (int r = r0; r < r1; ++r) {
-      const float x = wide[(int64_t)r * ldw + w];
-      colsum += x;
-#pragma unroll
-      for (int s = 0; s < SK; ++s)
-        if (s < S) acc[s] = fmaf(sS[r - r0][s], x, acc[s]);
+  float colsum = 0.f, scs = 0.f;          // column sums of the wide operand (thread w) / of the skinny one (thread s)
+  for (int r0 = y0; r0 < y1; r0 += ROWS) {
+    const int r1 = min(y1, r0 + ROWS);
+    __syncthreads();
+    for (int i = threadIdx.x; i < (r1 - r0) * S; i += blockDim.x) {
+      const int r = i / S, s = i - r * S;
+      sS[r][s] = skinny[(int64_t)(r0 + r) * lds + s];
     }
+    __syncthreads();
+    if (w < W) {
+#pragma unroll 8
+      for (int r = r0; r < r1; ++r) {
+        const float x = wide[(int64_t)r * ldw + w];
+        colsum += x;
 #pragma unroll
-    for (int s = 0; s < SK; ++s) {
-      if (s < S) {
-        float* dst = SKINNY_M ? g.C + (int64_t)s * g.ldc + w : g.C + (int64_t)w * g.ldc + s;
-        atomicAdd(dst, acc[s]);
+        for (int s = 0; s < SK; ++s)
+          if (s < S) acc[s] = fmaf(sS[r - r0][s], x, acc[s]);
       }
     }
-    // bias gradient = column sums of B: B is the wide operand when M is skinny
-    if (SKINNY_M && g.bias_grad) atomicAdd(g.bias_grad + w, colsum);
+    if (!SKINNY_M && blockIdx.x == 0 && (int)threadIdx.x < S)
+      for (int r = 0; r < r1 - r0; ++r) scs += sS[r][threadIdx.x];
   }
-  if (!SKINNY_M && g.bias_grad && blockIdx.x == 0) {
-    // B is the skinny operand: its column sums over this CTA's rows, from shared memory
-    for (int s = threadIdx.x; s < S; s += blockDim.x) {
-      float t = 0.f;
-      for (int r = 0; r < r1 - r0; ++r) t += sS[r][s];
-      atomicAdd(g.bias_grad + s, t);
+  float* __restrict__ part = g.ws + (int64_t)blockIdx.y * ((int64_t)S * W + max(S, W));
+  if (w < W) {
+#pragma unroll
+    for (int s = 0; s < SK; ++s)
+      if (s < S) part[(int64_t)s * W + w] = acc[s];
+    if (SKINNY_M) part[(int64_t)S * W + w] = colsum;        // B is the wide operand when M is skinny
+  }
+  if (!SKINNY_M && blockIdx.x == 0 && (int)threadIdx.x < S) part[(int64_t)S * W + threadIdx.x] = scs;
+}
+
+// second pass: C[s, w] (or C[w, s]) += sum_y ws[y][s][w]; bias_grad += sum_y of the column-sum partials; y ascending
+template <bool SKINNY_M>
+__global__ void __launch_bounds__(256) skinny_wgrad_reduce_kernel(GemmArgs g, int ny) {
+  const int S = SKINNY_M ? g.M : g.N, W = SKINNY_M ? g.N : g.M;
+  const int64_t stride = (int64_t)S * W + max(S, W);
+  const int nb = g.bias_grad ? g.N : 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)S * W + nb; i += (int64_t)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    if (i < (int64_t)S * W) {
+      for (int y = 0; y < ny; ++y) acc += g.ws[y * stride + i];
+      const int s = (int)(i / W), w = (int)(i - (int64_t)s * W);
+      float* dst = SKINNY_M ? g.C + (int64_t)s * g.ldc + w : g.C + (int64_t)w * g.ldc + s;
+      *dst += acc;
+    } else {
+      const int n = (int)(i - (int64_t)S * W);
+      for (int y = 0; y < ny; ++y) acc += g.ws[y * stride + (int64_t)S * W + n];
+      g.bias_grad[n] += acc;
     }
   }
+}
+
+// batch rows per CTA of the skinny weight gradient: 32, or more so that at most 256 slabs are summed by the second pass
+inline int skinny_wgrad_rows(int K) {
+  int rpc = ROWS;
+  if ((K + rpc - 1) / rpc > 256) rpc = (((K + 255) / 256) + ROWS - 1) / ROWS * ROWS;
+  return rpc;
 }
 
 inline int cap_grid(int64_t blocks) {
@@ -171,11 +197,28 @@ void launch_gemm_skinny(int kind, const GemmArgs& a, cudaStream_t s) {
     }
   } else {
     const bool skinny_m = a.M <= SK;
-    const int W = skinny_m ? a.N : a.M;
-    dim3 grid((W + 127) / 128, (a.K + ROWS - 1) / ROWS);
-    if (skinny_m) skinny_wgrad_kernel<true><<<grid, 128, 0, s>>>(a);
-    else skinny_wgrad_kernel<false><<<grid, 128, 0, s>>>(a);
+    const int W = skinny_m ? a.N : a.M, S = skinny_m ? a.M : a.N;
+    const int rpc = skinny_wgrad_rows(a.K);
+    const int ny = (a.K + rpc - 1) / rpc;
+    dim3 grid((W + 127) / 128, ny);
+    const int rgrid = (int)std::min<int64_t>(((int64_t)S * W + a.N + 255) / 256, 4 * kNumSMs);
+    if (skinny_m) {
+      skinny_wgrad_kernel<true><<<grid, 128, 0, s>>>(a, rpc);
+      skinny_wgrad_reduce_kernel<true><<<rgrid, 256, 0, s>>>(a, ny);
+    } else {
+      skinny_wgrad_kernel<false><<<grid, 128, 0, s>>>(a, rpc);
+      skinny_wgrad_reduce_kernel<false><<<rgrid, 256, 0, s>>>(a, ny);
+    }
   }
+}
+
+// workspace floats of the skinny weight gradient (0 for the other kinds)
+int64_t gemm_skinny_ws_floats(int kind, const GemmArgs& a) {
+  if (kind != 2) return 0;
+  const bool skinny_m = a.M <= SK;
+  const int64_t W = skinny_m ? a.N : a.M, S = skinny_m ? a.M : a.N;
+  const int rpc = skinny_wgrad_rows(a.K);
+  return (int64_t)((a.K + rpc - 1) / rpc) * (S * W + std::max(S, W));
 }
 
 }  // namespace vaeassoc

@@ -10,7 +10,8 @@ namespace vaeassoc {
 // 259-303 and their autodiff, :373-374):
 //   NN  C[M,N]  = act(A[M,K] . B[K,N] + bias[N])                     forward
 //   NT  C[M,N]  = (A[M,K] . B[N,K]^T) (*) act'(aux[M,N])             dgrad (aux = stored activation of the layer below)
-//   TN  C[M,N] += A[K,M]^T . B[K,N];  bias_grad[N] += colsum(B)      wgrad (K = batch; split-K, fp32 atomics)
+//   TN  C[M,N] += A[K,M]^T . B[K,N];  bias_grad[N] += colsum(B)      wgrad (K = batch; split-K: partial tiles in a
+//                                                                     workspace, summed in a fixed order -> deterministic)
 // ------------------------------------------------------------------------------------------------------
 struct GemmArgs {
   int M = 0, N = 0, K = 0;
@@ -23,6 +24,7 @@ struct GemmArgs {
   int act = 0;          // Act code: forward activation, or which act' to apply in dgrad
   int round_out = 0;    // round stored outputs to tf32 (they feed a tcgen05 kind::tf32 GEMM)
   int splitk = 1;       // TN only
+  float* ws = nullptr;  // TN, SIMT / skinny kernels: workspace of gemm_*_ws_floats() floats for the split partial sums
   // relu layers on the tcgen05 path: the forward epilogue also writes one bit per output (activation > 0), 32 columns
   // per word, row pitch ldmask words; the dgrad epilogue reads these words instead of the fp32 activation tile (`aux`)
   uint32_t* mask_out = nullptr;
@@ -33,12 +35,17 @@ struct GemmArgs {
 void launch_gemm_nn_simt(const GemmArgs& a, cudaStream_t s);
 void launch_gemm_nt_simt(const GemmArgs& a, cudaStream_t s);
 void launch_gemm_tn_simt(const GemmArgs& a, cudaStream_t s);
-// out[cols] += column sums of X[rows, cols] (bias gradient when the wgrad GEMM runs on the tensor cores)
-void launch_colsum(const float* X, int64_t ld, int rows, int cols, float* out, cudaStream_t s);
+int64_t gemm_tn_simt_ws_floats(const GemmArgs& a);
+// out[cols] += column sums of X[rows, cols] (bias gradient when the wgrad GEMM runs on the tensor cores); `ws` =
+// colsum_ws_floats(rows, cols) zero-initialised floats owned by the call site (per-CTA partials + arrival tickets; the
+// kernel leaves the tickets at zero), so that the sum has a fixed order
+int64_t colsum_ws_floats(int64_t rows, int cols);
+void launch_colsum(const float* X, int64_t ld, int64_t rows, int cols, float* out, float* ws, cudaStream_t s);
 
 // HBM-bound kernels for contractions with one extent <= 16 (the n_z-wide heads / decoder input layer), gemm_skinny.cu
 bool skinny_supported(int kind /*0 NN,1 NT,2 TN*/, const GemmArgs& a);
 void launch_gemm_skinny(int kind, const GemmArgs& a, cudaStream_t s);
+int64_t gemm_skinny_ws_floats(int kind, const GemmArgs& a);
 
 // tcgen05 / TMA path (gemm_group.cu): a persistent kernel that executes a list of 256 x BN tile tasks drawn from
 // several contractions ("problems"), ordered by dependency and linked by row-block completion counters.  A plan owns

@@ -101,6 +101,7 @@ class AssocVariationalAutoEncoder(object):
             mod.hidden_conv = 1 if na.get("hidden_conv", False) else 0
             mod.binary = 1 if self.binary[m] else 0
             mod.weight = float(self.weights[m])
+            mod.scope = str(na.get("scope", "")).encode()[:31]      # tf.variable_scope(scope), vae_assoc.py:168,248
             assert na["n_z"] == self.n_z, "all modalities share one latent size (vae_assoc.py:89-91)"
         self._cfg = cfg
         h = L.Handle()
@@ -117,8 +118,10 @@ class AssocVariationalAutoEncoder(object):
         self._rng = np.random.RandomState(seed)
         self._init_weights()
         self._prior_draws = 0
-        self._pinned = None
-        self._submitted = 0
+        self._keep = [None, None]       # host arrays of the two most recent pipelined submits (kept alive across the DMA)
+        self._world = 1
+        from . import tf_shim
+        tf_shim.register(self)          # tf.all_variables() / tf.reset_default_graph() see this model (weak reference)
 
     # ---- plumbing --------------------------------------------------------------------------------
     def _check(self, rc):
@@ -298,6 +301,12 @@ class AssocVariationalAutoEncoder(object):
             ptrs, keep = self._host_args(X)
             e = None if eps is None else np.ascontiguousarray(eps, dtype=np.float32)
             self._check(self._lib.vaeassoc_submit_host(self._h, ptrs, None if e is None else e.ctypes.data_as(C.c_void_p)))
+            # the H2D copies of PINNED arrays are asynchronous DMA: keep the arrays of the last two submits alive (the
+            # library double-buffers, so older copies have completed); callers that REFILL a pinned buffer must call
+            # wait_uploaded(k) first (include/vaeassoc.h, vaeassoc_submit_host)
+            k = int(self._lib.vaeassoc_submit_count(self._h)) - 1
+            self._keep[k & 1] = (keep, e)
+            return k
 
     def compute_gradients(self, X, eps=None):
         """Forward + backward without the Adam update; returns the cost.  Gradients: `get_grads()`."""
@@ -326,8 +335,30 @@ class AssocVariationalAutoEncoder(object):
         self._check(self._lib.vaeassoc_submit_costs(self._h, int(first_submit), int(n), out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def wait_uploaded(self, submit_index):
+        """Blocks until the host->device copies of pipelined submit `submit_index` (the value partial_fit_async returned)
+        have completed; after that its (pinned) host buffers may be refilled."""
+        self._check(self._lib.vaeassoc_upload_wait(self._h, int(submit_index)))
+
     def synchronize(self):
         self._check(self._lib.vaeassoc_stream_sync(self._h))
+
+    def relu_masks(self, m):
+        """The relu sign masks the tensor-core path stored for modality m at the most recent step, as boolean arrays
+        {"h1","h2","g1","g2"} of shape [batch_size, width] (TF ReluGrad's `y > 0`).  Parity tests feed them to the oracle."""
+        na = self.network_architectures[m]
+        out = {}
+        for layer, (name, width) in enumerate([("h1", na["n_hidden_recog_1"]), ("h2", na["n_hidden_recog_2"]),
+                                               ("g1", na["n_hidden_recog_1"]), ("g2", na["n_hidden_recog_2"])]):
+            wpr = (width + 31) // 32
+            buf = np.empty(self.batch_size * wpr, np.uint32)
+            n, w = C.c_int64(), C.c_int64()
+            self._check(self._lib.vaeassoc_probe_mask(self._h, layer, m, buf.ctypes.data_as(C.c_void_p), buf.size,
+                                                      C.byref(n), C.byref(w)))
+            words = buf.reshape(self.batch_size, wpr)
+            bits = (words[:, :, None] >> np.arange(32, dtype=np.uint32)[None, None, :]) & 1
+            out[name] = bits.reshape(self.batch_size, wpr * 32)[:, :width].astype(bool)
+        return out
 
     def evaluate_cost(self, X, eps=None):
         """vae_assoc.py:388-391"""
@@ -501,6 +532,17 @@ class AssocVariationalAutoEncoder(object):
         dist.broadcast_object_list(ids, src=0)
         buf = (C.c_ubyte * 128).from_buffer_copy(ids[0])
         self._check(self._lib.vaeassoc_comm_init(self._h, path, buf, rank, world))
+        self._world = world
+        # replicas must start identical (the all-reduce only averages gradients): rank 0's parameters, Adam slots and step
+        self.sync_replicas()
+
+    def sync_replicas(self):
+        """Broadcast rank 0's parameters / Adam state to every rank (call on ALL ranks, e.g. after a rank-0 restore_model)."""
+        self._check(self._lib.vaeassoc_comm_sync_state(self._h))
+
+    def check_communicator(self):
+        """ncclCommGetAsyncError; raises VaeAssocError (after aborting the communicator) on an asynchronous NCCL failure."""
+        self._check(self._lib.vaeassoc_comm_check(self._h))
 
     # ---- checkpoints (tf.train.Saver surface, vae_assoc.py:70,427-463) -------------------------------------
     def save_model(self, fname=None):
@@ -552,12 +594,26 @@ def train(data_sets, network_architectures, binary=True, weights=1.0, assoc_lamb
     n_mod = len(network_architectures)
     avg_cost_hist = []
     valid_cost = None
-    step = 0
+    # the reference slices the batch into per-modality column views (:543) and feed_dict copies them; here the slices are
+    # written into a ring of PINNED per-modality staging buffers (true async DMA, overlapping the previous step's compute);
+    # a slot is refilled only after vaeassoc_upload_wait says its previous upload has completed
+    torch = vae_assoc._torch
+    n_slots = 3
+    staging = [[torch.empty((batch_size, int(na["n_input"])), dtype=torch.float32, pin_memory=True).numpy()
+                for na in network_architectures] for _ in range(n_slots)]
+    slot_submit = [None] * n_slots
 
-    def segment(batch_xs):
-        return [np.ascontiguousarray(batch_xs[:, sens_indices[i]:sens_indices[i + 1]], dtype=np.float32)
-                for i in range(n_mod)]
+    def segment(batch_xs, slot=None):
+        if slot is None:
+            return [np.ascontiguousarray(batch_xs[:, sens_indices[i]:sens_indices[i + 1]], dtype=np.float32)
+                    for i in range(n_mod)]
+        if slot_submit[slot] is not None:
+            vae_assoc.wait_uploaded(slot_submit[slot])
+        for i in range(n_mod):
+            np.copyto(staging[slot][i], batch_xs[:, sens_indices[i]:sens_indices[i + 1]], casting="same_kind")
+        return staging[slot]
 
+    submits = 0
     for epoch in range(training_epochs):
         avg_cost = 0.
         total_batch = int(n_samples / batch_size)
@@ -574,16 +630,24 @@ def train(data_sets, network_architectures, binary=True, weights=1.0, assoc_lamb
                         print('Validation error increases. Early stop at epoch {} to prevent overfitting...'.format(epoch + 1))
                         break
                 valid_cost = curr_valid_cost
-        first = step
+        # costs come back from the pinned per-submit ring in chunks (one host synchronisation per chunk instead of the
+        # reference's one per step, vae_assoc.py:383-386); the ring holds 4096 submits
+        chunk_first = submits
+        def drain(upto):
+            nonlocal chunk_first, avg_cost
+            if upto > chunk_first:
+                for cost in vae_assoc.submit_costs(chunk_first, upto - chunk_first):
+                    avg_cost += cost / n_samples * batch_size
+                    avg_cost_hist.append(avg_cost)
+                chunk_first = upto
         for i in range(total_batch):
             batch_xs, _ = data_sets.train.next_batch(batch_size)
-            vae_assoc.partial_fit_async(segment(batch_xs))
-            step += 1
-        if total_batch:
-            costs = vae_assoc.cost_history(first, total_batch)
-            for cost in costs:
-                avg_cost += cost / n_samples * batch_size
-                avg_cost_hist.append(avg_cost)
+            slot = submits % n_slots
+            slot_submit[slot] = vae_assoc.partial_fit_async(segment(batch_xs, slot))
+            submits += 1
+            if submits - chunk_first >= 2048:
+                drain(submits)
+        drain(submits)
         if epoch % display_step == 0:
             print("Epoch:", '%04d' % (epoch + 1), "cost=", "{:.9f}".format(avg_cost))
     return vae_assoc, avg_cost_hist
