@@ -148,6 +148,128 @@ def cpu_reference_run(batch, steps, warmup, threads=None, archs=None):
     return batch * steps / dt, 1e3 * dt / steps, cores
 
 
+def pool_size(bytes_per_batch):
+    """distinct device-resident batches the timed loop rotates through: > 2 x the 126 MB L2"""
+    return min(max(4, int(np.ceil(2.2 * 126e6 / bytes_per_batch))), 512)
+
+
+def make_config(args, archs, desc, world):
+    """`config` of the JSON line -- the SAME dict for this repo's arm and for `--impl reference` (the driver compares them)."""
+    B = args.batch
+    bytes_per_batch = B * sum(na["n_input"] for na in archs) * 4
+    n = pool_size(bytes_per_batch)
+    return dict(workload="%s, %d pairs per GPU per step" % (desc, B), name=args.config, global_batch=B * world,
+                per_gpu_batch=B, parallelism="dp%d" % world,
+                l2="GPU arm: inputs rotate through a device pool of %d distinct batches (%.0f MB > 126 MB L2)"
+                   % (n, n * bytes_per_batch / 1e6))
+
+
+def committed_profile(name):
+    """numbers that come from committed profiler captures, never literals in this file"""
+    p = os.path.join(ROOT, "profiles", name)
+    return json.load(open(p)) if os.path.exists(p) else {}
+
+
+def parity_check(archs, B, precision, dynamic_first):
+    """Outside every timed region: ONE compute_gradients of the benchmarked path (same architecture, same per-GPU batch,
+    same precision, fused tile segments) against the CPU oracle -- the operand-rounding oracle for tf32, the exact one
+    for fp32 -- on a synthetic batch with injected Philox eps.  Returns {cost_rel, worst_grad_l2, worst_grad_max, ...}."""
+    from oracle import philox
+    from oracle import vae_assoc_oracle as vo
+    from vae_assoc_b200 import vae_assoc
+    if dynamic_first:
+        os.environ["VAEASSOC_DYNAMIC_FIRST"] = "1"      # the task-queue mode data-parallel runs use
+    try:
+        model = vae_assoc.AssocVariationalAutoEncoder(archs, [True, False], transfer_fct=vae_assoc.relu, weights=[50, 1],
+                                                      assoc_lambda=8, learning_rate=1e-3, batch_size=B, precision=precision, seed=0)
+    finally:
+        os.environ.pop("VAEASSOC_DYNAMIC_FIRST", None)
+    params = model.get_params()
+    rng = np.random.RandomState(5)
+    params = [p if p.ndim > 1 else (0.05 * rng.normal(size=p.shape)).astype(np.float32) for p in params]
+    model.set_params(params)
+    per_mod, k = [], 0
+    for na in archs:
+        n = len(vo.param_names(na))
+        per_mod.append([p.astype(np.float64) for p in params[k:k + n]]); k += n
+    oracle = vo.OracleAssocVAE(archs, [True, False], "relu", [50.0, 1.0], 8.0, 1e-3, B, params=per_mod,
+                               emulate_tf32=(precision == "tf32"))
+    xs = model.synth_batch(0, B)
+    X = [x.cpu().numpy() for x in xs]
+    eps = philox.eps_rows(0, 0, 0, B, archs[0]["n_z"]).astype(np.float32)
+    t0 = time.perf_counter()
+    cost = float(model.compute_gradients(xs, eps))
+    c_ref, g_ref, _ = oracle.loss_and_grads(X, eps)
+    l2 = mx = 0.0
+    worst = None
+    for g, r, n in zip(model.get_grads(), [g for gs in g_ref for g in gs], model.variable_roles()):
+        r = np.asarray(r, np.float64); g = np.asarray(g, np.float64)
+        e2 = float(np.linalg.norm(g - r) / max(np.linalg.norm(r), 1e-30))
+        em = float(np.abs(g - r).max() / max(np.abs(r).max(), 1e-30))
+        if e2 > l2:
+            l2, worst = e2, "%d/%s" % n
+        mx = max(mx, em)
+    fused = model.launch_count()
+    model.close()
+    return dict(cost_rel=abs(cost - c_ref) / abs(c_ref), worst_grad_l2=l2, worst_grad_max=mx, worst_tensor=worst,
+                oracle="fp64 numpy restatement, operands rounded to tf32 where the CUDA path rounds" if precision == "tf32"
+                else "fp64 numpy restatement (exact)",
+                bounds=dict(cost_rel=5e-4, worst_grad_l2=5e-4), batch=B, precision=precision,
+                seconds=round(time.perf_counter() - t0, 2))
+
+
+def timed_steps(model, pool, steps, warmup, barrier=None):
+    """K steps from device-resident batches, CUDA events on the library's stream; returns ms per step."""
+    import torch
+    n = len(pool)
+    for k in range(warmup):
+        model.partial_fit_async(pool[k % n])
+    (barrier or torch.cuda.synchronize)()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for k in range(steps):
+        model.partial_fit_async(pool[(warmup + k) % n])
+    ev1.record()
+    (barrier or torch.cuda.synchronize)()
+    return ev0.elapsed_time(ev1) / steps
+
+
+def secondary_runs(local_rank):
+    """The other BASELINE.json configurations, short (N = 1 only): reference arch at the reference's own batch 100, the fp32
+    (1e-4) path at 8192, the hidden_conv modality at 4096 (configs[3]) and the scaled model at 16 384 (configs[4], one
+    GPU's share).  Same timing rules as the headline (device events, inputs rotating through a pool larger than L2)."""
+    import torch
+    from vae_assoc_b200 import vae_assoc
+    out = []
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for name, cfg, B, precision, steps in (("ref_b100", "ref", 100, "tf32", 400), ("ref_fp32_b8192", "ref", 8192, "fp32", 12),
+                                           ("conv_b4096", "conv", 4096, "tf32", 20), ("scaled_b16384", "scaled", 16384, "tf32", 12)):
+        mk, _, desc = CONFIGS[cfg]
+        archs = mk()
+        try:
+            model = vae_assoc.AssocVariationalAutoEncoder(archs, [True, False], transfer_fct=vae_assoc.relu, weights=[50, 1],
+                                                          assoc_lambda=8, learning_rate=1e-3, batch_size=B, precision=precision, seed=0)
+            n = pool_size(B * sum(na["n_input"] for na in archs) * 4)
+            if B <= 256:
+                n = min(n, 64)         # 100-pair batches are 0.37 MB: a 64-batch pool is cycled; the 5.7 MB of weights dominate anyway
+            pool = [model.synth_batch(k * B, B) for k in range(n)]
+            torch.cuda.synchronize()
+            l0 = model.launch_count()
+            ms = timed_steps(model, pool, steps, 5)
+            launches = (model.launch_count() - l0) / float(steps + 5)
+            flops = dense_flops_per_sample(archs) * B if cfg != "conv" else None
+            out.append(dict(name=name, config=cfg, per_gpu_batch=B, dtype=precision, steps=steps, warmup=5, ms_per_step=ms,
+                            value=B / (ms * 1e-3), unit="samples/s", launches_per_step=launches,
+                            step_tflops=(flops / (ms * 1e-3) / 1e12) if flops else None, last_cost=float(model.last_cost())))
+            model.close()
+            del pool
+            torch.cuda.empty_cache()
+        except Exception as e:      # a secondary line must never take the headline down
+            out.append(dict(name=name, error=str(e)[:300]))
+    return out, sampler.stop()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -160,6 +282,8 @@ def main():
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the short runs of the other BASELINE configs")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the benchmarked path")
     ap.add_argument("--quick", action="store_true", help="diagnostics: only the HBM-resident timing loop")
     args = ap.parse_args()
 
@@ -175,22 +299,24 @@ def main():
     if args.batch <= 0:
         args.batch = default_batch
     archs = mk_archs()
-    workload = "%s, %d pairs per GPU per step" % (desc, args.batch)
 
     if args.impl == "reference":
         if rank != 0:
             return
-        # each step = a bounded sample (same per-GPU batch) so that the run ends within minutes
-        steps = min(args.steps, 10); warm = min(args.warmup, 2)
-        cpu_batch = min(args.batch, 8192 if args.config == "ref" else 2048)     # bounded sample of the per-GPU batch
-        sps, ms, cores = cpu_reference_run(cpu_batch, steps, warm, archs=archs)
+        # the reference's CPU implementation of the path (torch-CPU restatement: TensorFlow is not installable), all host
+        # threads, EXACTLY --steps timed and --warmup untimed steps; each step = a bounded sample of the arm's per-GPU batch
+        n_gpus = max(args.gpus, world)
+        cpu_batch = min(args.batch, 8192 if args.config == "ref" else 2048)
+        sps, ms, cores = cpu_reference_run(cpu_batch, args.steps, args.warmup, archs=archs)
         line = dict(impl="reference", metric="paired samples/sec/train step", value=sps, unit="samples/s",
-                    n_gpus=args.gpus, steps=steps, warmup=warm, ms_per_step=ms, higher_is_better=True, scaling="weak",
+                    n_gpus=n_gpus, steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak",
                     vs_baseline=None, dtype="fp32", data="synthetic",
-                    config=dict(workload=workload, name=args.config, global_batch=args.batch, note="CPU restatement (torch fp32) of the "
-                                "reference graph, not TensorFlow (not installable here); one process, host cores only"),
+                    config=make_config(args, archs, desc, n_gpus),
+                    reference_note="CPU restatement (torch fp32) of the reference graph, not TensorFlow (not installable here); "
+                                   "one process on rank 0, host cores only",
                     cpu_baseline=dict(value=sps, unit="samples/s", cores=cores, kind="port",
-                                      sample="%d steps of %d pairs after %d warm-up" % (steps, cpu_batch, warm)),
+                                      sample="each step = %d pairs (bounded sample of the %d-pair per-GPU batch), %d timed "
+                                             "steps after %d warm-up" % (cpu_batch, args.batch, args.steps, args.warmup)),
                     e2e=dict(value=sps, unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
         json_out.write(json.dumps(line) + "\n"); json_out.flush()
         return
@@ -212,11 +338,9 @@ def main():
     if world > 1:
         model.init_data_parallel()
 
-    # device-resident pool of distinct synthetic batches, larger than L2 (126 MB) so that no step re-reads a
-    # cached input: 16 x 30.5 MB at B = 8192
+    # device-resident pool of distinct synthetic batches, larger than L2 (126 MB) so that no step re-reads a cached input
     bytes_per_batch = B * sum(na["n_input"] for na in archs) * 4
-    pool_n = max(4, int(np.ceil(2.2 * 126e6 / bytes_per_batch)))
-    pool_n = min(pool_n, 512)
+    pool_n = pool_size(bytes_per_batch)
     pool = [model.synth_batch((k * world + rank) * B, B) for k in range(pool_n)]
     torch.cuda.synchronize()
 
@@ -256,7 +380,7 @@ def main():
     if ms_total < 400.0:
         # keep the same work running until the 100 ms clock sampler has seen it (these steps are not timed).  EVERY rank
         # runs the same number of extra steps (the count derives from the rank-reduced time): under data parallelism a
-        # step contains two all-reduces, and a rank that stepped alone would wait for its peers forever
+        # step contains all-reduces, and a rank that stepped alone would wait for its peers forever
         n_extra = int(min(5000, max(20, 600.0 / max(ms_total / args.steps, 1e-3))))
         for k in range(n_extra):
             model.partial_fit_async(pool[k % pool_n])
@@ -275,32 +399,55 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- end to end: pinned host batches -> H2D -> step -> D2H of the cost, every step --------------------------
+    # ---- end to end: host batches -> H2D -> step -> D2H of the cost, every step ----------------------------------
+    def e2e_run(host_pool, refill_guard):
+        n = len(host_pool)
+        tickets = [None] * n
+        for k in range(min(args.warmup, 5)):
+            tickets[k % n] = model.partial_fit_async(host_pool[k % n])
+        barrier()
+        t0 = time.perf_counter()
+        ev0.record()
+        for k in range(args.steps):
+            if refill_guard and tickets[k % n] is not None:
+                model.wait_uploaded(tickets[k % n])      # a pinned slot is handed out again only after its DMA has completed
+            tickets[k % n] = model.partial_fit_async(host_pool[k % n])
+        ev1.record()
+        model.synchronize()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = max_over_ranks(max(ev0.elapsed_time(ev1), wall * 1e3))
+        return Bg * args.steps / (ms * 1e-3), ms / args.steps
+
     host_n = 4
-    host_pool = []
-    for k in range(host_n):
-        xs = pool[k]
-        host_pool.append([torch.empty(x.shape, dtype=torch.float32, pin_memory=True).copy_(x).numpy() for x in xs])
+    pinned_pool = [[torch.empty(x.shape, dtype=torch.float32, pin_memory=True).copy_(x).numpy() for x in pool[k]] for k in range(host_n)]
     torch.cuda.synchronize()
-    e2e_steps = args.steps
-    for k in range(min(args.warmup, 5)):
-        model.partial_fit_async(host_pool[k % host_n])
+    e2e_value, e2e_ms = e2e_run(pinned_pool, True)
+    # the reference's callers hand partial_fit fresh PAGEABLE numpy arrays (vae_assoc.py:541-543): same loop, pageable memory
+    pageable_pool = [[np.array(a, copy=True) for a in hp] for hp in pinned_pool]
+    pg_value, pg_ms = e2e_run(pageable_pool, False)
+    # device-resident data set (train(device_data=True)): the pool's rows uploaded once, batches gathered by index
+    width = sum(na["n_input"] for na in archs)
+    rows = np.concatenate([np.concatenate(hp, axis=1) for hp in pinned_pool], axis=0)
+    data_dev = model.upload_dataset(rows)
+    idx_rng = np.random.RandomState(rank)
+    idx_pool = [np.ascontiguousarray(idx_rng.permutation(rows.shape[0])[:B].astype(np.int64)) for _ in range(8)]
+    for k in range(5):
+        model.partial_fit_indexed(data_dev, idx_pool[k % 8])
     barrier()
-    sub0 = None
     t0 = time.perf_counter()
     ev0.record()
-    for k in range(e2e_steps):
-        model.partial_fit_async(host_pool[k % host_n])
+    for k in range(args.steps):
+        model.partial_fit_indexed(data_dev, idx_pool[k % 8])
     ev1.record()
     model.synchronize()
     barrier()
-    wall = time.perf_counter() - t0
-    e2e_ms = max_over_ranks(max(ev0.elapsed_time(ev1), wall * 1e3))
-    e2e_value = Bg * e2e_steps / (e2e_ms * 1e-3)
+    dd_ms = max_over_ranks(max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3))
+    dd_value = Bg * args.steps / (dd_ms * 1e-3)
+    del data_dev
 
     # ---- per-kernel roofline: one eager step with CUDA events between ops, averaged ------------------------------
     import ctypes as C
-    from vae_assoc_b200 import _lib as L
     cap = 128
     names = C.create_string_buffer(32 * cap)
     ms = (C.c_float * cap)(); fl = (C.c_double * cap)(); by = (C.c_double * cap)()
@@ -330,21 +477,23 @@ def main():
     kernels.sort(key=lambda k: -k["ms"])
     top = kernels[0]
     eager_ms = sum(k["ms"] for k in kernels)
-    # dram__bytes_read.sum + dram__bytes_write.sum per launch of the four fused segments, from the committed ncu --set full
-    # capture of this workload (profiles/r1_group_final_ncu.md); other workloads / kernels: not captured -> null
-    ncu_traffic = {"seg_fwd_enc": 41.2e6, "seg_fwd_dec": 27.1e6, "seg_bwd_dec": 119.0e6, "seg_bwd_enc": 123.6e6}
-    traffic = ncu_traffic.get(top["name"]) if (args.config == "ref" and B == 8192 and args.precision == "tf32") else None
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of THIS workload
+    # (profiles/ncu_traffic.json names the capture it was read from); other workloads / kernels: not captured -> null
+    prof = committed_profile("ncu_traffic.json")
+    key = "%s_b%d_%s" % (args.config, B, args.precision)
+    traffic = prof.get(key, {}).get("dram_bytes_per_launch", {}).get(top["name"])
+    tf32_ref = committed_profile("r1_tf32_peak.json").get("tf32_tflops_burst")
     roofline = dict(bound=top.get("bound", "hbm"), kernel=top["name"], achieved=top.get("achieved"),
                     peak=pk["tensor"] if top.get("bound") == "tensor" else pk["hbm"], unit=top.get("unit"),
                     frac=top.get("frac"), traffic=traffic, traffic_unit="bytes per launch (DRAM read + write, ncu)",
+                    traffic_source=prof.get(key, {}).get("source"),
                     peak_source=pk["src"],
                     share_of_step=top["ms"] / eager_ms,
                     note="peak = measured cuBLAS bf16 (MEASURED_PEAKS.json); this path computes in kind::tf32, whose nominal peak "
-                         "is half of bf16 and whose measured cuBLAS 8192^3 throughput on this pool is 710.7 TFLOP/s "
-                         "(profiles/r1_tf32_peak.json): frac_of_tf32_cublas = achieved / 710.7"
+                         "is half of bf16; measured cuBLAS tf32 8192^3 on this pool: profiles/r1_tf32_peak.json"
                     if top.get("bound") == "tensor" else "")
-    if top.get("bound") == "tensor" and top.get("achieved"):
-        roofline["frac_of_tf32_cublas"] = top["achieved"] / 710.7
+    if top.get("bound") == "tensor" and top.get("achieved") and tf32_ref:
+        roofline["frac_of_tf32_cublas"] = top["achieved"] / tf32_ref
     # algorithmic FLOPs of one step = sum over the contractions of the schedule (2*M*N*K each); for the dense configs this
     # is SURVEY 8d's per-sample figure x B (7 744 400 x B at the reference arch)
     step_flops = sum(f for (_, f, _) in acc.values())
@@ -352,29 +501,43 @@ def main():
         assert abs(step_flops - dense_flops_per_sample(archs) * B) <= 1e-6 * step_flops, (step_flops, dense_flops_per_sample(archs) * B)
     step_tflops = step_flops / (ms_step * 1e-3) / 1e12
 
+    cfg = make_config(args, archs, desc, world)
     line = dict(metric="paired samples/sec/train step", value=value, unit="samples/s", n_gpus=world, steps=args.steps,
                 warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype=args.precision, data="synthetic",
-                config=dict(workload=workload, name=args.config, global_batch=Bg, per_gpu_batch=B, parallelism="dp%d" % world,
-                            l2="inputs rotate through a device pool of %d distinct batches (%.0f MB > 126 MB L2)"
-                               % (pool_n, pool_n * bytes_per_batch / 1e6),
-                            graph=not args.no_graph),
+                dtype=args.precision, data="synthetic", config=cfg, graph=not args.no_graph,
                 clocks=clocks, gpu_launches=int(launches),
                 e2e=dict(value=e2e_value, unit="samples/s", h2d_bytes_per_step=bytes_per_batch, d2h_bytes_per_step=4,
-                         ms_per_step=e2e_ms / e2e_steps,
+                         ms_per_step=e2e_ms,
                          path="AssocVariationalAutoEncoder.partial_fit_async(numpy pinned) -> vaeassoc_submit_host"),
+                e2e_pageable=dict(value=pg_value, unit="samples/s", h2d_bytes_per_step=bytes_per_batch, d2h_bytes_per_step=4,
+                                  ms_per_step=pg_ms, path="the same call with pageable numpy arrays (what the reference's callers pass)"),
+                e2e_device_dataset=dict(value=dd_value, unit="samples/s", h2d_bytes_per_step=8 * B, d2h_bytes_per_step=4,
+                                        ms_per_step=dd_ms / args.steps,
+                                        path="train(device_data=True): partial_fit_indexed -> vaeassoc_submit_indexed (data set "
+                                             "uploaded once, batches gathered on the device from host row indices)"),
                 roofline=roofline, step_tflops_per_gpu=step_tflops, last_cost=last_cost,
                 kernels=kernels[:40])
+    model.close()
+    del pool
+    torch.cuda.empty_cache()
 
+    if rank == 0 and not args.no_parity:
+        try:
+            line["parity"] = parity_check(archs, B, args.precision, dynamic_first=world > 1)
+        except Exception as e:
+            line["parity"] = dict(error=str(e)[:300])
+    if rank == 0 and world == 1 and not args.no_secondary and args.config == "ref":
+        line["secondary"], line["secondary_clocks"] = secondary_runs(local_rank)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_batch = min(B, 8192 if args.config == "ref" else 2048)
         sps, cms, cores = cpu_reference_run(cpu_batch, 5, 1, archs=archs)
         line["cpu_baseline"] = dict(value=sps, unit="samples/s", cores=cores, kind="port", ms_per_step=cms,
                                     sample="5 steps of %d pairs after 1 warm-up, torch-CPU fp32 restatement "
                                            "(not TensorFlow)" % cpu_batch)
+    if world > 1:
+        dist.barrier()
     if rank == 0:
         json_out.write(json.dumps(line) + "\n"); json_out.flush()
-    model.close()
     if world > 1:
         dist.destroy_process_group()
 

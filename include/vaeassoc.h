@@ -129,6 +129,12 @@ int vaeassoc_partial_fit_host(vaeassoc_handle h, const float* const* x_host, con
  * allocated and unmodified until `vaeassoc_upload_wait(h, k)` has returned for this submit's index k (= the number of
  * submits made before it; vaeassoc_submit_count).  train() and bench.py rotate pinned slots behind that call. */
 int vaeassoc_submit_host(vaeassoc_handle h, const float* const* x_host, const float* eps_host);
+/* device-resident data set (replaces dataset.py:22-43 next_batch + the column slicing of vae_assoc.py:510,543 + the
+ * feed_dict copy): `data_dev` = the whole training matrix [n_rows, >= sum n_input] uploaded ONCE (row pitch `ld` floats;
+ * modality m occupies columns [sum_{k<m} n_input_k, +n_input_m), the reference's sens_indices); `index_host` = the
+ * batch_size row indices of this step (the epoch's shuffled order).  Only the indices cross PCIe (8 B per pair). */
+int vaeassoc_submit_indexed(vaeassoc_handle h, const float* data_dev, int64_t ld, int64_t n_rows,
+                            const int64_t* index_host, const float* eps_host);
 int64_t vaeassoc_submit_count(vaeassoc_handle h);                     /* submits so far = index of the next one */
 int vaeassoc_upload_wait(vaeassoc_handle h, int64_t submit_index);    /* blocks until that submit's H2D completed */
 /* every submit also queues an async D2H of that step's cost into a pinned host ring (4096 entries);

@@ -29,7 +29,12 @@ def test_reference_arm_prints_one_json_line():
     assert d["higher_is_better"] is True and d["value"] > 0 and d["vs_baseline"] is None
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
     assert d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert "workload" in d["config"] and "not TensorFlow" in d["config"]["note"]
+    assert "workload" in d["config"] and "not TensorFlow" in d["reference_note"]
+    assert d["steps"] == 1 and d["warmup"] == 0 and d["n_gpus"] == 1            # the arm honours --steps / --warmup / --gpus
+    # `config` is built by ONE function for both arms (the driver compares them)
+    import argparse
+    a = argparse.Namespace(batch=128, config="ref")
+    assert d["config"] == bench.make_config(a, bench.ref_archs(), bench.CONFIGS["ref"][2], 1)
 
 
 def test_reference_arm_is_silent_on_other_ranks():

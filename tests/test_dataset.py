@@ -82,3 +82,17 @@ def test_extract_loaders_follow_reference_order(tmp_path):
     assert ds.train._data.shape[1] == 931
     assert ds.train._data.shape[0] + ds.validation._data.shape[0] + ds.test._data.shape[0] == 7
     np.testing.assert_allclose(m2, mean)
+
+
+def test_next_indices_equals_next_batch():
+    from vae_assoc_b200 import dataset
+    data = np.arange(53 * 3, dtype=np.float32).reshape(53, 3)
+    a, b = dataset.DataSet(data), dataset.DataSet(data)
+    np.random.seed(4)                         # the epoch shuffles draw from the global numpy RNG (dataset.py:29-30)
+    batches = [a.next_batch(8)[0] for _ in range(17)]     # crosses several epoch boundaries (53 rows, batches of 8)
+    np.random.seed(4)
+    for rows in batches:
+        idx = b.next_indices(8)
+        assert idx.dtype == np.int64
+        np.testing.assert_array_equal(rows, data[idx])
+    assert a._epochs_completed == b._epochs_completed > 0

@@ -513,3 +513,23 @@ def test_contract_entries(va):
         va.AssocVariationalAutoEncoder([archs[0], dict(archs[1], scope="joint")], [False, True], batch_size=8, precision="fp32")
     tf_shim.reset_default_graph()                                    # closes the registered model
     assert model._h is None and tf_shim.all_variables() == []
+
+
+def test_device_resident_dataset_path_matches_host_path(va):
+    """train(device_data=True): the training matrix is uploaded once and every batch is gathered on the device from the
+    row indices next_batch would use -- same batches, same costs as the host-buffer path (fp32: bit-identical)."""
+    from vae_assoc_b200 import dataset
+    archs = vo.reference_archs(4)
+    Xs = synth.synth_batch(archs, [True, False], 0, 1, 0, 300)
+    data = np.concatenate(Xs, axis=1).astype(np.float32)
+    hists = []
+    for device_data in (False, True):
+        np.random.seed(0)
+        ds = dataset.construct_datasets(data, validation_ratio=.1, test_ratio=.1)
+        model, hist = va.train(ds, archs, binary=[True, False], weights=[50, 1], assoc_lambda=8, learning_rate=1e-3,
+                               batch_size=32, training_epochs=3, display_step=1, precision="fp32", eps_seed=5,
+                               device_data=device_data)
+        hists.append(np.asarray(hist, np.float64))
+        model.close()
+    assert len(hists[0]) == len(hists[1]) > 0
+    np.testing.assert_array_equal(hists[0], hists[1])

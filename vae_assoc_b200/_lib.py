@@ -66,6 +66,7 @@ SIGNATURES = {
     "vaeassoc_cost_history": (C.c_int, [Handle, C.c_int64, C.c_int64, C.c_void_p]),
     "vaeassoc_partial_fit_host": (C.c_int, [Handle, FloatPP, C.c_void_p, C.POINTER(C.c_float)]),
     "vaeassoc_submit_host": (C.c_int, [Handle, FloatPP, C.c_void_p]),
+    "vaeassoc_submit_indexed": (C.c_int, [Handle, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "vaeassoc_submit_count": (C.c_int64, [Handle]),
     "vaeassoc_upload_wait": (C.c_int, [Handle, C.c_int64]),
     "vaeassoc_submit_costs": (C.c_int, [Handle, C.c_int64, C.c_int64, C.c_void_p]),

@@ -148,6 +148,8 @@ struct vaeassoc_ctx {
   float *p = nullptr, *g = nullptr, *m = nullptr, *v = nullptr, *p_tf32 = nullptr;   // g has n_flat + 32 floats
   bool shadow_dirty = true;
   float *eps = nullptr, *eps_in[2] = {nullptr, nullptr}, *lat_partials = nullptr, *scalars = nullptr;
+  int64_t* idx_in[2] = {nullptr, nullptr};      // batch row indices of the device-resident data-set path (double buffered)
+  int64_t indexed_count = 0;
   float *cost_hist = nullptr, *last_cost = nullptr;
   float* host_cost_ring = nullptr;   // pinned; one async D2H of the step's cost per vaeassoc_submit_host
   static constexpr int kHostRing = 4096;
@@ -401,6 +403,8 @@ void alloc_buffers(Ctx* c) {
   c->eps = c->dalloc<float>(B * nz);
   c->eps_in[0] = c->dalloc<float>(B * nz);
   c->eps_in[1] = c->dalloc<float>(B * nz);
+  c->idx_in[0] = c->dalloc<int64_t>(B);
+  c->idx_in[1] = c->dalloc<int64_t>(B);
   c->lat_partials = c->dalloc<float>((int64_t)kMaxPartialBlocks * kCostSlots);
   c->scalars = c->dalloc<float>(16);
   c->cost_hist = c->dalloc<float>(c->hist_cap);
@@ -1145,8 +1149,9 @@ void refresh_shadow(Ctx* c, cudaStream_t s) {
 }
 
 void stage_inputs(Ctx* c, const float* const* x, const int64_t* ld, const float* eps, cudaStream_t s,
-                  int only_modality = -1, bool want_eps = true) {
+                  int only_modality = -1, bool want_eps = true, const int64_t* row_index = nullptr) {
   StageArgs a;
+  a.row_index = row_index;
   a.n_mod = c->cfg.n_modalities; a.batch = c->cfg.batch_size;
   for (int m = 0; m < a.n_mod; ++m) {
     const Mod& d = c->mods[m];
@@ -1571,6 +1576,38 @@ int vaeassoc_submit_host(vaeassoc_handle h, const float* const* x_host, const fl
   run_step(h, true);
   CUDA_OK(cudaMemcpyAsync(h->host_cost_ring + (h->submit_count % Ctx::kHostRing), h->last_cost, sizeof(float),
                           cudaMemcpyDeviceToHost, h->stream));
+  h->submit_count += 1;
+  API_END(h)
+}
+
+int vaeassoc_submit_indexed(vaeassoc_handle h, const float* data_dev, int64_t ld, int64_t n_rows,
+                            const int64_t* index_host, const float* eps_host) {
+  API_BEGIN(h)
+  if (!data_dev || !index_host) fail("data_dev / index_host is null");
+  int64_t width = 0;
+  for (int m = 0; m < h->cfg.n_modalities; ++m) width += h->mods[m].ni;
+  if (ld < width) fail("row pitch %lld < %lld columns (sum of n_input)", (long long)ld, (long long)width);
+  const int64_t B = h->cfg.batch_size;
+  for (int64_t r = 0; r < B; ++r)
+    if (index_host[r] < 0 || index_host[r] >= n_rows) fail("row index %lld out of range [0, %lld)", (long long)index_host[r], (long long)n_rows);
+  const int slot = (int)(h->indexed_count & 1);
+  cudaStream_t s = h->stream;
+  // 8 B per pair of indices (+ eps when injected) is all that crosses PCIe; the rows are gathered on the device from the
+  // data set uploaded once.  Stream order makes the slot reuse safe (the stage kernel two submits back has run).
+  CUDA_OK(cudaMemcpyAsync(h->idx_in[slot], index_host, (size_t)B * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+  if (eps_host) CUDA_OK(cudaMemcpyAsync(h->eps_in[slot], eps_host, (size_t)B * h->cfg.n_z * 4, cudaMemcpyHostToDevice, s));
+  const float* xd[VAEASSOC_MAX_MODALITIES] = {nullptr, nullptr, nullptr, nullptr};
+  int64_t lds[VAEASSOC_MAX_MODALITIES] = {0, 0, 0, 0};
+  int64_t col = 0;
+  for (int m = 0; m < h->cfg.n_modalities; ++m) { xd[m] = data_dev + col; lds[m] = ld; col += h->mods[m].ni; }
+  stage_inputs(h, xd, lds, eps_host ? h->eps_in[slot] : nullptr, s, -1, true, h->idx_in[slot]);
+  run_step(h, true);
+  CUDA_OK(cudaMemcpyAsync(h->host_cost_ring + (h->submit_count % Ctx::kHostRing), h->last_cost, sizeof(float),
+                          cudaMemcpyDeviceToHost, s));
+  // (no host buffer of the caller is read after this call returns except index_host / eps_host when they are pinned:
+  // same lifetime rule as vaeassoc_submit_host, vaeassoc_upload_wait applies)
+  CUDA_OK(cudaEventRecord(h->ev_upload[h->submit_count % Ctx::kUploadRing], s));
+  h->indexed_count += 1;
   h->submit_count += 1;
   API_END(h)
 }

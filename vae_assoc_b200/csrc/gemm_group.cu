@@ -1031,7 +1031,8 @@ bool tc_supported(int kind, const GemmArgs& a) {
 // epilogue to 1-2 chunks per warp.
 int group_tile_width(int N, int batch_rows) {
   const int row_blocks = (batch_rows + BM - 1) / BM;
-  const int max_bn = row_blocks >= 16 ? 256 : (row_blocks >= 4 ? 128 : 64);
+  int max_bn = row_blocks >= 16 ? 256 : (row_blocks >= 4 ? 128 : 64);
+  if (const char* e = getenv("VAEASSOC_MAX_BN")) { const int v = atoi(e); if (v == 64 || v == 128 || v == 192 || v == 256) max_bn = v; }
   const int tiles_n = (N + max_bn - 1) / max_bn;
   return std::min(max_bn, (((N + tiles_n - 1) / tiles_n) + 63) / 64 * 64);
 }

@@ -112,6 +112,7 @@ struct StageArgs {
   int batch = 0;
   const float* src[4] = {nullptr, nullptr, nullptr, nullptr};
   int64_t src_ld[4] = {0, 0, 0, 0};
+  const int64_t* row_index = nullptr;  // device-resident data set: batch row r is source row row_index[r] (null: r)
   float* dst[4] = {nullptr, nullptr, nullptr, nullptr};
   int64_t dst_ld[4] = {0, 0, 0, 0};
   int n_input[4] = {0, 0, 0, 0};

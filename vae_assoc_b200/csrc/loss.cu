@@ -38,7 +38,8 @@ __global__ void __launch_bounds__(256) stage_kernel(StageArgs a) {
       for (int64_t i = tid; i < total; i += nthreads) {
         const int64_t r = i / q;
         const int c = (int)(i - r * q) * 4;
-        float4 v = __ldg(reinterpret_cast<const float4*>(src + r * sld + c));
+        const int64_t sr = a.row_index ? __ldg(a.row_index + r) : r;
+        float4 v = __ldg(reinterpret_cast<const float4*>(src + sr * sld + c));
         if (a.round_tf32) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
         *reinterpret_cast<float4*>(dst + r * dld + c) = v;
       }
@@ -47,7 +48,8 @@ __global__ void __launch_bounds__(256) stage_kernel(StageArgs a) {
       for (int64_t i = tid; i < total; i += nthreads) {
         const int64_t r = i / ni;
         const int c = (int)(i - r * ni);
-        float v = __ldg(src + r * sld + c);
+        const int64_t sr = a.row_index ? __ldg(a.row_index + r) : r;
+        float v = __ldg(src + sr * sld + c);
         if (a.round_tf32) v = round_tf32(v);
         dst[r * dld + c] = v;
       }

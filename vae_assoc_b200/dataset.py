@@ -63,9 +63,7 @@ class DataSet(object):
             labs = None if self._row_labels is None else self._row_labels[idx]
         return rows, labs
 
-    def next_batch(self, batch_size):
-        """The next `batch_size` examples; a batch that would cross the end starts the next epoch instead, on a freshly
-        shuffled order (the tail of the old epoch is dropped, as in dataset.py:25-38)."""
+    def _advance(self, batch_size):
         n = self._num_examples
         lo, hi = self._cursor, self._cursor + batch_size
         if hi > n:
@@ -75,7 +73,21 @@ class DataSet(object):
             self._order = perm if self._order is None else self._order[perm]
             lo, hi = 0, batch_size
         self._cursor = hi
+        return lo, hi
+
+    def next_batch(self, batch_size):
+        """The next `batch_size` examples; a batch that would cross the end starts the next epoch instead, on a freshly
+        shuffled order (the tail of the old epoch is dropped, as in dataset.py:25-38)."""
+        lo, hi = self._advance(batch_size)
         return self._take(lo, hi)
+
+    def next_indices(self, batch_size):
+        """Row indices (into the immutable row block `_rows`) of the batch `next_batch` would return, with the same
+        cursor / epoch / RNG behaviour -- for the device-resident data-set path, which gathers the rows on the GPU."""
+        lo, hi = self._advance(batch_size)
+        if self._order is None:
+            return np.arange(lo, hi, dtype=np.int64)
+        return np.ascontiguousarray(self._order[lo:hi], dtype=np.int64)
 
 
 def construct_datasets(data, labels=None, shuffle=True, validation_ratio=.1, test_ratio=.1):

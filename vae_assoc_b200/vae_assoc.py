@@ -335,6 +335,29 @@ class AssocVariationalAutoEncoder(object):
         self._check(self._lib.vaeassoc_submit_costs(self._h, int(first_submit), int(n), out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def upload_dataset(self, rows):
+        """Uploads a whole [N, sum n_input] training matrix once (row pitch padded to 16 bytes); returns the device
+        tensor to pass to `partial_fit_indexed`.  The reference keeps the data set in host RAM and copies every batch
+        through feed_dict (vae_assoc.py:541-543,574); here only the batch's row indices cross PCIe."""
+        t = self._torch
+        rows = np.asarray(rows)
+        width = sum(int(na["n_input"]) for na in self.network_architectures)
+        assert rows.ndim == 2 and rows.shape[1] == width, (rows.shape, width)
+        dev = t.zeros((rows.shape[0], (width + 3) // 4 * 4), dtype=t.float32, device=self._dev)
+        dev[:, :width].copy_(t.as_tensor(np.ascontiguousarray(rows, dtype=np.float32)))
+        return dev
+
+    def partial_fit_indexed(self, data_dev, indices, eps=None):
+        """One pipelined train step on rows `indices` (host int64 [batch_size]) of a device-resident data set."""
+        self._bind_stream()
+        idx = np.ascontiguousarray(indices, dtype=np.int64)
+        assert idx.shape == (self.batch_size,)
+        e = None if eps is None else np.ascontiguousarray(eps, dtype=np.float32)
+        self._check(self._lib.vaeassoc_submit_indexed(self._h, C.c_void_p(data_dev.data_ptr()), data_dev.stride(0),
+                                                      data_dev.shape[0], idx.ctypes.data_as(C.c_void_p),
+                                                      None if e is None else e.ctypes.data_as(C.c_void_p)))
+        return int(self._lib.vaeassoc_submit_count(self._h)) - 1
+
     def wait_uploaded(self, submit_index):
         """Blocks until the host->device copies of pipelined submit `submit_index` (the value partial_fit_async returned)
         have completed; after that its (pinned) host buffers may be refilled."""
@@ -582,10 +605,12 @@ class AssocVariationalAutoEncoder(object):
 
 
 def train(data_sets, network_architectures, binary=True, weights=1.0, assoc_lambda=1e-5, learning_rate=0.001,
-          batch_size=100, training_epochs=10, display_step=5, early_stop=False, **model_kwargs):
+          batch_size=100, training_epochs=10, display_step=5, early_stop=False, device_data=False, **model_kwargs):
     """vae_assoc.py:498-583.  Same loop and return value `(model, avg_cost_hist)`; differences that do not change
-    results: batches are uploaded through the pipelined host path and the per-step cost is read back once per
-    epoch from the device-side history instead of synchronising every step (vae_assoc.py:383-386)."""
+    results: batches are uploaded through the pipelined host path and the per-step cost is read back in chunks
+    from a pinned ring instead of synchronising every step (vae_assoc.py:383-386).  `device_data=True` uploads
+    `data_sets.train` ONCE and gathers every batch on the device from the row indices `next_batch` would use
+    (same batches, same RNG consumption): 8 bytes per pair cross PCIe instead of 3 724."""
     vae_assoc = AssocVariationalAutoEncoder(network_architectures, binary, transfer_fct=relu, weights=weights,
                                             assoc_lambda=assoc_lambda, learning_rate=learning_rate,
                                             batch_size=batch_size, **model_kwargs)
@@ -613,6 +638,7 @@ def train(data_sets, network_architectures, binary=True, weights=1.0, assoc_lamb
             np.copyto(staging[slot][i], batch_xs[:, sens_indices[i]:sens_indices[i + 1]], casting="same_kind")
         return staging[slot]
 
+    train_dev = vae_assoc.upload_dataset(data_sets.train._rows) if device_data else None
     submits = 0
     for epoch in range(training_epochs):
         avg_cost = 0.
@@ -641,9 +667,12 @@ def train(data_sets, network_architectures, binary=True, weights=1.0, assoc_lamb
                     avg_cost_hist.append(avg_cost)
                 chunk_first = upto
         for i in range(total_batch):
-            batch_xs, _ = data_sets.train.next_batch(batch_size)
-            slot = submits % n_slots
-            slot_submit[slot] = vae_assoc.partial_fit_async(segment(batch_xs, slot))
+            if train_dev is not None:
+                vae_assoc.partial_fit_indexed(train_dev, data_sets.train.next_indices(batch_size))
+            else:
+                batch_xs, _ = data_sets.train.next_batch(batch_size)
+                slot = submits % n_slots
+                slot_submit[slot] = vae_assoc.partial_fit_async(segment(batch_xs, slot))
             submits += 1
             if submits - chunk_first >= 2048:
                 drain(submits)
