@@ -362,11 +362,14 @@ def main():
         sampler.start()                 # nvidia-smi needs ~1 s to produce its first line: start before the warm-up
     for k in range(args.warmup):
         model.partial_fit_async(pool[k % pool_n])
-    barrier()
     if rank == 0:
+        # BEFORE the barrier: a rank that waited here after it would start its timed loop late and every other rank's
+        # first step (a collective) would wait for it inside THEIR timed region
         t_wait = time.time()
         while not sampler.lines and time.time() - t_wait < 3.0:
             time.sleep(0.05)
+    barrier()
+    if rank == 0:
         sampler.lines.clear()           # keep only samples taken during the timed region
     l0 = model.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -505,7 +508,7 @@ def main():
     line = dict(metric="paired samples/sec/train step", value=value, unit="samples/s", n_gpus=world, steps=args.steps,
                 warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype=args.precision, data="synthetic", config=cfg, graph=not args.no_graph,
-                clocks=clocks, gpu_launches=int(launches),
+                clocks=clocks, gpu_launches=int(launches), dp_mode=model.dp_mode,
                 e2e=dict(value=e2e_value, unit="samples/s", h2d_bytes_per_step=bytes_per_batch, d2h_bytes_per_step=4,
                          ms_per_step=e2e_ms,
                          path="AssocVariationalAutoEncoder.partial_fit_async(numpy pinned) -> vaeassoc_submit_host"),

@@ -197,6 +197,22 @@ int vaeassoc_comm_sync_state(vaeassoc_handle h);
  * the handle's error text is set and a non-zero status is returned (also checked by vaeassoc_stream_sync) */
 int vaeassoc_comm_check(vaeassoc_handle h);
 
+/* ---- peer-memory data-parallel step (one NVSwitch box, <= 8 ranks) ---------------------------------------------------
+ * Replaces `ncclAllReduce` + the replicated Adam of the schedule above by ONE kernel per step (csrc/peer_adam.cu):
+ * reduce-scatter of the flat gradient buffers read straight from the peers' HBM over NVLink, Adam on the owned shard,
+ * all-gather of the updated parameters (+ tf32 shadow) by peer stores; cross-GPU arrival words instead of a host or
+ * NCCL barrier.  Set-up: every rank exports one blob (cudaIpc handle of the block holding its flat buffers), the host
+ * side all-gathers the blobs (torch.distributed, vae_assoc.py: init_data_parallel) and every rank attaches ALL of them
+ * (rank order), then the ranks barrier once before the first step.  Needs vaeassoc_comm_init first (rank / world; NCCL
+ * still serves vaeassoc_comm_sync_state, evaluate_cost and compute_gradients).  Adam's m / v become sharded: reads
+ * through vaeassoc_tensor_get / vaeassoc_save pull the peers' shards first.  vaeassoc_peer_detach (or comm_destroy)
+ * must be preceded by a barrier of the ranks: a peer may not touch a detached rank's memory. */
+#define VAEASSOC_PEER_BLOB_BYTES 128
+int vaeassoc_peer_export(vaeassoc_handle h, void* blob /* VAEASSOC_PEER_BLOB_BYTES */);
+int vaeassoc_peer_attach(vaeassoc_handle h, const void* all_blobs /* world x VAEASSOC_PEER_BLOB_BYTES, rank order */);
+int vaeassoc_peer_detach(vaeassoc_handle h);
+int vaeassoc_peer_active(vaeassoc_handle h);      /* 1 while the peer-memory step is in use */
+
 /* ---- checkpoints: tf.train.Saver.save / .restore over ALL variables incl. the Adam slots (vae_assoc.py:70,427-463) --
  * One self-describing binary file ("VAEASSOC" magic, tensor table with the TF-style names, parameters, both Adam
  * slots, step count).  vaeassoc_load matches tensors by NAME and shape and fails (non-zero, handle unchanged) on a

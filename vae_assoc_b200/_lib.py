@@ -7,6 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # VAEASSOC_LIB selects a build-time variant of the library (vae_assoc_b200/build.py: build_variant); default = the product
 LIB_PATH = os.environ.get("VAEASSOC_LIB") or os.path.join(HERE, "libvaeassoc.so")
 MAX_MODALITIES = 4
+PEER_BLOB_BYTES = 128
 ABI_VERSION = 2
 
 RELU, SOFTPLUS = 0, 1
@@ -84,6 +85,10 @@ SIGNATURES = {
     "vaeassoc_comm_destroy": (C.c_int, [Handle]),
     "vaeassoc_comm_sync_state": (C.c_int, [Handle]),
     "vaeassoc_comm_check": (C.c_int, [Handle]),
+    "vaeassoc_peer_export": (C.c_int, [Handle, C.c_void_p]),
+    "vaeassoc_peer_attach": (C.c_int, [Handle, C.c_void_p]),
+    "vaeassoc_peer_detach": (C.c_int, [Handle]),
+    "vaeassoc_peer_active": (C.c_int, [Handle]),
     "vaeassoc_save": (C.c_int, [Handle, C.c_char_p]),
     "vaeassoc_load": (C.c_int, [Handle, C.c_char_p]),
     "vaeassoc_launch_count": (C.c_int64, [Handle]),

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libvaeassoc.so")
-SOURCES = ["api.cu", "gemm_simt.cu", "gemm_skinny.cu", "gemm_group.cu", "conv.cu", "loss.cu", "adam.cu", "synth.cu"]
+SOURCES = ["api.cu", "gemm_simt.cu", "gemm_skinny.cu", "gemm_group.cu", "conv.cu", "loss.cu", "adam.cu", "peer_adam.cu", "synth.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr",
               "-Xptxas", "-v"]

@@ -1,6 +1,7 @@
 // libvaeassoc C-ABI implementation: flat parameter layout, op schedule of the train step, CUDA-graph replay,
 // NCCL data parallelism.  See include/vaeassoc.h for the contract and the reference call sites each entry
 // point replaces.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
@@ -189,6 +190,18 @@ struct vaeassoc_ctx {
   void* comm = nullptr;
   int rank = 0, world = 1;
   uint64_t comm_calls = 0;
+  // peer-memory data-parallel step (peer_adam.cu): the arena of every rank mapped through cudaIpc
+  float* arena = nullptr;
+  int64_t arena_floats = 0;
+  struct Peer {
+    bool on = false;
+    void* mapped[kMaxPeers] = {};     // what cudaIpcOpenMemHandle returned for rank r (block base)
+    float* base[kMaxPeers] = {};      // arena of rank r in THIS process' address space (own rank: c->arena)
+    uint32_t* flags = nullptr;        // local arrival words (inside the arena)
+    cudaGraphExec_t graph = nullptr;  // a1 + a2 + peer_adam: the whole data-parallel step as one graph
+    int graph_nodes = 0;
+    bool slots_stale = false;         // m / v of the shards owned by peers are behind (refreshed on demand)
+  } peer;
 
   template <typename T>
   T* dalloc(int64_t n, bool zero = true) {
@@ -218,6 +231,12 @@ struct vaeassoc_ctx {
 namespace {
 
 using Ctx = vaeassoc_ctx;
+void peer_detach(Ctx* c);
+void refresh_peer_slots(Ctx* c);
+
+// the task queue hands out EVERY task (first one included) whenever a kernel that waits on a peer GPU may hold SMs next to
+// the tile kernel: the NCCL schedules.  The peer-memory step runs alone on the stream, so it keeps the static first task.
+bool dyn_first(const Ctx* c) { return c->force_dynamic || (c->comm != nullptr && !c->peer.on); }
 
 int64_t global_batch(const Ctx* c) { return c->cfg.global_batch > 0 ? c->cfg.global_batch : c->cfg.batch_size; }
 int fwd_act(const Ctx* c) { return c->cfg.transfer_fct == VAEASSOC_SOFTPLUS ? ACT_SOFTPLUS : ACT_RELU; }
@@ -388,11 +407,21 @@ void build_layout(Ctx* c) {
 void alloc_buffers(Ctx* c) {
   const int64_t B = c->cfg.batch_size;
   const int nz = c->cfg.n_z;
-  c->p = c->dalloc<float>(c->n_flat);
-  c->g = c->dalloc<float>(c->n_flat + 32);
-  c->m = c->dalloc<float>(c->n_flat);
-  c->v = c->dalloc<float>(c->n_flat);
-  c->p_tf32 = c->dalloc<float>(c->n_flat);
+  {
+    // ONE allocation ("arena") holds the flat buffers and the peer arrival words, so that a single cudaIpc handle maps
+    // everything a peer rank touches in the data-parallel step (peer_adam.cu).  Every sub-buffer starts on a 256-byte
+    // boundary and is followed by >= 256 bytes of slack (the 3-D tensor maps of MN-major operands may read 124 B past
+    // the last row, gemm_group.cu).
+    const int64_t slot = round_up(c->n_flat + 32, 64) + 64;     // floats per flat buffer incl. slack
+    c->arena_floats = 5 * slot + 64;
+    c->arena = c->dalloc<float>(c->arena_floats);
+    c->p = c->arena;
+    c->g = c->arena + slot;
+    c->m = c->arena + 2 * slot;
+    c->v = c->arena + 3 * slot;
+    c->p_tf32 = c->arena + 4 * slot;
+    c->peer.flags = reinterpret_cast<uint32_t*>(c->arena + 5 * slot);   // 2 x kMaxPeers arrival words, then sync[2]
+  }
   {
     // row-block counters: 8 activation / gradient tensors per modality x row blocks of 256; then the launch sites
     const int64_t rb = (B + 255) / 256;
@@ -494,12 +523,12 @@ Op make_gemm(Ctx* c, const char* name, int m, int kind, GemmArgs a, int64_t w_of
       op.launches = 2;
       float* cws = c->op_ws(colsum_ws_floats(b.K, b.N));
       op.run = [cc, site, b, cws](cudaStream_t s) {
-        group_launch(cc->gplan, site, cc->gsync + cc->n_ctr + 2 * site, 0, 0, cc->comm != nullptr || cc->force_dynamic, s);
+        group_launch(cc->gplan, site, cc->gsync + cc->n_ctr + 2 * site, 0, 0, dyn_first(cc), s);
         launch_colsum(b.B, b.ldb, b.K, b.N, b.bias_grad, cws, s);
       };
     } else {
       op.run = [cc, site](cudaStream_t s) {
-        group_launch(cc->gplan, site, cc->gsync + cc->n_ctr + 2 * site, 0, 0, cc->comm != nullptr || cc->force_dynamic, s);
+        group_launch(cc->gplan, site, cc->gsync + cc->n_ctr + 2 * site, 0, 0, dyn_first(cc), s);
       };
     }
     return op;
@@ -547,7 +576,7 @@ GemmArgs gemm_wgrad(int B, int K, int N, const float* X, int64_t ldx, const floa
 }
 
 void destroy_graphs(Ctx* c) {
-  for (cudaGraphExec_t* g : {&c->graph_train, &c->graph_grad, &c->graph_a1, &c->graph_a2, &c->graph_adam}) {
+  for (cudaGraphExec_t* g : {&c->graph_train, &c->graph_grad, &c->graph_a1, &c->graph_a2, &c->graph_adam, &c->peer.graph}) {
     if (*g) cudaGraphExecDestroy(*g);
     *g = nullptr;
   }
@@ -928,7 +957,7 @@ void build_segments(Ctx* c) {
 }
 
 void launch_seg(Ctx* c, const Ctx::Seg& sg, cudaStream_t s) {
-  group_launch(c->gplan, sg.site, c->gsync + c->n_ctr + 2 * sg.site, sg.reset_first, sg.reset_count, c->comm != nullptr || c->force_dynamic, s);
+  group_launch(c->gplan, sg.site, c->gsync + c->n_ctr + 2 * sg.site, sg.reset_first, sg.reset_count, dyn_first(c), s);
   c->launches += 1;
 }
 
@@ -1076,6 +1105,30 @@ void enqueue_adam(Ctx* c, cudaStream_t s) {
   launch_adam(adam_args(c), s);
   c->launches += 1;
 }
+// rank r owns float4 indices [lo, hi) of the flat buffers: equal shards, multiples of 8 float4 (128 bytes)
+void peer_shard(const Ctx* c, int r, int64_t* lo, int64_t* hi) {
+  const int64_t n4 = c->n_flat >> 2;
+  const int64_t per = round_up((n4 + c->world - 1) / c->world, 8);
+  *lo = std::min<int64_t>(n4, per * r);
+  *hi = std::min<int64_t>(n4, per * (r + 1));
+}
+void enqueue_peer_adam(Ctx* c, cudaStream_t s) {
+  PeerAdamArgs a;
+  a.adam = adam_args(c);
+  a.world = c->world; a.rank = c->rank;
+  const bool shadow = a.adam.p_tf32 != nullptr;
+  for (int r = 0; r < c->world; ++r) {
+    float* b = c->peer.base[r];
+    a.p_peer[r] = b + (c->p - c->arena);
+    a.g_peer[r] = b + (c->g - c->arena);
+    a.ptf_peer[r] = shadow ? b + (c->p_tf32 - c->arena) : nullptr;
+    a.flag_peer[r] = reinterpret_cast<uint32_t*>(b + (reinterpret_cast<float*>(c->peer.flags) - c->arena));
+  }
+  a.sync = c->peer.flags + 2 * kMaxPeers;
+  peer_shard(c, c->rank, &a.shard_lo, &a.shard_hi);
+  launch_peer_adam(a, s);
+  c->launches += 1;
+}
 void allreduce(Ctx* c, float* buf, int64_t count, cudaStream_t s);
 void enqueue_forward_loss(Ctx* c, cudaStream_t s) {   // evaluate_cost: no gradients
   run_ops(c, c->ops_fwd_enc, s);
@@ -1193,6 +1246,24 @@ void run_step(Ctx* c, bool with_adam) {
   refresh_shadow(c, s);
   ensure_graphs(c);
   const bool dp = c->comm != nullptr && c->world > 1;
+  if (dp && c->peer.on && with_adam) {
+    // peer-memory step: forward, backward and ONE kernel that reduce-scatters the gradients over NVLink, runs Adam on
+    // the owned shard and all-gathers the parameters (peer_adam.cu) -- no NCCL, one graph launch per step
+    c->peer.slots_stale = true;
+    if (c->cfg.use_graph) {
+      if (!c->peer.graph)
+        c->peer.graph_nodes = capture(c, &c->peer.graph, [&](cudaStream_t cs) {
+          enqueue_a1(c, cs); enqueue_a2(c, cs, 1); enqueue_peer_adam(c, cs);
+        });
+      CUDA_OK(cudaGraphLaunch(c->peer.graph, s));
+      c->launches += c->peer.graph_nodes;
+    } else {
+      enqueue_a1(c, s);
+      enqueue_a2(c, s, 1);
+      enqueue_peer_adam(c, s);
+    }
+    return;
+  }
   if (!dp) {
     if (c->cfg.use_graph) {
       CUDA_OK(cudaGraphLaunch(with_adam ? c->graph_train : c->graph_grad, s));
@@ -1360,6 +1431,7 @@ int vaeassoc_destroy(vaeassoc_handle h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
+  peer_detach(h);
   if (h->comm) { g_nccl.CommDestroy(h->comm); h->comm = nullptr; }
   destroy_graphs(h);
   group_destroy(h->gplan);
@@ -1467,6 +1539,7 @@ int vaeassoc_tensor_get(vaeassoc_handle h, int which, int i, float* dst_host) {
   if (i < 0 || i >= (int)h->tensors.size() || !dst_host) fail("tensor index %d out of range", i);
   const vaeassoc_tensor_info& t = h->tensors[i];
   CUDA_OK(cudaStreamSynchronize(h->stream));
+  if (which == VAEASSOC_ADAM_M || which == VAEASSOC_ADAM_V) refresh_peer_slots(h);
   CUDA_OK(cudaMemcpy2D(dst_host, (size_t)t.cols * 4, base + t.offset, (size_t)t.ld * 4, (size_t)t.cols * 4, (size_t)t.rows,
                        cudaMemcpyDeviceToHost));
   API_END(h)
@@ -1801,6 +1874,8 @@ int vaeassoc_comm_destroy(vaeassoc_handle h) {
   if (h->comm) {
     CUDA_OK(cudaStreamSynchronize(h->stream));
     CUDA_OK(cudaStreamSynchronize(h->comm_stream));
+    refresh_peer_slots(h);
+    peer_detach(h);
     g_nccl.CommDestroy(h->comm);
     h->comm = nullptr; h->world = 1; h->rank = 0;
     destroy_graphs(h);
@@ -1822,6 +1897,7 @@ int vaeassoc_comm_sync_state(vaeassoc_handle h) {
     bc(h->step_dev, 1, kNcclInt64);
     h->launches += 4;
     h->shadow_dirty = true;
+    h->peer.slots_stale = false;
     CUDA_OK(cudaStreamSynchronize(s));
     comm_check(h);
   }
@@ -1853,6 +1929,124 @@ int vaeassoc_probe_mask(vaeassoc_handle h, int layer, int modality, uint32_t* ds
   API_END(h)
 }
 
+}  // extern "C"
+
+// ---- peer-memory data-parallel step (peer_adam.cu) ------------------------------------------------------------------
+namespace {
+struct PeerBlob {                 // what a rank publishes: VAEASSOC_PEER_BLOB_BYTES
+  cudaIpcMemHandle_t handle;      // 64 bytes: the cudaMalloc block that contains the arena
+  int64_t offset;                 // arena start inside that block (small arenas are sub-allocated)
+  int64_t arena_floats;
+  int64_t n_flat;
+  int32_t device, pad;
+};
+static_assert(sizeof(PeerBlob) <= VAEASSOC_PEER_BLOB_BYTES, "peer blob must fit the ABI constant");
+
+void peer_detach(Ctx* c) {
+  if (!c->peer.on) return;
+  cudaStreamSynchronize(c->stream);
+  if (c->peer.graph) { cudaGraphExecDestroy(c->peer.graph); c->peer.graph = nullptr; }
+  for (int r = 0; r < kMaxPeers; ++r) {
+    if (c->peer.base[r] && r != c->rank) cudaIpcCloseMemHandle(c->peer.mapped[r]);
+    c->peer.base[r] = nullptr; c->peer.mapped[r] = nullptr;
+  }
+  c->peer.on = false;
+}
+
+// m / v of the shards owned by the peers, pulled through the peer mapping (one-sided: the caller's stream is idle and
+// the ranks step in lockstep, so no peer is inside an update)
+void refresh_peer_slots(Ctx* c) {
+  if (!c->peer.on || !c->peer.slots_stale) return;
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  for (int r = 0; r < c->world; ++r) {
+    if (r == c->rank) continue;
+    int64_t lo, hi;
+    peer_shard(c, r, &lo, &hi);
+    if (hi <= lo) continue;
+    const size_t bytes = (size_t)(hi - lo) * 16;
+    for (float* buf : {c->m, c->v})
+      CUDA_OK(cudaMemcpy(buf + 4 * lo, c->peer.base[r] + (buf - c->arena) + 4 * lo, bytes, cudaMemcpyDeviceToDevice));
+  }
+  c->peer.slots_stale = false;
+}
+}  // namespace
+
+extern "C" {
+
+int vaeassoc_peer_export(vaeassoc_handle h, void* blob) {
+  API_BEGIN(h)
+  if (!blob) fail("null blob");
+  PeerBlob b;
+  memset(&b, 0, sizeof b);
+  CUDA_OK(cudaIpcGetMemHandle(&b.handle, h->arena));
+  // the handle names the whole cudaMalloc block: find the arena's offset inside it
+  typedef CUresult (*RangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
+  void* fp = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fp, cudaEnableDefault, &qres) != cudaSuccess || !fp)
+    fail("cuMemGetAddressRange entry point not available");
+  CUdeviceptr base = 0; size_t size = 0;
+  if (reinterpret_cast<RangeFn>(fp)(&base, &size, (CUdeviceptr)h->arena) != CUDA_SUCCESS) fail("cuMemGetAddressRange failed");
+  b.offset = (int64_t)((CUdeviceptr)h->arena - base);
+  b.arena_floats = h->arena_floats; b.n_flat = h->n_flat; b.device = h->device;
+  memset(blob, 0, VAEASSOC_PEER_BLOB_BYTES);
+  memcpy(blob, &b, sizeof b);
+  API_END(h)
+}
+
+int vaeassoc_peer_attach(vaeassoc_handle h, const void* all_blobs) {
+  API_BEGIN(h)
+  if (!h->comm || h->world < 2) fail("vaeassoc_peer_attach needs an initialised communicator with world >= 2");
+  if (h->world > kMaxPeers) fail("the peer-memory step serves at most %d ranks (one NVSwitch box)", kMaxPeers);
+  if (!all_blobs) fail("null blobs");
+  peer_detach(h);
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  const char* src = reinterpret_cast<const char*>(all_blobs);
+  try {
+    for (int r = 0; r < h->world; ++r) {
+      PeerBlob b;
+      memcpy(&b, src + (size_t)r * VAEASSOC_PEER_BLOB_BYTES, sizeof b);
+      if (b.arena_floats != h->arena_floats || b.n_flat != h->n_flat)
+        fail("rank %d has a different parameter layout (%lld floats, ours %lld)", r, (long long)b.n_flat, (long long)h->n_flat);
+      if (r == h->rank) { h->peer.base[r] = h->arena; continue; }
+      int can = 0;
+      CUDA_OK(cudaDeviceCanAccessPeer(&can, h->device, b.device));
+      if (!can) fail("device %d cannot access device %d through peer memory", h->device, b.device);
+      void* mapped = nullptr;
+      CUDA_OK(cudaIpcOpenMemHandle(&mapped, b.handle, cudaIpcMemLazyEnablePeerAccess));
+      h->peer.mapped[r] = mapped;
+      h->peer.base[r] = reinterpret_cast<float*>(reinterpret_cast<char*>(mapped) + b.offset);
+    }
+  } catch (...) {
+    for (int r = 0; r < kMaxPeers; ++r) {
+      if (h->peer.mapped[r]) cudaIpcCloseMemHandle(h->peer.mapped[r]);
+      h->peer.mapped[r] = nullptr; h->peer.base[r] = nullptr;
+    }
+    throw;
+  }
+  // arrival words and epoch start from zero on every rank (the caller barriers between attach and the first step)
+  CUDA_OK(cudaMemset(h->peer.flags, 0, (2 * kMaxPeers + 2) * sizeof(uint32_t)));
+  CUDA_OK(cudaDeviceSynchronize());
+  h->peer.on = true;
+  h->peer.slots_stale = false;
+  destroy_graphs(h);       // the captured launches bake in the task-queue mode
+  API_END(h)
+}
+
+int vaeassoc_peer_detach(vaeassoc_handle h) {
+  API_BEGIN(h)
+  refresh_peer_slots(h);
+  peer_detach(h);
+  destroy_graphs(h);
+  API_END(h)
+}
+
+int vaeassoc_peer_active(vaeassoc_handle h) { return (h && h->peer.on) ? 1 : 0; }
+
+}  // extern "C"
+
+extern "C" {
+
 // ---- checkpoint file: "VAEASSOC" | u32 version | u32 n_tensors | i64 step | per tensor { name[48], role[16], i32 ndim,
 // i32 shape[4], i64 count, f32 p[count], f32 m[count], f32 v[count] } -- dense logical tensors in the reference's
 // tf.Variable creation order (what tf.train.Saver would write: every variable plus its two Adam slots, vae_assoc.py:70)
@@ -1877,6 +2071,7 @@ int vaeassoc_save(vaeassoc_handle h, const char* path) {
   API_BEGIN(h)
   if (!path || !path[0]) fail("empty checkpoint path");
   CUDA_OK(cudaStreamSynchronize(h->stream));
+  refresh_peer_slots(h);
   File fl; fl.f = fopen(path, "wb");
   if (!fl.f) fail("cannot open %s for writing", path);
   const uint32_t version = 1, n = (uint32_t)h->tensors.size();
@@ -1965,7 +2160,7 @@ int vaeassoc_debug_gemm(vaeassoc_handle h, int kind, int use_tc, int M, int N, i
                          kind == KIND_TN ? std::min(per * 8, kb - r0 * 8) : kb, -1, 0, 0, -1, 0, -1);
     group_set_counters(plan, h->gsync, h->n_ctr);
     if (!group_end(plan, err, sizeof err) || !group_upload(plan, err, sizeof err)) { group_destroy(plan); fail("%s", err); }
-    group_launch(plan, dsite, h->gsync + h->n_ctr + 2 * (h->max_sites - 1), 0, 0, h->comm != nullptr || h->force_dynamic, h->stream);
+    group_launch(plan, dsite, h->gsync + h->n_ctr + 2 * (h->max_sites - 1), 0, 0, dyn_first(h), h->stream);
     float* cws = nullptr;
     if (kind == KIND_TN && bias_grad) {
       const int64_t nws = colsum_ws_floats(K, N);

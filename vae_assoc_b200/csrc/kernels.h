@@ -201,6 +201,22 @@ struct AdamArgs {
   float* last_cost = nullptr;
 };
 void launch_adam(const AdamArgs& a, cudaStream_t s);
+
+// Data-parallel step over NVLink peer memory (peer_adam.cu): reduce-scatter of the flat gradient buffers + Adam on the
+// owned shard + all-gather of the updated parameters, ONE kernel, no NCCL on the step.  Rank r owns float4 indices
+// [shard_lo, shard_hi) of the flat buffers; every pointer table is indexed by rank (entry `rank` = the local buffer).
+constexpr int kMaxPeers = 8;
+struct PeerAdamArgs {
+  AdamArgs adam;                     // local p / m / v / p_tf32, hyper-parameters, cost publication
+  int world = 1, rank = 0;
+  const float* g_peer[kMaxPeers] = {};   // flat gradient buffer of every rank (n + 32 floats; [n] = cost slot)
+  float* p_peer[kMaxPeers] = {};
+  float* ptf_peer[kMaxPeers] = {};       // tf32 shadow of every rank (entries null in fp32 mode)
+  uint32_t* flag_peer[kMaxPeers] = {};   // [2][kMaxPeers] arrival words of every rank: [phase][source rank] = epoch
+  uint32_t* sync = nullptr;              // local: [0] epoch of the last completed step, [1] CTAs done
+  int64_t shard_lo = 0, shard_hi = 0;    // float4 units
+};
+void launch_peer_adam(const PeerAdamArgs& a, cudaStream_t s);
 void launch_round_copy(const float* src, float* dst, int64_t n, cudaStream_t s);   // dst = round_tf32(src)
 void launch_publish_cost(const float* cost_slot, float* last_cost, cudaStream_t s);
 

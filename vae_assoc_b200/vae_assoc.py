@@ -138,6 +138,11 @@ class AssocVariationalAutoEncoder(object):
 
     def close(self):
         if getattr(self, "_h", None):
+            if getattr(self, "_peer", False):
+                try:
+                    self.detach_peers()
+                except Exception:
+                    pass
             self._lib.vaeassoc_destroy(self._h)
             self._h = None
 
@@ -542,8 +547,11 @@ class AssocVariationalAutoEncoder(object):
         return out
 
     # ---- data parallelism ----------------------------------------------------------------------------
-    def init_data_parallel(self):
-        """Join the NCCL communicator of the current torch.distributed job (one process per GPU)."""
+    def init_data_parallel(self, peer=None):
+        """Join the data-parallel job of the current torch.distributed process group (one process per GPU): an NCCL
+        communicator for the set-up / evaluation collectives and, with `peer` (default: on, VAEASSOC_DP_PEER=0 turns it
+        off), the NVLink peer-memory train step -- one kernel that reduce-scatters the gradients, runs Adam on the owned
+        shard and all-gathers the parameters (csrc/peer_adam.cu) -- in place of ncclAllReduce + replicated Adam."""
         import torch.distributed as dist
         world, rank = dist.get_world_size(), dist.get_rank()
         path = L.nccl_library_path().encode()
@@ -558,6 +566,48 @@ class AssocVariationalAutoEncoder(object):
         self._world = world
         # replicas must start identical (the all-reduce only averages gradients): rank 0's parameters, Adam slots and step
         self.sync_replicas()
+        if peer is None:
+            peer = os.environ.get("VAEASSOC_DP_PEER", "1") != "0"
+        self._peer = False
+        if peer and 2 <= world <= 8:
+            self._attach_peers(dist, world)
+
+    def _attach_peers(self, dist, world):
+        """Peer-memory data-parallel step (csrc/peer_adam.cu): exchange the cudaIpc blobs of the flat buffers and map
+        every rank's.  All ranks end up in the same mode: if any rank cannot map a peer (no NVLink / P2P, IPC refused)
+        every rank stays on the NCCL all-reduce schedule."""
+        blob = (C.c_ubyte * L.PEER_BLOB_BYTES)()
+        ok = self._lib.vaeassoc_peer_export(self._h, blob) == 0
+        blobs = [None] * world
+        dist.all_gather_object(blobs, bytes(blob) if ok else None)
+        if ok and all(b is not None for b in blobs):
+            allb = (C.c_ubyte * (L.PEER_BLOB_BYTES * world)).from_buffer_copy(b"".join(blobs))
+            ok = self._lib.vaeassoc_peer_attach(self._h, allb) == 0
+        else:
+            ok = False
+        self._peer_error = None if ok else self._lib.vaeassoc_last_error(self._h).decode()
+        oks = [None] * world
+        dist.all_gather_object(oks, bool(ok))          # also the barrier between attach and the first step
+        if all(oks):
+            self._peer = True
+        elif ok:
+            self._check(self._lib.vaeassoc_peer_detach(self._h))
+
+    def detach_peers(self):
+        """Back to the NCCL all-reduce schedule (collective: every rank calls it; no peer may still be stepping)."""
+        if getattr(self, "_peer", False):
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                self.synchronize()
+                dist.barrier()
+            self._check(self._lib.vaeassoc_peer_detach(self._h))
+            self._peer = False
+
+    @property
+    def dp_mode(self):
+        if getattr(self, "_world", 1) < 2:
+            return "single"
+        return "peer" if self._lib.vaeassoc_peer_active(self._h) else "nccl"
 
     def sync_replicas(self):
         """Broadcast rank 0's parameters / Adam state to every rank (call on ALL ranks, e.g. after a rank-0 restore_model)."""
