@@ -14,6 +14,6 @@ for w in which:
         print("  prob %2d n %3d nkb %3d | prod start %.1f..%.1f | mma end max %.1f | epi dur avg %.2f | epi end max %.1f | run cyc/kb %.0f | ld0 +%.0f cyc chunk0 +%.0f cyc loop +%.2f us | math +%.0f mask +%.0f wait +%.0f sts +%.0f cyc" % (
             p, len(ts), ts[0][4], min(t[7] for t in ts), max(t[7] for t in ts), max(t[9] for t in ts),
             sum(t[12] - t[11] for t in ts) / len(ts), max(t[12] for t in ts),
-            sum((t[9] - max(t[7], t[8])) * 1965 / t[4] for t in ts) / len(ts),
+            sum((t[9] - max(t[7], t[8])) * 1965 / max(t[4], 1) for t in ts) / len(ts),
             sum(t[13] for t in ts) / len(ts), sum(t[14] for t in ts) / len(ts), sum(t[15] - t[11] for t in ts) / len(ts),
             *[sum(t[k] for t in ts) / len(ts) for k in (16, 17, 18, 19)]))

@@ -355,6 +355,52 @@ def test_dynamic_task_queue_mode_matches(va, monkeypatch):
     np.testing.assert_allclose(costs["dynamic"], costs["static"], rtol=2e-5)
 
 
+@pytest.mark.parametrize("batch", [100, 700, 2048])
+def test_two_launch_schedule_matches_four_launch(va, monkeypatch, batch):
+    """Default tf32 schedule: the latent stages (reparameterisation, KL terms and their gradients, the bias gradient of
+    the heads) run as elementwise TASKS of the persistent tile kernel, so the step is two launches of it (forward,
+    backward).  VAEASSOC_NO_ELT=1 selects the four-segment schedule with the stand-alone latent kernels (same device
+    code: csrc/latent.cuh).  Both must agree to summation order: every gradient of a first step, then the costs of 5 training steps.
+    Batch 700 = three row blocks of 256, the last one ragged."""
+    archs = vo.reference_archs(4)
+    X = [x.astype(np.float32) for x in synth.synth_batch(archs, [True, False], 0, 1, 0, batch)]
+    eps = philox.eps_rows(3, 0, 0, batch, 4).astype(np.float32)
+    out = {}
+    for mode in ("two", "four"):
+        if mode == "four":
+            monkeypatch.setenv("VAEASSOC_NO_ELT", "1")
+        model = va.AssocVariationalAutoEncoder(archs, [True, False], transfer_fct="relu", weights=[50, 1], assoc_lambda=8,
+                                               learning_rate=1e-3, batch_size=batch, precision="tf32", seed=0, eps_seed=3)
+        c = float(model.compute_gradients(X, eps))          # fresh model: identical parameters in both schedules
+        grads, lat, dzm = model.get_grads(), model.vae_latent_losses, model.d_z_means
+        n0 = model.launch_count()
+        model.partial_fit_async([model._torch.as_tensor(x).cuda() for x in X])
+        launches = model.launch_count() - n0
+        costs = [float(model.partial_fit(X, eps)) for _ in range(4)]
+        out[mode] = (costs, c, grads, lat, dzm, launches)
+        model.close()
+    np.testing.assert_allclose(out["two"][0], out["four"][0], rtol=2e-5)
+    assert abs(out["two"][1] - out["four"][1]) <= 2e-5 * abs(out["four"][1])
+    for a, b, n in zip(out["two"][2], out["four"][2], range(100)):
+        assert rel_l2(a, b) < 2e-5, (n, rel_l2(a, b))       # same masks (the forward is bit-identical): order noise only
+    for m in range(2):
+        assert rel(out["two"][3][m], out["four"][3][m]) < 1e-5
+        assert rel(out["two"][4][m], out["four"][4][m]) < 1e-4
+    assert out["two"][5] < out["four"][5], (out["two"][5], out["four"][5])     # fewer launches per step
+
+
+@pytest.mark.parametrize("f", ["relu", "softplus"])
+def test_gradient_step_ragged_row_blocks(va, f):
+    """B = 700 (two full 256-row blocks + a ragged one) through the two-launch tf32 schedule vs the operand-rounding
+    oracle: cost, probes and all 28 gradients (the elementwise tasks mask rows >= B, their partial sums are per warp)."""
+    archs = vo.reference_archs(4)
+    batch = 700
+    model, oracle = make_pair(va, archs, batch, f, "tf32", seed=7)
+    X, eps = inputs(archs, batch, seed=7)
+    check_step(model, oracle, X, eps, tol=5e-4, grad_tol=5e-2 if f == "relu" else None)
+    model.close()
+
+
 # ---------------------------------------------------------------------------------------------------------
 # round 2: determinism, mask-conditioned tensor-core gradients, checkpoint formats, contract entries
 # ---------------------------------------------------------------------------------------------------------

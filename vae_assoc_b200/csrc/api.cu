@@ -178,6 +178,14 @@ struct vaeassoc_ctx {
   struct Seg { int site = 0, reset_first = 0, reset_count = 0; };
   Seg seg_enc, seg_dec, seg_bwd_dec, seg_bwd_enc;     // fused segments of the train step (dense modalities, tf32)
   bool fused = false;
+  // two-launch form: the latent stages run as elementwise tasks INSIDE the tile kernel, so that encoder + latent +
+  // decoder forward are one launch and decoder + latent + encoder backward another (build_segments)
+  Seg seg_fwd, seg_bwd;
+  bool elt_built = false;
+  int lat_blocks_elt = 0;
+  bool lat_mode_elt = false;          // which latent kernel wrote lat_partials last (layout of the block partials)
+  LatentArgs lat_fwd_args;
+  LatentBwdArgs lat_bwd_args;
   bool masks_in_use[VAEASSOC_MAX_MODALITIES] = {false, false, false, false};   // relu sign masks written / read this schedule
   int dp_single = -1;                                 // VAEASSOC_DP_SINGLE=0/1; default (-1): one all-reduce per step iff fused and world > 4
   bool force_dynamic = false;                         // VAEASSOC_DYNAMIC_FIRST: the data-parallel task-queue mode on one GPU (tests)
@@ -423,9 +431,9 @@ void alloc_buffers(Ctx* c) {
     c->peer.flags = reinterpret_cast<uint32_t*>(c->arena + 5 * slot);   // 2 x kMaxPeers arrival words, then sync[2]
   }
   {
-    // row-block counters: 8 activation / gradient tensors per modality x row blocks of 256; then the launch sites
+    // row-block counters: 12 activation / gradient tensors per modality x row blocks of 256; then the launch sites
     const int64_t rb = (B + 255) / 256;
-    c->n_ctr = (int)(c->cfg.n_modalities * 8 * rb);
+    c->n_ctr = (int)(c->cfg.n_modalities * 12 * rb);
     c->max_sites = 1024;
     c->gsync = c->dalloc<uint32_t>(c->n_ctr + 2 * c->max_sites);
   }
@@ -830,6 +838,7 @@ void build_ops(Ctx* c) {
     op.bytes = 4.0 * B * nz * (1 + M * 5);
     op.run = [a](cudaStream_t s) { launch_latent_fwd(a, s); };
     c->ops_latent_fwd.push_back(op);
+    c->lat_fwd_args = a;
   }
   {
     Op op; op.name = "latent_bwd";
@@ -842,6 +851,7 @@ void build_ops(Ctx* c) {
     op.bytes = 4.0 * B * nz * (1 + M * 6);
     op.run = [a](cudaStream_t s) { launch_latent_bwd(a, s); };
     c->ops_latent_bwd.push_back(op);
+    c->lat_bwd_args = a;
   }
   build_segments(c);
 }
@@ -850,7 +860,9 @@ void build_ops(Ctx* c) {
 // The layers of a segment become ONE launch of the persistent tile kernel: tasks in dependency order, linked by
 // row-block counters (tensor T of modality m over rows [256 rb, +256) is complete when its counter reaches
 // 16 x (N-tiles of the producing layer)).  Counter index = (T * n_modalities + m) * RB + rb.
-enum { T_H1 = 0, T_H2, T_G1, T_G2, T_DG2, T_DG1, T_DH2, T_DH1 };
+// (forward tensors first, then backward ones: a launch rewinds one contiguous range of counters when it leaves)
+enum { T_H1 = 0, T_H2, T_HD, T_Z, T_G1, T_G2, T_DG2, T_DG1, T_DZ, T_DHD, T_DH2, T_DH1, T_COUNT };
+static_assert(T_COUNT == 12, "alloc_buffers sizes the counter array for 12 tensors per modality");
 
 void build_segments(Ctx* c) {
   const int M = c->cfg.n_modalities;
@@ -870,8 +882,9 @@ void build_segments(Ctx* c) {
     GroupPlan* g = c->gplan;
     auto ctr = [&](int m, int T, int rb) { return (T * M + m) * RB + rb; };
     // tiles of a row-wise layer (NN / NT): one task per (row block, column tile)
-    auto add_rowwise = [&](const Op& op, int m, int inT, int in_tn, int outT, float* colsum) -> int {
+    auto add_rowwise = [&](const Op& op, int m, int inT, int in_tn, int outT, float* colsum, int in_m = -1) -> int {
       if (nodeps) { inT = -1; outT = -1; }
+      if (in_m < 0) in_m = m;
       GemmArgs a = op.gargs;
       a.bias_grad = colsum;
       const int prob = group_add_problem(g, op.kind, a, err, sizeof err);
@@ -879,14 +892,15 @@ void build_segments(Ctx* c) {
       const int tm = group_problem_tiles_m(g, prob), tn = group_problem_tiles_n(g, prob), kb = group_problem_kblocks(g, prob);
       for (int i = 0; i < tm; ++i)
         for (int j = 0; j < tn; ++j)
-          group_add_task(g, prob, i, j, 0, kb, inT >= 0 ? ctr(m, inT, i) : -1, inT >= 0 ? 1 : 0,
+          group_add_task(g, prob, i, j, 0, kb, inT >= 0 ? ctr(in_m, inT, i) : -1, inT >= 0 ? 1 : 0,
                          kGroupSignalsPerTile * in_tn, -1, 0, outT >= 0 ? ctr(m, outT, i) : -1);
       return tn;
     };
     // weight gradient (TN): the batch contraction is cut into row-block ranges; a task waits for dY over its range
-    auto add_wgrad = [&](const Op& op, int m, int dyT, int dy_tn) {
+    auto add_wgrad = [&](const Op& op, int m, int dyT, int dy_tn, int dy_m = -1) {
       const bool external = dyT < 0;
       if (nodeps) dyT = -1;
+      if (dy_m < 0) dy_m = m;
       GemmArgs a = op.gargs;
       a.bias_grad = nullptr;
       const int prob = group_add_problem(g, op.kind, a, err, sizeof err);
@@ -899,7 +913,7 @@ void build_segments(Ctx* c) {
         const int nrb = std::min(per, rbs - r0);
         for (int i = 0; i < tm; ++i)
           for (int j = 0; j < tn; ++j)
-            group_add_task(g, prob, i, j, r0 * 8, std::min(nrb * 8, kb - r0 * 8), dyT >= 0 ? ctr(m, dyT, r0) : -1,
+            group_add_task(g, prob, i, j, r0 * 8, std::min(nrb * 8, kb - r0 * 8), dyT >= 0 ? ctr(dy_m, dyT, r0) : -1,
                            dyT >= 0 ? nrb : 0, kGroupSignalsPerTile * dy_tn, -1, 0, -1);
       }
       if (external && op.gargs.bias_grad) {
@@ -912,11 +926,11 @@ void build_segments(Ctx* c) {
       }
       return Op();
     };
-    auto begin = [&](Ctx::Seg& sg, int T0) {
+    auto begin = [&](Ctx::Seg& sg, int T0, int n_tensors = 2) {
       sg.site = group_begin(g);
       if (sg.site >= c->max_sites - 1) fail("too many tensor-core launch sites");
       sg.reset_first = ctr(0, T0, 0);
-      sg.reset_count = 2 * M * RB;
+      sg.reset_count = n_tensors * M * RB;
     };
     auto end = [&](Ctx::Seg& sg) { (void)sg; if (!group_end(g, err, sizeof err)) fail("%s", err); };
     std::vector<int> tn1(M), tn2(M);
@@ -951,6 +965,46 @@ void build_segments(Ctx* c) {
     for (int m = 0; m < M; ++m) add_wgrad(c->ops_bwd_enc_mod[m][4], m, T_DH1, tn2[m]);
     end(c->seg_bwd_enc);
     c->fused = true;
+    // ---- two-launch form: latent stages as elementwise tasks between the encoder and decoder layers ----
+    c->elt_built = false;
+    if (M <= 2 && RB * 8 <= kMaxPartialBlocks && !nodeps && !getenv("VAEASSOC_NO_ELT")) {
+      GElem el;
+      el.lf = c->lat_fwd_args;
+      el.lb = c->lat_bwd_args;
+      for (int m = 0; m < M; ++m) el.bh_grad[m] = c->ops_bwd_enc_mod[m][0].gargs.bias_grad;
+      group_set_elem(g, el);
+      c->lat_blocks_elt = RB * 8;
+      const int S = kGroupSignalsPerTile;
+      std::vector<int> tnh(M), tnz(M);
+      begin(c->seg_fwd, T_H1, 6);
+      for (int m = 0; m < M; ++m) tn1[m] = add_rowwise(c->ops_enc_mod[m][0], m, -1, 0, T_H1, nullptr);
+      for (int m = 0; m < M; ++m) tn2[m] = add_rowwise(c->ops_enc_mod[m][1], m, T_H1, tn1[m], T_H2, nullptr);
+      for (int m = 0; m < M; ++m) tnh[m] = add_rowwise(c->ops_enc_mod[m][2], m, T_H2, tn2[m], T_HD, nullptr);
+      for (int rb = 0; rb < RB; ++rb)
+        group_add_elt_task(g, 0, rb, B, ctr(0, T_HD, rb), 1, S * tnh[0], M > 1 ? ctr(1, T_HD, rb) : -1, M > 1 ? S * tnh[1] : 0,
+                           ctr(0, T_Z, rb));
+      for (int m = 0; m < M; ++m) tn1[m] = add_rowwise(c->ops_dec_mod[m][0], m, T_Z, 1, T_G1, nullptr, 0);
+      for (int m = 0; m < M; ++m) tn2[m] = add_rowwise(c->ops_dec_mod[m][1], m, T_G1, tn1[m], T_G2, nullptr);
+      for (int m = 0; m < M; ++m) add_rowwise(c->ops_dec_mod[m][2], m, T_G2, tn2[m], -1, nullptr);
+      end(c->seg_fwd);
+      begin(c->seg_bwd, T_DG2, 6);
+      for (int m = 0; m < M; ++m) { auto& bd = c->ops_bwd_dec_mod[m]; tn1[m] = add_rowwise(bd[1], m, -1, 0, T_DG2, bd[2].gargs.bias_grad); }
+      for (int m = 0; m < M; ++m) add_wgrad(c->ops_bwd_dec_mod[m][0], m, -1, 0);     // (its column sums: ops_colsum_dec, built above)
+      for (int m = 0; m < M; ++m) { auto& bd = c->ops_bwd_dec_mod[m]; tn2[m] = add_rowwise(bd[3], m, T_DG2, tn1[m], T_DG1, bd[4].gargs.bias_grad); }
+      for (int m = 0; m < M; ++m) add_wgrad(c->ops_bwd_dec_mod[m][2], m, T_DG2, tn1[m]);
+      for (int m = 0; m < M; ++m) tnz[m] = add_rowwise(c->ops_bwd_dec_mod[m][5], m, T_DG1, tn2[m], T_DZ, nullptr);
+      for (int m = 0; m < M; ++m) add_wgrad(c->ops_bwd_dec_mod[m][4], m, T_DG1, tn2[m]);
+      for (int rb = 0; rb < RB; ++rb)
+        group_add_elt_task(g, 1, rb, B, ctr(0, T_DZ, rb), 1, S * tnz[0], M > 1 ? ctr(1, T_DZ, rb) : -1, M > 1 ? S * tnz[1] : 0,
+                           ctr(0, T_DHD, rb));
+      for (int m = 0; m < M; ++m) { auto& be = c->ops_bwd_enc_mod[m]; tn1[m] = add_rowwise(be[1], m, T_DHD, 1, T_DH2, be[2].gargs.bias_grad, 0); }
+      for (int m = 0; m < M; ++m) add_wgrad(c->ops_bwd_enc_mod[m][0], m, T_DHD, 1, 0);   // bias gradient: by the latent-backward task
+      for (int m = 0; m < M; ++m) { auto& be = c->ops_bwd_enc_mod[m]; tn2[m] = add_rowwise(be[3], m, T_DH2, tn1[m], T_DH1, be[4].gargs.bias_grad); }
+      for (int m = 0; m < M; ++m) add_wgrad(c->ops_bwd_enc_mod[m][2], m, T_DH2, tn1[m]);
+      for (int m = 0; m < M; ++m) add_wgrad(c->ops_bwd_enc_mod[m][4], m, T_DH1, tn2[m]);
+      end(c->seg_bwd);
+      c->elt_built = true;
+    }
   }
   group_set_counters(c->gplan, c->gsync, c->n_ctr);
   if (!group_upload(c->gplan, err, sizeof err)) fail("%s", err);
@@ -991,6 +1045,15 @@ void run_bwd_ops(Ctx* c, int m, std::vector<Op>& ops, cudaStream_t s) {
   }
 }
 
+// the two-launch form (latent stages inside the tile kernel) serves every schedule except the two-bucket NCCL one, whose
+// first all-reduce starts between the decoder and the encoder backward
+bool dp_two_buckets(const Ctx* c) {
+  const bool dp = c->comm != nullptr && c->world > 1;
+  if (!dp || c->peer.on) return false;
+  return !(c->dp_single >= 0 ? c->dp_single != 0 : (c->fused && c->world > 4));
+}
+bool elt_mode(const Ctx* c) { return c->fused && c->elt_built && !dp_two_buckets(c); }
+
 FinalizeArgs finalize_args(Ctx* c, int advance) {
   FinalizeArgs a;
   a.n_mod = c->cfg.n_modalities;
@@ -999,7 +1062,7 @@ FinalizeArgs finalize_args(Ctx* c, int advance) {
     a.partials_recon[m] = c->mods[m].partials; a.blocks_recon[m] = c->mods[m].recon_blocks;
   }
   a.inv_global_batch = 1.0f / (float)global_batch(c); a.lambda = c->cfg.assoc_lambda;
-  a.partials_latent = c->lat_partials; a.blocks_latent = c->lat_blocks;
+  a.partials_latent = c->lat_partials; a.blocks_latent = c->lat_mode_elt ? c->lat_blocks_elt : c->lat_blocks;
   a.scalars = c->scalars; a.cost_slot = c->g + c->n_flat; a.step_dev = c->step_dev; a.advance = advance;
   return a;
 }
@@ -1046,6 +1109,22 @@ void join_colsums(Ctx* c, std::vector<Op>& ops, cudaStream_t s) {
 // segment A1: zero grads, forward, losses, decoder backward   (gradient bucket 0 complete at its end)
 void enqueue_a1(Ctx* c, cudaStream_t s) {
   const int M = c->cfg.n_modalities;
+  c->lat_mode_elt = false;
+  if (elt_mode(c)) {
+    // two launches of the persistent tile kernel carry the step: forward (encoders, latent stage, decoders) here,
+    // backward in enqueue_a2; the gradient memset runs as a parallel branch of the forward
+    c->lat_mode_elt = true;
+    CUDA_OK(cudaEventRecord(c->ev_aux_fork, s));
+    CUDA_OK(cudaStreamWaitEvent(c->aux_stream, c->ev_aux_fork, 0));
+    CUDA_OK(cudaMemsetAsync(c->g, 0, (size_t)(c->n_flat + 32) * sizeof(float), c->aux_stream));
+    CUDA_OK(cudaEventRecord(c->ev_aux_join, c->aux_stream));
+    launch_seg(c, c->seg_fwd, s);
+    fork_modalities(c, s);
+    for (int m = 0; m < M; ++m) run_ops(c, c->ops_loss_mod[m], mod_stream(c, m, s));
+    join_modalities(c, s);
+    CUDA_OK(cudaStreamWaitEvent(s, c->ev_aux_join, 0));
+    return;
+  }
   if (c->fused) {
     // the gradient buffer is first touched by the decoder backward: its memset runs as a parallel branch of the forward
     CUDA_OK(cudaEventRecord(c->ev_aux_fork, s));
@@ -1080,6 +1159,19 @@ void enqueue_a1(Ctx* c, cudaStream_t s) {
 }
 // segment A2: latent + encoder backward, cost finalize (bucket 1 + cost slot complete at its end)
 void enqueue_a2(Ctx* c, cudaStream_t s, int advance) {
+  if (elt_mode(c)) {
+    c->lat_mode_elt = true;
+    CUDA_OK(cudaEventRecord(c->ev_aux_fork, s));
+    CUDA_OK(cudaStreamWaitEvent(c->aux_stream, c->ev_aux_fork, 0));
+    launch_finalize(finalize_args(c, advance), c->aux_stream);
+    c->launches += 1;
+    CUDA_OK(cudaEventRecord(c->ev_aux_join, c->aux_stream));
+    fork_colsums(c, c->ops_colsum_dec, s);
+    launch_seg(c, c->seg_bwd, s);
+    join_colsums(c, c->ops_colsum_dec, s);
+    CUDA_OK(cudaStreamWaitEvent(s, c->ev_aux_join, 0));
+    return;
+  }
   run_ops(c, c->ops_latent_bwd, s);
   if (c->fused) {
     // the cost reduction (block partials of the loss kernels -> cost slot, step counter) runs next to the encoder backward
@@ -1131,6 +1223,7 @@ void enqueue_peer_adam(Ctx* c, cudaStream_t s) {
 }
 void allreduce(Ctx* c, float* buf, int64_t count, cudaStream_t s);
 void enqueue_forward_loss(Ctx* c, cudaStream_t s) {   // evaluate_cost: no gradients
+  c->lat_mode_elt = false;
   run_ops(c, c->ops_fwd_enc, s);
   {
     // latent forward without the gradient stash
@@ -2210,7 +2303,20 @@ int vaeassoc_profile_step(vaeassoc_handle h, const float* const* x_dev, const in
       z.run = [c](cudaStream_t st) { CUDA_OK(cudaMemsetAsync(c->g, 0, (size_t)(c->n_flat + 32) * sizeof(float), st)); };
       all.push_back(z);
     }
-    if (h->fused) {
+    h->lat_mode_elt = elt_mode(h);
+    if (elt_mode(h)) {
+      Ctx* c = h;
+      auto seg_op = [&](const char* name, const Ctx::Seg* sg, std::initializer_list<std::vector<Op>*> members) {
+        Op o; o.name = name;
+        for (auto* v : members) for (auto& op : *v) o.flops += op.flops;
+        o.run = [c, sg](cudaStream_t st) { launch_seg(c, *sg, st); c->launches -= 1; };
+        all.push_back(o);
+      };
+      seg_op("seg_fwd", &h->seg_fwd, {&h->ops_fwd_enc, &h->ops_fwd_dec});
+      for (auto& op : h->ops_loss) all.push_back(op);
+      for (auto& op : h->ops_colsum_dec) all.push_back(op);
+      seg_op("seg_bwd", &h->seg_bwd, {&h->ops_bwd_dec, &h->ops_bwd_enc});
+    } else if (h->fused) {
       // the train step's own launches: four fused segments + the elementwise kernels between them
       Ctx* c = h;
       auto seg_op = [&](const char* name, const Ctx::Seg* sg, std::initializer_list<std::vector<Op>*> members) {
@@ -2242,7 +2348,9 @@ int vaeassoc_profile_step(vaeassoc_handle h, const float* const* x_dev, const in
     }
     if (h->fused && getenv("VAEASSOC_TC_TIMELINE")) {
       CUDA_OK(cudaStreamSynchronize(s));
-      for (const Ctx::Seg* sg : {&h->seg_enc, &h->seg_dec, &h->seg_bwd_dec, &h->seg_bwd_enc})
+      std::vector<const Ctx::Seg*> segs = {&h->seg_enc, &h->seg_dec, &h->seg_bwd_dec, &h->seg_bwd_enc};
+      if (elt_mode(h)) segs = {&h->seg_fwd, &h->seg_bwd};
+      for (const Ctx::Seg* sg : segs)
         group_debug_timeline(h->gplan, sg->site, h->gsync + h->n_ctr + 2 * sg->site, sg->reset_first, sg->reset_count, s);
     }
     const int n = (int)std::min<size_t>(all.size(), (size_t)capacity);

@@ -49,6 +49,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "latent.cuh"
 
 namespace vaeassoc {
 
@@ -345,7 +346,11 @@ struct alignas(16) GTask {
   int act, M, N;
 };
 static_assert(sizeof(GTask) == 64, "GTask is loaded as four 16-byte words");
-enum { TF_A_MN = 1, TF_B_MN = 2, TF_REDUCE = 4, TF_AUX = 8, TF_ROUND = 16, TF_COLSUM = 32, TF_MASK_OUT = 64, TF_MASK_IN = 128 };
+enum { TF_A_MN = 1, TF_B_MN = 2, TF_REDUCE = 4, TF_AUX = 8, TF_ROUND = 16, TF_COLSUM = 32, TF_MASK_OUT = 64, TF_MASK_IN = 128,
+       // elementwise tasks (no contraction: nkb = 0; the epilogue warps of the pair execute them over the 256 rows of
+       // row block m_blk; the producer and the MMA issuer skip them): latent forward / backward (latent.cuh)
+       TF_ELT_LATENT_FWD = 256, TF_ELT_LATENT_BWD = 512, TF_ELT = TF_ELT_LATENT_FWD | TF_ELT_LATENT_BWD };
+
 
 namespace {
 
@@ -399,7 +404,8 @@ struct GParams { GProblem p[NP]; };
 
 template <int NP>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-gemm_group_kernel(const __grid_constant__ GParams<NP> params, const GTask* __restrict__ tasks, int ntasks,
+gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_constant__ GElem elem,
+                  const GTask* __restrict__ tasks, int ntasks,
                   uint32_t* __restrict__ counters, uint32_t* __restrict__ queue, int reset_first, int reset_count,
                   int mode, unsigned long long* __restrict__ tl) {
   extern __shared__ uint8_t smem_raw[];
@@ -409,6 +415,9 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const GTask* __res
   const uint32_t strip_base = bar_base + 512u;
   const int dynamic_first = mode & 1;
   const bool bias_smem = (mode & 2) != 0, tma_store = (mode & 4) != 0;
+  // timing experiments only (wrong results): VAEASSOC_DEBUG_SKIP_MATH / _SKIP_STORE drop parts of the NN / NT epilogue
+  const bool dbg_skip_math = (mode & 8) != 0, dbg_skip_store = (mode & 16) != 0;
+  const uint32_t stagger_ns = (uint32_t)mode >> 8;      // VAEASSOC_EPI_STAGGER_NS: the odd chunk slots start this much later
   // barriers: full[s] (leader CTA only), empty[s], tmem_full[2], tmem_empty[2] (leader CTA only), aux[epilogue warp],
   // sched_full[kSched], sched_empty[kSched] (leader CTA only); then the TMEM slot and the task-index ring
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -495,6 +504,14 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const GTask* __res
     while (t >= 0) {
       uint32_t raw = 0;
       if (lane == 0 && rank == 0) raw = atomicAdd(queue, 1u);      // consumed below, after the first loads are issued
+      if (tk.flags & TF_ELT) {               // nothing to stream: hand the next task to every role at once
+        int t_next = -1;
+        if (elect_one()) t_next = (rank == 0) ? publish(queue_base + raw) : next_task();
+        __syncwarp();
+        t = bcast(t_next);
+        tk = load_task(tasks, t);
+        continue;
+      }
       const GProblem* p = &params.p[tk.problem];
       const int BN = tk.bn, BNH = BN >> 1;
       const bool a_mn = (tk.flags & TF_A_MN) != 0, b_mn = (tk.flags & TF_B_MN) != 0;
@@ -545,6 +562,13 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const GTask* __res
       GTask tk = load_task(tasks, t);
       for (; t >= 0; ++tcount) {
         int t_after = -1;
+        if (tk.flags & TF_ELT) {             // no accumulator involved (tcount counts contraction tasks only)
+          if (lane == 0) t_after = next_task();
+          t = bcast(t_after);
+          tk = load_task(tasks, t);
+          --tcount;
+          continue;
+        }
         const int announce = min(tk.nkb, kStages) - 1;   // the producer publishes the next task at this k-block
         const bool a_mn = (tk.flags & TF_A_MN) != 0, b_mn = (tk.flags & TF_B_MN) != 0;
         const uint32_t idesc = make_idesc(BM, tk.bn, a_mn, b_mn);
@@ -600,6 +624,56 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const GTask* __res
     for (; t >= 0; ++tcount) {
       const int t_after = next_task_warp();
       const GTask tk_after = load_task(tasks, t_after);
+      if (tk.flags & TF_ELT) {
+        // ---- elementwise task: rows [256 m_blk + 128 rank, +128) of the batch, one thread per row (warps 0..3) ----
+        if (lane == 0) {
+          for (int c = 0; c < tk.wait_cnt; ++c) wait_counter(counters + tk.wait_ctr + c, (uint32_t)tk.wait_val);
+          if (tk.wait2_ctr >= 0) wait_counter(counters + tk.wait2_ctr, (uint32_t)tk.wait2_val);
+          fence_acq_rel_gpu();               // pairs with the producers' red.release.gpu (inputs are read with ld.cg)
+        }
+        __syncwarp();
+        if (e < 4) {
+          const int64_t r = (int64_t)tk.m_blk * BM + (int64_t)rank * BM_CTA + e * 32 + lane;
+          const bool live = r < (int64_t)tk.M;
+          if (tk.flags & TF_ELT_LATENT_FWD) {
+            float kl0 = 0.f, kl1 = 0.f, assoc = 0.f;
+            if (live) {
+              if (elem.lf.n_mod == 1) {
+                float rk[1];
+                latent_fwd_row<1, LoadCg>(elem.lf, r, rk, assoc);
+                kl0 = rk[0];
+              } else {
+                float rk[2];
+                latent_fwd_row<2, LoadCg>(elem.lf, r, rk, assoc);
+                kl0 = rk[0]; kl1 = rk[1];
+              }
+            }
+            kl0 = warp_sum(kl0); kl1 = warp_sum(kl1); assoc = warp_sum(assoc);
+            if (lane == 0) {
+              float* part = elem.lf.partials + (size_t)((tk.m_blk * 2 + (int)rank) * 4 + e) * kCostSlots;
+              part[1] = kl0; part[3] = kl1; part[8] = assoc;
+            }
+          } else {
+            const int nz = elem.lb.n_z;
+            for (int m = 0; m < elem.lb.n_mod; ++m) {
+              for (int k = 0; k < nz; ++k) {
+                float dm = 0.f, dl = 0.f;
+                if (live) latent_bwd_elem<LoadCg>(elem.lb, m, r, k, dm, dl);
+                if (elem.bh_grad[m] != nullptr) {
+                  dm = warp_sum(dm); dl = warp_sum(dl);
+                  if (lane == 0) { atomicAdd(elem.bh_grad[m] + k, dm); atomicAdd(elem.bh_grad[m] + nz + k, dl); }
+                }
+              }
+            }
+          }
+        }
+        __syncwarp();
+        if (elect_one() && tk.signal_ctr >= 0) red_release_gpu_add(counters + tk.signal_ctr, 1u);
+        t = t_after;
+        tk = tk_after;
+        --tcount;
+        continue;
+      }
       const GProblem* p = &params.p[tk.problem];
       const int BN = tk.bn, N = tk.N, act = tk.act;
       const bool reduce = (tk.flags & TF_REDUCE) != 0, use_aux = (tk.flags & TF_AUX) != 0, round_out = (tk.flags & TF_ROUND) != 0;
@@ -664,6 +738,7 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const GTask* __res
       // ~32 B/clk: ~1000 cycles per 4 KB chunk)
       uint32_t v[32];
       const uint32_t tmem_row = tmem_base + acc * kAccCols + ((uint32_t)(q * 32) << 16);
+      if (stagger_ns != 0u && (slot & 1) && nmine > 0) __nanosleep(stagger_ns);
       if (nmine > 0) tmem_ld32_issue(tmem_row + (uint32_t)(slot * 32), v);
 #pragma unroll 1
       for (int i = 0; i < nmine; ++i, ++cidx) {
@@ -672,7 +747,8 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const GTask* __res
         const uint32_t ob = ebuf + b * CHUNK_BYTES;
         tmem_ld_wait(v);
         if (tl && rank == 0 && warp == 2 && lane == 0 && i == 0) tl[kTL * t + 9] = (unsigned long long)clock64();
-        if (mask_in != nullptr) {
+        if (dbg_skip_math) {
+        } else if (mask_in != nullptr) {
           // relu': one bit per element, already in registers; the tf32 rounding (round-to-nearest, ties away = add half
           // an ulp to the magnitude, truncate) is folded into the same AND
           const uint32_t mw = i == 0 ? mw0 : i == 1 ? mw1 : i == 2 ? mw2 : mw3;
@@ -764,7 +840,7 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const GTask* __res
           for (int j = 0; j < 32; ++j) v[j] = (n0 + c * 32 + j < N) ? v[j] : 0u;
         }
         if (tl && rank == 0 && warp == 2 && lane == 0 && i == 0) tl[kTL * t + 11] = (unsigned long long)clock64();
-        if (mask_out != nullptr) {
+        if (mask_out != nullptr && !dbg_skip_math) {
           // bit j = (output j > 0); relu outputs are >= +0, so "bits != 0": sign of the negated bits, shifted in from
           // the right, two independent chains of 16
           uint32_t wl = 0u, wh = 0u;
@@ -802,7 +878,7 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const GTask* __res
             bulk_commit();
           }
           red_pending = 1;
-        } else {
+        } else if (!dbg_skip_store) {
           // transposed read-back: 8 lanes cover one 128-byte row segment, 4 rows per instruction -> coalesced 128-bit
           // stores; rows >= M and columns >= roundup4(N) are clipped (the TMA loads zero-filled them)
           __syncwarp();
@@ -969,6 +1045,7 @@ struct GroupPlan {
   std::vector<GProblem> problems;
   std::vector<GTask> tasks;          // .problem is relative to the site's first problem once the site is closed
   std::vector<GroupSite> sites;
+  GElem elem;                        // arguments of the elementwise tasks (one latent stage per handle)
   bool open = false;
   GTask* d_tasks = nullptr;
   uint32_t* d_counters = nullptr;    // row-block completion counters of the step (not owned; self-cleaning)
@@ -1102,6 +1179,25 @@ int group_add_task(GroupPlan* g, int prob, int m_blk, int n_blk, int kb0, int nk
   return (int)g->tasks.size() - 1;
 }
 
+// an elementwise task over row block m_blk (kind 0: latent forward, 1: latent backward; arguments: group_set_elem)
+int group_add_elt_task(GroupPlan* g, int kind, int m_blk, int batch, int wait_ctr, int wait_cnt, int wait_val,
+                       int wait2_ctr, int wait2_val, int signal_ctr) {
+  GTask t;
+  memset(&t, 0, sizeof t);
+  t.problem = (int)g->problems.size() > 0 ? g->sites.back().first_problem : 0;   // unused; keeps the site-relative rebase >= 0
+  t.m_blk = m_blk; t.nkb = 0;
+  t.wait_ctr = wait_ctr; t.wait_cnt = wait_cnt; t.wait_val = wait_val;
+  t.wait2_ctr = wait2_ctr; t.wait2_val = wait2_val; t.signal_ctr = signal_ctr;
+  t.bn = 64;
+  t.flags = kind == 0 ? TF_ELT_LATENT_FWD : TF_ELT_LATENT_BWD;
+  t.M = batch;
+  g->tasks.push_back(t);
+  g->uploaded = false;
+  return (int)g->tasks.size() - 1;
+}
+
+void group_set_elem(GroupPlan* g, const GElem& e) { g->elem = e; }
+
 int group_num_tasks(const GroupPlan* g) { return (int)g->tasks.size(); }
 
 void group_set_counters(GroupPlan* g, uint32_t* d_counters, int n) { g->d_counters = d_counters; g->n_counters = n; }
@@ -1131,19 +1227,21 @@ void launch_site(const GroupPlan* g, int site, uint32_t* queue, int reset_first,
                  unsigned long long* tl, cudaStream_t s) {
   const GroupSite& st = g->sites[site];
   if (st.n_tasks <= 0) return;
-  static const int env_mode = (getenv("VAEASSOC_EPI_BIAS_SHFL") ? 0 : 2) | (getenv("VAEASSOC_EPI_TMA_STORE") ? 4 : 0);
+  static const int env_mode = (getenv("VAEASSOC_EPI_BIAS_SHFL") ? 0 : 2) | (getenv("VAEASSOC_EPI_TMA_STORE") ? 4 : 0) |
+                              (getenv("VAEASSOC_DEBUG_SKIP_MATH") ? 8 : 0) | (getenv("VAEASSOC_DEBUG_SKIP_STORE") ? 16 : 0) |
+                              (getenv("VAEASSOC_EPI_STAGGER_NS") ? (std::max(0, std::min(4000, atoi(getenv("VAEASSOC_EPI_STAGGER_NS")))) << 8) : 0);
   const int mode = (dynamic_first ? 1 : 0) | env_mode;
   const int clusters = std::min(st.n_tasks, kNumSMs / 2);
   if (st.n_problems <= kSiteProblemsSmall) {
     GParams<kSiteProblemsSmall> prm;
     memcpy(prm.p, g->problems.data() + st.first_problem, (size_t)st.n_problems * sizeof(GProblem));
     gemm_group_kernel<kSiteProblemsSmall><<<2 * clusters, kThreads, SMEM_BYTES, s>>>(
-        prm, g->d_tasks + st.first_task, st.n_tasks, g->d_counters, queue, reset_first, reset_count, mode, tl);
+        prm, g->elem, g->d_tasks + st.first_task, st.n_tasks, g->d_counters, queue, reset_first, reset_count, mode, tl);
   } else {
     GParams<kSiteProblemsLarge> prm;
     memcpy(prm.p, g->problems.data() + st.first_problem, (size_t)st.n_problems * sizeof(GProblem));
     gemm_group_kernel<kSiteProblemsLarge><<<2 * clusters, kThreads, SMEM_BYTES, s>>>(
-        prm, g->d_tasks + st.first_task, st.n_tasks, g->d_counters, queue, reset_first, reset_count, mode, tl);
+        prm, g->elem, g->d_tasks + st.first_task, st.n_tasks, g->d_counters, queue, reset_first, reset_count, mode, tl);
   }
 }
 }  // namespace
@@ -1171,7 +1269,10 @@ void group_debug_timeline(const GroupPlan* g, int site, uint32_t* queue, int res
   cudaMemcpy(h.data(), dev, (size_t)count * kTL * 8 + 192 * 8, cudaMemcpyDeviceToHost);
   cudaFree(dev);
   unsigned long long t0 = ~0ull, t1 = 0;
-  for (int i = 0; i < count; ++i) { t0 = std::min(t0, h[kTL * i + 6]); t1 = std::max(t1, h[kTL * i + 4]); }
+  for (int i = 0; i < count; ++i) {
+    if (g->tasks[first + i].nkb == 0) continue;      // elementwise tasks carry no stamps
+    t0 = std::min(t0, h[kTL * i + 6]); t1 = std::max(t1, h[kTL * i + 4]);
+  }
   fprintf(stderr, "[group timeline] %d tasks on %d clusters, %.1f us from first entry to last epilogue end\n", count, clusters,
           (t1 - t0) * 1e-3);
   {
@@ -1186,6 +1287,7 @@ void group_debug_timeline(const GroupPlan* g, int site, uint32_t* queue, int res
   for (int k = 0; k < show; ++k) {
     const int i = (k < show / 2 || show == count) ? k : count - (show - k);
     const GTask& tk = g->tasks[first + i];
+    if (tk.nkb == 0) continue;
     fprintf(stderr, "  task %4d prob %2d (%2d,%2d) nkb %3d cl %2llu entry %6.2f | prod %6.2f mma %6.2f..%6.2f (%llu cyc) epi %6.2f..%6.2f us | ld0 %6.0f chunk0 %6.0f loop %6.2f | math %6.0f mask %6.0f wait %6.0f sts %6.0f\n", i,
             tk.problem, tk.m_blk, tk.n_blk, tk.nkb, h[kTL * i + 5], (h[kTL * i + 6] - t0) * 1e-3, (h[kTL * i + 0] - t0) * 1e-3,
             (h[kTL * i + 1] - t0) * 1e-3, (h[kTL * i + 2] - t0) * 1e-3, h[kTL * i + 7], (h[kTL * i + 3] - t0) * 1e-3, (h[kTL * i + 4] - t0) * 1e-3,

@@ -64,6 +64,12 @@ int group_problem_kblocks(const GroupPlan* g, int prob);      // k-blocks of 32
 int group_add_task(GroupPlan* g, int prob, int m_blk, int n_blk, int kb0, int nkb, int wait_ctr, int wait_cnt,
                    int wait_val, int wait2_ctr, int wait2_val, int signal_ctr);
 int group_num_tasks(const GroupPlan* g);
+// elementwise task over the 256 rows of row block m_blk, executed by the epilogue warps of whichever CTA pair pops it
+// (kind 0: latent forward, 1: latent backward -- arguments from group_set_elem); waits / signals like a tile task
+int group_add_elt_task(GroupPlan* g, int kind, int m_blk, int batch, int wait_ctr, int wait_cnt, int wait_val,
+                       int wait2_ctr, int wait2_val, int signal_ctr);
+struct GElem;
+void group_set_elem(GroupPlan* g, const GElem& e);
 // a launch site = the problems / tasks added between group_begin() and group_end(): ONE kernel launch (<= 24 problems)
 int group_begin(GroupPlan* g);
 bool group_end(GroupPlan* g, char* err, int errlen);
@@ -161,6 +167,14 @@ struct LatentBwdArgs {
   int round_out = 0;
 };
 void launch_latent_bwd(const LatentBwdArgs& a, cudaStream_t s);
+
+// arguments of the elementwise tasks of a tile-kernel plan (kernel parameter of gemm_group_kernel)
+struct GElem {
+  LatentArgs lf;             // partials: [(row block * 2 + CTA) * 4 + warp][kCostSlots]
+  LatentBwdArgs lb;
+  float* bh_grad[4] = {nullptr, nullptr, nullptr, nullptr};   // bias gradient of the heads layer per modality
+                                                              // (column sums of d mu | d log sigma^2), or null
+};
 
 struct ReconArgs {
   int batch = 0, n_input = 0, binary = 0, slot = 0;

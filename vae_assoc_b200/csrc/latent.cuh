@@ -1,0 +1,86 @@
+// Row-level arithmetic of the latent stage (reparameterisation, prior KL, symmetric association KL and their
+// gradients; vae_assoc.py:102-103, 335-337, 346-366), shared by the stand-alone kernels (loss.cu) and by the
+// elementwise tasks of the persistent tile kernel (gemm_group.cu), so that both paths produce the same bits.
+#pragma once
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vaeassoc {
+
+// LOAD: how global memory is read -- plain loads in a stand-alone kernel (its inputs were written by earlier launches),
+// L1-bypassing loads inside the persistent kernel (the inputs were written by other SMs of the SAME launch)
+struct LoadPlain { __device__ __forceinline__ static float ld(const float* p) { return *p; } };
+struct LoadCg { __device__ __forceinline__ static float ld(const float* p) { return __ldcg(p); } };
+
+// one batch row of the latent forward; accumulates the row's prior-KL sums and association-KL sum
+template <int NMOD, typename LOAD>
+__device__ __forceinline__ void latent_fwd_row(const LatentArgs& a, int64_t r, float (&row_kl)[NMOD], float& row_assoc) {
+  const int nz = a.n_z;
+#pragma unroll
+  for (int m = 0; m < NMOD; ++m) row_kl[m] = 0.f;
+  row_assoc = 0.f;
+  for (int k = 0; k < nz; ++k) {
+    const float e = LOAD::ld(a.eps + r * nz + k);
+    float mu[NMOD], lv[NMOD], ex[NMOD];
+#pragma unroll
+    for (int m = 0; m < NMOD; ++m) {
+      mu[m] = LOAD::ld(a.heads[m] + r * 2 * nz + k);
+      lv[m] = LOAD::ld(a.heads[m] + r * 2 * nz + nz + k);
+      ex[m] = expf(lv[m]);
+      const float zv = mu[m] + sqrtf(ex[m]) * e;                             // :102-103
+      a.z[m][r * nz + k] = a.round_z ? round_tf32(zv) : zv;
+      row_kl[m] += 1.0f + lv[m] - mu[m] * mu[m] - ex[m];                     // :335-337 (element)
+    }
+    float gmu[NMOD], glv[NMOD];
+#pragma unroll
+    for (int m = 0; m < NMOD; ++m) {
+      const float w = a.weight[m] * a.inv_global_batch;
+      gmu[m] = w * mu[m];
+      glv[m] = w * 0.5f * (ex[m] - 1.0f);
+    }
+#pragma unroll
+    for (int p = 0; p < NMOD; ++p) {
+#pragma unroll
+      for (int q = p + 1; q < NMOD; ++q) {                                    // itertools.combinations, :346
+        const float d = mu[p] - mu[q];
+        const float ip = expf(-lv[p]), iq = expf(-lv[q]);
+        const float epq = expf(lv[p] - lv[q]), eqp = expf(lv[q] - lv[p]);
+        // 0.5*(lq - lp - 1 + e^{lp-lq} + d^2 e^{-lq}) + 0.5*(lp - lq - 1 + e^{lq-lp} + d^2 e^{-lp})   :355-365
+        row_assoc += 0.5f * (epq + eqp - 2.0f + d * d * (ip + iq));
+        gmu[p] += a.lambda * d * (ip + iq);
+        gmu[q] -= a.lambda * d * (ip + iq);
+        glv[p] += a.lambda * 0.5f * (epq - eqp - d * d * ip);
+        glv[q] += a.lambda * 0.5f * (eqp - epq - d * d * iq);
+      }
+    }
+    if (a.with_grad) {
+#pragma unroll
+      for (int m = 0; m < NMOD; ++m) {
+        a.gstat[m][r * 2 * nz + k] = gmu[m];
+        a.gstat[m][r * 2 * nz + nz + k] = glv[m];
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < NMOD; ++m) {
+    row_kl[m] *= -0.5f;
+    if (a.latent_loss[m]) a.latent_loss[m][r] = row_kl[m];                   // vae_latent_losses probe, :339
+  }
+}
+
+// element (r, k) of the latent backward for modality m: (d mu, d log sigma^2) from d z and the stashed KL gradients
+template <typename LOAD>
+__device__ __forceinline__ void latent_bwd_elem(const LatentBwdArgs& a, int m, int64_t r, int k, float& dm, float& dl) {
+  const int nz = a.n_z;
+  const float e = LOAD::ld(a.eps + r * nz + k);
+  const float lv = LOAD::ld(a.heads[m] + r * 2 * nz + nz + k);
+  const float s = sqrtf(expf(lv));                                           // d z / d lv = eps * s / 2
+  const float dz = LOAD::ld(a.dz[m] + r * nz + k);
+  dm = dz + LOAD::ld(a.gstat[m] + r * 2 * nz + k);
+  dl = dz * e * 0.5f * s + LOAD::ld(a.gstat[m] + r * 2 * nz + nz + k);
+  if (a.round_out) { dm = round_tf32(dm); dl = round_tf32(dl); }
+  a.dheads[m][r * 2 * nz + k] = dm;
+  a.dheads[m][r * 2 * nz + nz + k] = dl;
+}
+
+}  // namespace vaeassoc

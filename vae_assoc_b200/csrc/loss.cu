@@ -10,6 +10,7 @@
 // plus the analytic gradients tf.train.AdamOptimizer.minimize (:373-374) would derive.
 #include "common.cuh"
 #include "kernels.h"
+#include "latent.cuh"
 #include "philox.cuh"
 
 namespace vaeassoc {
@@ -100,65 +101,15 @@ __global__ void __launch_bounds__(256) philox_normal_kernel(float* __restrict__ 
 template <int NMOD>
 __global__ void __launch_bounds__(256) latent_fwd_kernel(LatentArgs a) {
   __shared__ float red[32];
-  const int nz = a.n_z;
   float s_lat[NMOD];
   float s_assoc = 0.f;
 #pragma unroll
   for (int m = 0; m < NMOD; ++m) s_lat[m] = 0.f;
-
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < a.batch; r += (int64_t)gridDim.x * blockDim.x) {
-    float row_kl[NMOD];
+    float row_kl[NMOD], row_assoc;
+    latent_fwd_row<NMOD, LoadPlain>(a, r, row_kl, row_assoc);
 #pragma unroll
-    for (int m = 0; m < NMOD; ++m) row_kl[m] = 0.f;
-    float row_assoc = 0.f;
-    for (int k = 0; k < nz; ++k) {
-      const float e = a.eps[r * nz + k];
-      float mu[NMOD], lv[NMOD], ex[NMOD];
-#pragma unroll
-      for (int m = 0; m < NMOD; ++m) {
-        mu[m] = a.heads[m][r * 2 * nz + k];
-        lv[m] = a.heads[m][r * 2 * nz + nz + k];
-        ex[m] = expf(lv[m]);
-        const float zv = mu[m] + sqrtf(ex[m]) * e;                             // :102-103
-        a.z[m][r * nz + k] = a.round_z ? round_tf32(zv) : zv;
-        row_kl[m] += 1.0f + lv[m] - mu[m] * mu[m] - ex[m];                     // :335-337 (element)
-      }
-      float gmu[NMOD], glv[NMOD];
-#pragma unroll
-      for (int m = 0; m < NMOD; ++m) {
-        const float w = a.weight[m] * a.inv_global_batch;
-        gmu[m] = w * mu[m];
-        glv[m] = w * 0.5f * (ex[m] - 1.0f);
-      }
-#pragma unroll
-      for (int p = 0; p < NMOD; ++p) {
-#pragma unroll
-        for (int q = p + 1; q < NMOD; ++q) {                                    // itertools.combinations, :346
-          const float d = mu[p] - mu[q];
-          const float ip = expf(-lv[p]), iq = expf(-lv[q]);
-          const float epq = expf(lv[p] - lv[q]), eqp = expf(lv[q] - lv[p]);
-          // 0.5*(lq - lp - 1 + e^{lp-lq} + d^2 e^{-lq}) + 0.5*(lp - lq - 1 + e^{lq-lp} + d^2 e^{-lp})   :355-365
-          row_assoc += 0.5f * (epq + eqp - 2.0f + d * d * (ip + iq));
-          gmu[p] += a.lambda * d * (ip + iq);
-          gmu[q] -= a.lambda * d * (ip + iq);
-          glv[p] += a.lambda * 0.5f * (epq - eqp - d * d * ip);
-          glv[q] += a.lambda * 0.5f * (eqp - epq - d * d * iq);
-        }
-      }
-      if (a.with_grad) {
-#pragma unroll
-        for (int m = 0; m < NMOD; ++m) {
-          a.gstat[m][r * 2 * nz + k] = gmu[m];
-          a.gstat[m][r * 2 * nz + nz + k] = glv[m];
-        }
-      }
-    }
-#pragma unroll
-    for (int m = 0; m < NMOD; ++m) {
-      const float kl = -0.5f * row_kl[m];
-      if (a.latent_loss[m]) a.latent_loss[m][r] = kl;                          // vae_latent_losses probe, :339
-      s_lat[m] += kl;
-    }
+    for (int m = 0; m < NMOD; ++m) s_lat[m] += row_kl[m];
     s_assoc += row_assoc;
   }
   // deterministic block partials
@@ -178,17 +129,10 @@ __global__ void __launch_bounds__(256) latent_bwd_kernel(LatentBwdArgs a) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / nz;
     const int k = (int)(i - r * nz);
-    const float e = a.eps[i];
 #pragma unroll
     for (int m = 0; m < NMOD; ++m) {
-      const float lv = a.heads[m][r * 2 * nz + nz + k];
-      const float s = sqrtf(expf(lv));                                         // d z / d lv = eps * s / 2
-      const float dz = a.dz[m][i];
-      float dm = dz + a.gstat[m][r * 2 * nz + k];
-      float dl = dz * e * 0.5f * s + a.gstat[m][r * 2 * nz + nz + k];
-      if (a.round_out) { dm = round_tf32(dm); dl = round_tf32(dl); }
-      a.dheads[m][r * 2 * nz + k] = dm;
-      a.dheads[m][r * 2 * nz + nz + k] = dl;
+      float dm, dl;
+      latent_bwd_elem<LoadPlain>(a, m, r, k, dm, dl);
     }
   }
 }
