@@ -267,7 +267,43 @@ def secondary_runs(local_rank):
             torch.cuda.empty_cache()
         except Exception as e:      # a secondary line must never take the headline down
             out.append(dict(name=name, error=str(e)[:300]))
+    out.append(inference_run())
     return out, sampler.stop()
+
+
+def inference_run(B=100, calls=200):
+    """The inference surface at the callers' batch (baxter_vae_assoc_writer.py:142-145 pads to a full batch of 100):
+    wall-clock per call of transform / generate / reconstruct with HOST arrays in and out -- vaeassoc_infer_host: one
+    graph launch + one D2H per call -- next to the per-modality device entry points + .cpu() copies (round 1)."""
+    import torch
+    from vae_assoc_b200 import vae_assoc
+    try:
+        archs = ref_archs()
+        model = vae_assoc.AssocVariationalAutoEncoder(archs, [True, False], transfer_fct=vae_assoc.relu, weights=[50, 1],
+                                                      assoc_lambda=8, learning_rate=1e-3, batch_size=B, precision="tf32", seed=0)
+        X = [x.cpu().numpy() for x in model.synth_batch(0, B)]
+        Xd = [torch.as_tensor(x).cuda() for x in X]
+        z = np.random.RandomState(0).normal(size=(B, archs[0]["n_z"])).astype(np.float32)
+        zd = torch.as_tensor(z).cuda()
+        res = dict(name="inference_b%d" % B, per_gpu_batch=B, dtype="tf32", calls=calls, unit="ms per call (wall clock, host arrays out)")
+        for label, fn_host, fn_dev in (("transform", lambda: model.transform(X), lambda: model.transform(Xd)),
+                                       ("generate", lambda: model.generate(z), lambda: model.generate(zd)),
+                                       ("reconstruct", lambda: model.reconstruct(X), lambda: model.reconstruct(Xd))):
+            for tag, fn in (("", fn_host), ("_device_entry_points", fn_dev)):
+                for _ in range(10):
+                    fn()
+                model.synchronize()
+                t0 = time.perf_counter()
+                l0 = model.launch_count()
+                for _ in range(calls):
+                    fn()
+                model.synchronize()
+                res[label + tag + "_ms"] = (time.perf_counter() - t0) * 1e3 / calls
+                res[label + tag + "_launches"] = (model.launch_count() - l0) / float(calls)
+        model.close()
+        return res
+    except Exception as e:
+        return dict(name="inference_b%d" % B, error=str(e)[:300])
 
 
 def main():

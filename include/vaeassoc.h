@@ -152,6 +152,14 @@ int vaeassoc_decode(vaeassoc_handle h, int modality, const float* z_dev, float* 
 /* reconstruct (vae_assoc.py:421-425): encode + sample + decode of ONE modality */
 int vaeassoc_reconstruct(vaeassoc_handle h, int modality, const float* x_dev, int64_t ld, const float* eps_dev,
                          float* xhat_dev);
+/* The same three entry points for HOST callers (what baxter_vae_assoc_writer.py:142-145 and vae_assoc_model_viewer.py:113
+ * pass: numpy arrays): ONE call = the inputs' H2D, the forward launches of every requested modality, packing and ONE
+ * D2H, captured as one CUDA graph per (kind, modality set); blocking.  kind 0 transform: x_host[m] -> out_host[m] =
+ * z_mean [B, n_z]; kind 1 generate: z_or_eps_host = z [B, n_z] -> out_host[m] = x_reconstr_mean [B, n_input_m];
+ * kind 2 reconstruct: x_host[m] (+ optional injected eps [B, n_z], NULL = Philox) -> out_host[m].  modality -1 = all
+ * modalities (dense tf32 models then run the fused encoder / decoder / whole-forward launch of the tile kernel). */
+int vaeassoc_infer_host(vaeassoc_handle h, int kind, int modality, const float* const* x_host, const float* z_or_eps_host,
+                        float* const* out_host);
 
 /* the probe points of vae_assoc.py:545-571 after the most recent step.  kind: */
 enum {
@@ -212,6 +220,10 @@ int vaeassoc_peer_export(vaeassoc_handle h, void* blob /* VAEASSOC_PEER_BLOB_BYT
 int vaeassoc_peer_attach(vaeassoc_handle h, const void* all_blobs /* world x VAEASSOC_PEER_BLOB_BYTES, rank order */);
 int vaeassoc_peer_detach(vaeassoc_handle h);
 int vaeassoc_peer_active(vaeassoc_handle h);      /* 1 while the peer-memory step is in use */
+
+/* Own bounds check (debug): every device buffer of the handle ends in a 256-byte guard pattern that no kernel may
+ * write; reports how many guards exist and how many no longer hold the pattern (0 expected, tests/test_gpu_parity.py). */
+int vaeassoc_debug_guard_check(vaeassoc_handle h, int64_t* n_guards, int64_t* n_corrupt);
 
 /* ---- checkpoints: tf.train.Saver.save / .restore over ALL variables incl. the Adam slots (vae_assoc.py:70,427-463) --
  * One self-describing binary file ("VAEASSOC" magic, tensor table with the TF-style names, parameters, both Adam

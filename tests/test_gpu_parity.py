@@ -122,6 +122,9 @@ def check_step(model, oracle, X, eps, tol, grads=True, grad_tol=None):
         for g, r, n in zip(model.get_grads(), flat_ref, model.variable_roles()):
             assert g.shape == r.shape
             assert rel(g, r) < (grad_tol or tol), (n, rel(g, r))
+    # the library's own bounds check: no kernel of the step wrote past the end of any device buffer
+    n_guards, n_corrupt = model.guard_check()
+    assert n_guards > 40 and n_corrupt == 0, (n_guards, n_corrupt)
 
 
 @pytest.mark.parametrize("f", ["relu", "softplus"])
@@ -240,25 +243,45 @@ def test_odd_shapes_and_three_modalities(va):
     model.close()
 
 
-def test_inference_surface(va):
-    """evaluate_cost / transform / generate / reconstruct (vae_assoc.py:388-425) against the oracle."""
+@pytest.mark.parametrize("precision,batch", [("fp32", 64), ("tf32", 64), ("tf32", 100)])
+def test_inference_surface(va, precision, batch):
+    """evaluate_cost / transform / generate / reconstruct (vae_assoc.py:388-425) against the oracle.  Host arrays (what
+    the reference's callers pass) go through vaeassoc_infer_host: ONE graph launch per call -- H2D, the forward launches
+    of all modalities (tf32: the fused encoder / decoder / whole-forward launch of the tile kernel), packing, ONE D2H;
+    CUDA tensors take the per-modality device entry points.  Both must agree with the oracle and with each other."""
+    import torch
     archs = vo.reference_archs(4)
-    batch = 64
-    model, oracle = make_pair(va, archs, batch, "relu", "fp32", seed=2)
+    tol = TOL[precision]
+    model, oracle = make_pair(va, archs, batch, "relu", precision, seed=2, emulate=False)
     X, eps = inputs(archs, batch, 2)
-    assert abs(model.evaluate_cost(X, eps) - oracle.evaluate_cost(X, eps)) <= 1e-4 * abs(oracle.evaluate_cost(X, eps))
+    Xd = [torch.as_tensor(x).cuda() for x in X]
+    assert abs(model.evaluate_cost(X, eps) - oracle.evaluate_cost(X, eps)) <= tol * abs(oracle.evaluate_cost(X, eps))
     zt, zo = model.transform(X), oracle.transform(X)
-    for a, b in zip(zt, zo):
-        assert a.shape == (batch, 4) and rel(a, b) < 1e-4
-    assert rel(model.transform(X[0], sens_idx=0), zo[0]) < 1e-4
+    for a, b, c in zip(zt, zo, model.transform(Xd)):
+        assert a.shape == (batch, 4) and rel(a, b) < tol and rel(a, c) < 1e-6
+    assert rel(model.transform(X[0], sens_idx=0), zo[0]) < tol
+    assert rel(model.transform(X[1], sens_idx=1), zo[1]) < tol
     z_mu = np.zeros((batch, 4), np.float32); z_mu[0] = [0.5, -1.0, 2.0, 0.1]     # viewer pattern: row 0 only
     go, gr = model.generate(z_mu=z_mu), oracle.generate(z_mu)
-    for a, b in zip(go, gr):
-        assert rel(a, b) < 1e-4
+    for a, b, c in zip(go, gr, model.generate(z_mu=torch.as_tensor(z_mu).cuda())):
+        assert rel(a, b) < tol and rel(a, c) < 1e-6
     assert [g.shape for g in model.generate()] == [(batch, 784), (batch, 147)]
     ro, rr = model.reconstruct(X, eps=eps), oracle.reconstruct(X, eps=eps)
-    for a, b in zip(ro, rr):
-        assert rel(a, b) < 1e-4
+    for a, b, c in zip(ro, rr, model.reconstruct(Xd, eps=eps)):
+        assert rel(a, b) < tol and rel(a, c) < 1e-6
+    # one call = one graph launch; on the tensor-core path the graph holds at most 8 nodes (2 H2D, staging, ONE tile-kernel
+    # launch, 2 packing copies, 1 D2H) against 3 launches per modality and layer on the device entry points
+    n0 = model.launch_count()
+    model.transform(X)
+    n_host = model.launch_count() - n0
+    n0 = model.launch_count()
+    model.transform(Xd)
+    n_dev = model.launch_count() - n0
+    if precision == "tf32":
+        assert n_host < n_dev, (n_host, n_dev)
+    # inference leaves training untouched: a step afterwards still matches the oracle
+    c, c_ref = model.partial_fit(X, eps), oracle.partial_fit(X, eps)
+    assert abs(c - c_ref) <= tol * abs(c_ref)
     model.close()
 
 

@@ -75,6 +75,7 @@ SIGNATURES = {
     "vaeassoc_encode": (C.c_int, [Handle, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "vaeassoc_decode": (C.c_int, [Handle, C.c_int, C.c_void_p, C.c_void_p]),
     "vaeassoc_reconstruct": (C.c_int, [Handle, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "vaeassoc_infer_host": (C.c_int, [Handle, C.c_int, C.c_int, FloatPP, C.c_void_p, FloatPP]),
     "vaeassoc_probe_get": (C.c_int, [Handle, C.c_int, C.c_int, C.c_void_p, C.c_int64, I64P]),
     "vaeassoc_probe_mask": (C.c_int, [Handle, C.c_int, C.c_int, C.c_void_p, C.c_int64, I64P, I64P]),
     "vaeassoc_synth_batch": (C.c_int, [Handle, C.c_uint32, C.c_uint32, C.c_int64, C.c_int64, FloatPP]),
@@ -89,6 +90,7 @@ SIGNATURES = {
     "vaeassoc_peer_attach": (C.c_int, [Handle, C.c_void_p]),
     "vaeassoc_peer_detach": (C.c_int, [Handle]),
     "vaeassoc_peer_active": (C.c_int, [Handle]),
+    "vaeassoc_debug_guard_check": (C.c_int, [Handle, I64P, I64P]),
     "vaeassoc_save": (C.c_int, [Handle, C.c_char_p]),
     "vaeassoc_load": (C.c_int, [Handle, C.c_char_p]),
     "vaeassoc_launch_count": (C.c_int64, [Handle]),

@@ -194,6 +194,16 @@ struct vaeassoc_ctx {
   cudaGraphExec_t graph_train = nullptr, graph_grad = nullptr, graph_a1 = nullptr, graph_a2 = nullptr,
                   graph_adam = nullptr;
   int graph_train_nodes = 0, graph_grad_nodes = 0, graph_a1_nodes = 0, graph_a2_nodes = 0, graph_adam_nodes = 0;
+  // inference surface with host buffers (vaeassoc_infer_host): per (kind, modality set) one captured graph =
+  // H2D of the inputs, the forward launches, packing of the results, ONE D2H
+  struct Infer {
+    float* pin_in = nullptr;  float* pin_out = nullptr;     // pinned staging, sized for a full batch of every modality
+    float* xin[VAEASSOC_MAX_MODALITIES] = {nullptr, nullptr, nullptr, nullptr};   // device: dense [B, n_input_m]
+    float* zin = nullptr;     // device: [B, n_z] (z of generate / injected eps of reconstruct)
+    float* pack = nullptr;    // device: results of all modalities, contiguous
+    cudaGraphExec_t graph[3][1 << VAEASSOC_MAX_MODALITIES][2] = {};   // [kind][modality mask][eps injected]
+    int nodes[3][1 << VAEASSOC_MAX_MODALITIES][2] = {};
+  } inf;
   // comm
   void* comm = nullptr;
   int rank = 0, world = 1;
@@ -211,27 +221,44 @@ struct vaeassoc_ctx {
     bool slots_stale = false;         // m / v of the shards owned by peers are behind (refreshed on demand)
   } peer;
 
+  // Own bounds check (compute-sanitizer is closed on the GPU pool): every device buffer is followed by a 256-byte guard
+  // filled with kGuardByte; nothing in the library may WRITE there (the 3-D tensor maps of MN-major GEMM operands may
+  // READ up to 124 B past the last row, gemm_group.cu -- those lanes only feed clipped outputs).
+  // vaeassoc_debug_guard_check compares every guard with the pattern.
+  static constexpr int kGuardBytes = 256;
+  static constexpr int kGuardByte = 0x2b;        // 0x2b2b2b2b as a float is 6.1e-13: harmless where a guard is read
+  std::vector<std::pair<char*, size_t>> guards;
+  void add_guard(void* addr, size_t len) {
+    CUDA_OK(cudaMemset(addr, kGuardByte, len));
+    guards.emplace_back(reinterpret_cast<char*>(addr), len);
+  }
   template <typename T>
   T* dalloc(int64_t n, bool zero = true) {
     void* ptr = nullptr;
-    // + 256 B: the 3-D tensor maps of MN-major GEMM operands may read up to 124 B past the last row (gemm_group.cu)
-    const size_t bytes = (size_t)std::max<int64_t>(n, 1) * sizeof(T) + 256;
+    const size_t payload = (size_t)std::max<int64_t>(n, 1) * sizeof(T);
+    const size_t bytes = payload + kGuardBytes;
     CUDA_OK(cudaMalloc(&ptr, bytes));
     if (zero) CUDA_OK(cudaMemset(ptr, 0, bytes));
     allocs.push_back(ptr);
+    add_guard(reinterpret_cast<char*>(ptr) + payload, kGuardBytes);
     return reinterpret_cast<T*>(ptr);
   }
   // zero-initialised workspace owned by one op of the schedule: ops of different streams never share one
   float* op_ws(int64_t floats) {
     if (floats <= 0) return nullptr;
     void* ptr = nullptr;
-    CUDA_OK(cudaMalloc(&ptr, (size_t)floats * sizeof(float)));
+    CUDA_OK(cudaMalloc(&ptr, (size_t)floats * sizeof(float) + kGuardBytes));
     CUDA_OK(cudaMemset(ptr, 0, (size_t)floats * sizeof(float)));
     op_allocs.push_back(ptr);
+    char* gaddr = reinterpret_cast<char*>(ptr) + (size_t)floats * sizeof(float);
+    CUDA_OK(cudaMemset(gaddr, kGuardByte, kGuardBytes));
+    op_guards.emplace_back(gaddr, (size_t)kGuardBytes);
     return reinterpret_cast<float*>(ptr);
   }
+  std::vector<std::pair<char*, size_t>> op_guards;   // guards of the per-op workspaces (rebuilt with the ops)
   void free_op_ws() {
     for (void* p : op_allocs) cudaFree(p);
+    op_guards.clear();
     op_allocs.clear();
   }
 };
@@ -429,6 +456,10 @@ void alloc_buffers(Ctx* c) {
     c->v = c->arena + 3 * slot;
     c->p_tf32 = c->arena + 4 * slot;
     c->peer.flags = reinterpret_cast<uint32_t*>(c->arena + 5 * slot);   // 2 x kMaxPeers arrival words, then sync[2]
+    for (int i = 0; i < 5; ++i) {           // the slack behind each flat buffer doubles as its guard
+      const int64_t used = (i == 1) ? c->n_flat + 32 : c->n_flat;
+      c->add_guard(c->arena + i * slot + used, (size_t)(slot - used) * sizeof(float));
+    }
   }
   {
     // row-block counters: 12 activation / gradient tensors per modality x row blocks of 256; then the launch sites
@@ -448,6 +479,17 @@ void alloc_buffers(Ctx* c) {
   c->last_cost = c->dalloc<float>(1);
   c->step_dev = c->dalloc<int64_t>(1);
   CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&c->host_cost_ring), sizeof(float) * Ctx::kHostRing));
+  {
+    int64_t width = 0;
+    for (int m = 0; m < c->cfg.n_modalities; ++m) {
+      c->inf.xin[m] = c->dalloc<float>(B * c->mods[m].ni);
+      width += c->mods[m].ni;
+    }
+    c->inf.zin = c->dalloc<float>(B * nz);
+    c->inf.pack = c->dalloc<float>(B * width);
+    CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&c->inf.pin_in), sizeof(float) * (size_t)(B * (width + nz))));
+    CUDA_OK(cudaMallocHost(reinterpret_cast<void**>(&c->inf.pin_out), sizeof(float) * (size_t)(B * width)));
+  }
   for (Mod& d : c->mods) {
     d.xin[0] = c->dalloc<float>(B * d.ni);
     d.xin[1] = c->dalloc<float>(B * d.ni);
@@ -588,6 +630,12 @@ void destroy_graphs(Ctx* c) {
     if (*g) cudaGraphExecDestroy(*g);
     *g = nullptr;
   }
+  for (auto& k : c->inf.graph)
+    for (auto& mk : k)
+      for (cudaGraphExec_t& g : mk) {
+        if (g) cudaGraphExecDestroy(g);
+        g = nullptr;
+      }
 }
 
 // ---- hidden_conv=True modality: conv / deconv layers as im2col -> GEMM -> col2im (conv.cu) ------------------------
@@ -967,7 +1015,10 @@ void build_segments(Ctx* c) {
     c->fused = true;
     // ---- two-launch form: latent stages as elementwise tasks between the encoder and decoder layers ----
     c->elt_built = false;
-    if (M <= 2 && RB * 8 <= kMaxPartialBlocks && !nodeps && !getenv("VAEASSOC_NO_ELT")) {
+    // (a latent task is one thread per batch row, serial over n_z: at n_z = 64 it costs more on the critical path of its
+    // row block than the stand-alone kernel spread over all SMs -- measured 3.86 against 3.52 ms per step at the scaled
+    // config -- so wide latents keep the four-launch form)
+    if (M <= 2 && c->cfg.n_z <= 16 && RB * 8 <= kMaxPartialBlocks && !nodeps && !getenv("VAEASSOC_NO_ELT")) {
       GElem el;
       el.lf = c->lat_fwd_args;
       el.lb = c->lat_bwd_args;
@@ -1531,6 +1582,8 @@ int vaeassoc_destroy(vaeassoc_handle h) {
   for (void* p : h->allocs) cudaFree(p);
   h->free_op_ws();
   if (h->host_cost_ring) cudaFreeHost(h->host_cost_ring);
+  if (h->inf.pin_in) cudaFreeHost(h->inf.pin_in);
+  if (h->inf.pin_out) cudaFreeHost(h->inf.pin_out);
   for (int i = 0; i < 2; ++i) {
     if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
     if (h->ev_consumed[i]) cudaEventDestroy(h->ev_consumed[i]);
@@ -2024,6 +2077,132 @@ int vaeassoc_probe_mask(vaeassoc_handle h, int layer, int modality, uint32_t* ds
 
 }  // extern "C"
 
+// ---- inference surface with host buffers: transform / generate / reconstruct as ONE graph launch + ONE D2H -----------
+namespace {
+enum { INF_TRANSFORM = 0, INF_GENERATE = 1, INF_RECONSTRUCT = 2 };
+
+// the launches of one inference call (captured once per kind / modality set); inputs sit in pin_in, results go to pin_out
+void enqueue_infer(Ctx* c, int kind, unsigned mask, bool eps_given, cudaStream_t s) {
+  const int M = c->cfg.n_modalities;
+  const int64_t B = c->cfg.batch_size;
+  const int nz = c->cfg.n_z;
+  const bool all = mask == (1u << M) - 1u;
+  // 1. host -> device (pinned source: asynchronous DMA inside the graph)
+  int64_t off = 0;
+  const float* xs[VAEASSOC_MAX_MODALITIES] = {nullptr, nullptr, nullptr, nullptr};
+  int64_t lds[VAEASSOC_MAX_MODALITIES] = {0, 0, 0, 0};
+  if (kind != INF_GENERATE) {
+    for (int m = 0; m < M; ++m) {
+      const int64_t n = B * c->mods[m].ni;
+      if (mask & (1u << m)) {
+        CUDA_OK(cudaMemcpyAsync(c->inf.xin[m], c->inf.pin_in + off, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+        xs[m] = c->inf.xin[m]; lds[m] = c->mods[m].ni;
+      }
+      off += n;
+    }
+  } else {
+    for (int m = 0; m < M; ++m) off += B * c->mods[m].ni;
+  }
+  const bool z_in = kind == INF_GENERATE || (kind == INF_RECONSTRUCT && eps_given);
+  if (z_in) CUDA_OK(cudaMemcpyAsync(c->inf.zin, c->inf.pin_in + off, (size_t)(B * nz) * 4, cudaMemcpyHostToDevice, s));
+  // 2. forward
+  if (kind == INF_TRANSFORM) {
+    stage_inputs(c, xs, lds, nullptr, s, -1, /*want_eps=*/false);
+    if (all && c->fused) launch_seg(c, c->seg_enc, s);
+    else for (int m = 0; m < M; ++m) if (mask & (1u << m)) run_ops(c, c->ops_enc_mod[m], s);
+  } else if (kind == INF_GENERATE) {
+    for (int m = 0; m < M; ++m)
+      if (mask & (1u << m)) CUDA_OK(cudaMemcpyAsync(c->mods[m].z, c->inf.zin, (size_t)(B * nz) * 4, cudaMemcpyDeviceToDevice, s));
+    if (all && c->fused) launch_seg(c, c->seg_dec, s);
+    else for (int m = 0; m < M; ++m) if (mask & (1u << m)) run_ops(c, c->ops_dec_mod[m], s);
+  } else {
+    stage_inputs(c, xs, lds, eps_given ? c->inf.zin : nullptr, s, -1, /*want_eps=*/true);
+    if (all && elt_mode(c)) {
+      launch_seg(c, c->seg_fwd, s);          // encoders, latent stage and decoders of every modality: one launch
+    } else {
+      for (int m = 0; m < M; ++m) {
+        if (!(mask & (1u << m))) continue;
+        const Mod& d = c->mods[m];
+        run_ops(c, c->ops_enc_mod[m], s);
+        LatentArgs a;
+        a.n_mod = 1; a.batch = (int)B; a.n_z = nz; a.inv_global_batch = 0.f; a.lambda = 0.f;
+        a.weight[0] = 0.f; a.heads[0] = d.hd; a.z[0] = d.z; a.gstat[0] = d.gstat; a.latent_loss[0] = nullptr;
+        a.eps = c->eps; a.partials = c->lat_partials; a.with_grad = 0; a.round_z = c->round_z ? 1 : 0;
+        launch_latent_fwd(a, s);
+        c->launches += 1;
+        run_ops(c, c->ops_dec_mod[m], s);
+      }
+    }
+  }
+  // 3. pack the results of the requested modalities, 4. ONE device -> host copy
+  int64_t total = 0;
+  for (int m = 0; m < M; ++m) {
+    if (!(mask & (1u << m))) continue;
+    const Mod& d = c->mods[m];
+    if (kind == INF_TRANSFORM) {
+      CUDA_OK(cudaMemcpy2DAsync(c->inf.pack + total, (size_t)nz * 4, d.hd, (size_t)d.nh * 4, (size_t)nz * 4, (size_t)B,
+                                cudaMemcpyDeviceToDevice, s));
+      total += B * nz;
+    } else {
+      CUDA_OK(cudaMemcpy2DAsync(c->inf.pack + total, (size_t)d.ni * 4, d.xh, (size_t)d.nip * 4, (size_t)d.ni * 4, (size_t)B,
+                                cudaMemcpyDeviceToDevice, s));
+      total += B * d.ni;
+    }
+  }
+  CUDA_OK(cudaMemcpyAsync(c->inf.pin_out, c->inf.pack, (size_t)total * 4, cudaMemcpyDeviceToHost, s));
+}
+}  // namespace
+
+extern "C" {
+
+int vaeassoc_infer_host(vaeassoc_handle h, int kind, int modality, const float* const* x_host, const float* z_or_eps_host,
+                        float* const* out_host) {
+  API_BEGIN(h)
+  const int M = h->cfg.n_modalities;
+  const int64_t B = h->cfg.batch_size;
+  const int nz = h->cfg.n_z;
+  if (kind < INF_TRANSFORM || kind > INF_RECONSTRUCT) fail("kind must be 0 (transform), 1 (generate) or 2 (reconstruct)");
+  if (modality >= M) fail("modality %d out of range", modality);
+  if (!out_host) fail("out_host is null");
+  const unsigned mask = modality < 0 ? (1u << M) - 1u : 1u << modality;
+  if (kind == INF_GENERATE && !z_or_eps_host) fail("generate needs z_host [batch, n_z]");
+  const bool eps_given = kind == INF_RECONSTRUCT && z_or_eps_host != nullptr;
+  // inputs -> pinned staging (the graph's H2D nodes read it)
+  int64_t off = 0;
+  for (int m = 0; m < M; ++m) {
+    const int64_t n = B * h->mods[m].ni;
+    if (kind != INF_GENERATE && (mask & (1u << m))) {
+      if (!x_host || !x_host[m]) fail("x_host[%d] is null", m);
+      memcpy(h->inf.pin_in + off, x_host[m], (size_t)n * 4);
+    }
+    if ((mask & (1u << m)) && !out_host[m]) fail("out_host[%d] is null", m);
+    off += n;
+  }
+  if (z_or_eps_host && kind != INF_TRANSFORM) memcpy(h->inf.pin_in + off, z_or_eps_host, (size_t)(B * nz) * 4);
+  cudaStream_t s = h->stream;
+  refresh_shadow(h, s);
+  if (h->cfg.use_graph) {
+    cudaGraphExec_t& g = h->inf.graph[kind][mask][eps_given ? 1 : 0];
+    int& nodes = h->inf.nodes[kind][mask][eps_given ? 1 : 0];
+    if (!g) nodes = capture(h, &g, [&](cudaStream_t cs) { enqueue_infer(h, kind, mask, eps_given, cs); });
+    CUDA_OK(cudaGraphLaunch(g, s));
+    h->launches += nodes;
+  } else {
+    enqueue_infer(h, kind, mask, eps_given, s);
+  }
+  CUDA_OK(cudaStreamSynchronize(s));
+  int64_t total = 0;
+  for (int m = 0; m < M; ++m) {
+    if (!(mask & (1u << m))) continue;
+    const int64_t n = B * (kind == INF_TRANSFORM ? nz : h->mods[m].ni);
+    memcpy(out_host[m], h->inf.pin_out + total, (size_t)n * 4);
+    total += n;
+  }
+  API_END(h)
+}
+
+}  // extern "C"
+
 // ---- peer-memory data-parallel step (peer_adam.cu) ------------------------------------------------------------------
 namespace {
 struct PeerBlob {                 // what a rank publishes: VAEASSOC_PEER_BLOB_BYTES
@@ -2135,6 +2314,24 @@ int vaeassoc_peer_detach(vaeassoc_handle h) {
 }
 
 int vaeassoc_peer_active(vaeassoc_handle h) { return (h && h->peer.on) ? 1 : 0; }
+
+int vaeassoc_debug_guard_check(vaeassoc_handle h, int64_t* n_guards, int64_t* n_corrupt) {
+  API_BEGIN(h)
+  CUDA_OK(cudaDeviceSynchronize());
+  int64_t bad = 0;
+  std::vector<unsigned char> host;
+  for (const auto* vec : {&h->guards, &h->op_guards}) {
+    for (const auto& g : *vec) {
+      host.resize(g.second);
+      CUDA_OK(cudaMemcpy(host.data(), g.first, g.second, cudaMemcpyDeviceToHost));
+      for (unsigned char b : host)
+        if (b != (unsigned char)Ctx::kGuardByte) { ++bad; break; }
+    }
+  }
+  if (n_guards) *n_guards = (int64_t)(h->guards.size() + h->op_guards.size());
+  if (n_corrupt) *n_corrupt = bad;
+  API_END(h)
+}
 
 }  // extern "C"
 

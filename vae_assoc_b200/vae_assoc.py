@@ -222,6 +222,13 @@ class AssocVariationalAutoEncoder(object):
         self._check(self._lib.vaeassoc_set_precision(self._h, {"fp32": L.FP32, "tf32": L.TF32}[precision]))
         self.precision = precision
 
+    def guard_check(self):
+        """(number of guard regions, number corrupted): every device buffer of the handle ends in a 256-byte pattern that
+        no kernel may write (the library's own bounds check; compute-sanitizer is closed on the GPU pool)."""
+        n, bad = C.c_int64(), C.c_int64()
+        self._check(self._lib.vaeassoc_debug_guard_check(self._h, C.byref(n), C.byref(bad)))
+        return int(n.value), int(bad.value)
+
     def launch_count(self):
         return int(self._lib.vaeassoc_launch_count(self._h))
 
@@ -409,18 +416,60 @@ class AssocVariationalAutoEncoder(object):
                                               C.c_void_p(mu.data_ptr()), None))
         return mu.cpu().numpy()
 
+    def _infer_host(self, kind, modality, X, z_or_eps, widths):
+        """transform / generate / reconstruct for host arrays: one graph launch + one D2H (vaeassoc_infer_host)."""
+        M = len(self.network_architectures)
+        ptrs = (C.c_void_p * L.MAX_MODALITIES)()
+        outs = (C.c_void_p * L.MAX_MODALITIES)()
+        keep, res = [], [None] * M
+        mods = range(M) if modality < 0 else [modality]
+        for m in mods:
+            if X is not None:
+                a = np.ascontiguousarray(X[m], dtype=np.float32)
+                assert a.shape == (self.batch_size, self.network_architectures[m]["n_input"]), \
+                    "modality %d: expected %s, got %s (the batch size is static, vae_assoc.py:90)" % (
+                        m, (self.batch_size, self.network_architectures[m]["n_input"]), a.shape)
+                keep.append(a)
+                ptrs[m] = a.ctypes.data
+            res[m] = np.empty((self.batch_size, widths[m]), np.float32)
+            outs[m] = res[m].ctypes.data
+        zp = None
+        if z_or_eps is not None:
+            z = np.ascontiguousarray(z_or_eps, dtype=np.float32)
+            assert z.shape == (self.batch_size, self.n_z), \
+                "z / eps must be [batch_size, n_z] (the reference's callers pad to a full batch, baxter_vae_assoc_writer.py:142-145)"
+            keep.append(z)
+            zp = z.ctypes.data_as(C.c_void_p)
+        self._check(self._lib.vaeassoc_infer_host(self._h, kind, modality, ptrs if X is not None else None, zp, outs))
+        return res
+
+    def _all_host(self, X):
+        t = self._torch
+        return not any(t.is_tensor(x) and x.is_cuda for x in X)
+
     def transform(self, X, sens_idx=None):
         """Transform data by mapping it into the latent space (z_mean).  (vae_assoc.py:393-403)"""
         self._bind_stream()
+        M = len(self.network_architectures)
         if sens_idx is None:
+            if self._all_host(X):
+                return self._infer_host(0, -1, [x.cpu().numpy() if self._torch.is_tensor(x) else x for x in X], None,
+                                        [self.n_z] * M)
             return [self._encode(m, x) for m, x in enumerate(X)]
-        assert sens_idx < len(self.network_architectures)
+        assert sens_idx < M
+        if self._all_host([X]):
+            Xs = [None] * M
+            Xs[sens_idx] = X.cpu().numpy() if self._torch.is_tensor(X) else X
+            return self._infer_host(0, sens_idx, Xs, None, [self.n_z] * M)[sens_idx]
         return self._encode(sens_idx, X)
 
     def generate(self, z_mu=None):
         """Generate data by sampling from latent space; z feeds the decoders directly.  (vae_assoc.py:405-419)"""
         self._bind_stream()
         t = self._torch
+        widths = [na["n_input"] for na in self.network_architectures]
+        if z_mu is not None and not (t.is_tensor(z_mu) and z_mu.is_cuda):
+            return self._infer_host(1, -1, None, z_mu.cpu().numpy() if t.is_tensor(z_mu) else z_mu, widths)
         if z_mu is None:
             # the reference draws np.random.normal((batch_size, n_z)) (:414); here Philox on the device
             z = t.empty((self.batch_size, self.n_z), dtype=t.float32, device=self._dev)
@@ -428,8 +477,7 @@ class AssocVariationalAutoEncoder(object):
                                                          self._prior_draws, C.c_void_p(z.data_ptr())))
             self._prior_draws += 1
         else:
-            z = t.as_tensor(np.ascontiguousarray(z_mu, dtype=np.float32)).to(self._dev) if not t.is_tensor(z_mu) \
-                else z_mu.to(self._dev, t.float32).contiguous()
+            z = z_mu.to(self._dev, t.float32).contiguous()
         assert tuple(z.shape) == (self.batch_size, self.n_z), \
             "z_mu must be [batch_size, n_z] (the reference's callers pad to a full batch, baxter_vae_assoc_writer.py:142-145)"
         out = []
@@ -443,6 +491,11 @@ class AssocVariationalAutoEncoder(object):
         """Use VAE to reconstruct given data: one encode+sample+decode per modality.  (vae_assoc.py:421-425)"""
         self._bind_stream()
         t = self._torch
+        shared_eps = eps is None or not isinstance(eps, (list, tuple))
+        if self._all_host(X) and shared_eps and not (t.is_tensor(eps) and eps.is_cuda):
+            e = eps.cpu().numpy() if t.is_tensor(eps) else eps
+            return self._infer_host(2, -1, [x.cpu().numpy() if t.is_tensor(x) else x for x in X], e,
+                                    [na["n_input"] for na in self.network_architectures])
         out = []
         for m, x in enumerate(X):
             na = self.network_architectures[m]
