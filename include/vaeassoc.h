@@ -218,6 +218,15 @@ int vaeassoc_comm_check(vaeassoc_handle h);
 #define VAEASSOC_PEER_BLOB_BYTES 128
 int vaeassoc_peer_export(vaeassoc_handle h, void* blob /* VAEASSOC_PEER_BLOB_BYTES */);
 int vaeassoc_peer_attach(vaeassoc_handle h, const void* all_blobs /* world x VAEASSOC_PEER_BLOB_BYTES, rank order */);
+/* The same step over SYMMETRIC memory (e.g. torch.distributed._symmetric_memory: identical allocation on every rank,
+ * mapped into every process, optionally bound to an NVSwitch multicast object): the library moves its flat buffers
+ * (vaeassoc_arena_floats floats) into `local_arena`, reaches rank r's through rank_arenas[r] and, when `multicast_arena`
+ * is non-null, reduces the gradients INSIDE the switch (multimem.ld_reduce) and broadcasts the updated parameters with one
+ * store per element (multimem.st) -- 1/world of the NVLink bytes of the plain peer form.  The caller keeps the memory
+ * alive until vaeassoc_destroy. */
+int64_t vaeassoc_arena_floats(vaeassoc_handle h);
+int vaeassoc_peer_attach_symmetric(vaeassoc_handle h, void* local_arena, const void* const* rank_arenas, void* multicast_arena);
+int vaeassoc_peer_multicast(vaeassoc_handle h);   /* 1 while the NVLS (multimem) form is in use */
 int vaeassoc_peer_detach(vaeassoc_handle h);
 int vaeassoc_peer_active(vaeassoc_handle h);      /* 1 while the peer-memory step is in use */
 

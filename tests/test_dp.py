@@ -80,8 +80,15 @@ def _nccl_worker(rank, world, port, out, precision, mode="nccl"):
     model = vae_assoc.AssocVariationalAutoEncoder(archs, [True, False], transfer_fct="relu", weights=[50, 1],
                                                   assoc_lambda=8, learning_rate=1e-3, batch_size=B, precision=precision,
                                                   seed=0, eps_seed=5, global_batch=Bg, global_row0=rank * B)
-    model.init_data_parallel(peer=(mode == "peer"))
-    assert model.dp_mode == mode, (model.dp_mode, getattr(model, "_peer_error", None))
+    # peer: cudaIpc mapping, plain peer loads / stores; peer-nvls: symmetric memory + multimem through the NVSwitch
+    os.environ["VAEASSOC_DP_SYMMETRIC"] = "1" if mode == "peer-nvls" else "0"
+    model.init_data_parallel(peer=(mode != "nccl"))
+    if mode == "peer-nvls" and model.dp_mode != "peer-nvls":
+        # no symmetric memory / multicast on this box: the library must have fallen back consistently on every rank
+        assert model.dp_mode in ("peer", "nccl")
+        print("[dp] NVLS form unavailable here: %s" % getattr(model, "_peer_error", None))
+    else:
+        assert model.dp_mode == mode, (model.dp_mode, getattr(model, "_peer_error", None))
     costs = []
     for t in range(4):
         xs = model.synth_batch(t * Bg + rank * B, B)
@@ -97,11 +104,13 @@ def _nccl_worker(rank, world, port, out, precision, mode="nccl"):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["nccl", "peer"])
+@pytest.mark.parametrize("mode", ["nccl", "peer", "peer-nvls"])
 @pytest.mark.parametrize("precision", ["fp32", "tf32"])
 def test_dp_matches_single_gpu(tmp_path, precision, mode):
     """nccl: ncclAllReduce of the flat gradients + replicated Adam; peer: the one-kernel reduce-scatter + sharded Adam +
-    all-gather over NVLink peer memory (csrc/peer_adam.cu).  Both must reproduce the single-GPU run."""
+    all-gather over NVLink peer memory (csrc/peer_adam.cu) through cudaIpc mappings; peer-nvls: the same kernel over
+    symmetric memory with the reduction done inside the NVSwitch (multimem.ld_reduce / multimem.st).  All must reproduce
+    the single-GPU run."""
     import torch
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")

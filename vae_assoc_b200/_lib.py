@@ -88,6 +88,9 @@ SIGNATURES = {
     "vaeassoc_comm_check": (C.c_int, [Handle]),
     "vaeassoc_peer_export": (C.c_int, [Handle, C.c_void_p]),
     "vaeassoc_peer_attach": (C.c_int, [Handle, C.c_void_p]),
+    "vaeassoc_arena_floats": (C.c_int64, [Handle]),
+    "vaeassoc_peer_attach_symmetric": (C.c_int, [Handle, C.c_void_p, FloatPP, C.c_void_p]),
+    "vaeassoc_peer_multicast": (C.c_int, [Handle]),
     "vaeassoc_peer_detach": (C.c_int, [Handle]),
     "vaeassoc_peer_active": (C.c_int, [Handle]),
     "vaeassoc_debug_guard_check": (C.c_int, [Handle, I64P, I64P]),

@@ -219,6 +219,11 @@ struct vaeassoc_ctx {
     cudaGraphExec_t graph = nullptr;  // a1 + a2 + peer_adam: the whole data-parallel step as one graph
     int graph_nodes = 0;
     bool slots_stale = false;         // m / v of the shards owned by peers are behind (refreshed on demand)
+    bool pending = false;             // the last step's kernel left without waiting for the peers' parameter stores:
+                                      // the next step's graph (or peer_quiesce) waits for them first
+    float* mc = nullptr;              // NVLS multicast address of the arena (symmetric attach), or null
+    bool symmetric = false;           // the arena lives in caller-provided symmetric memory (not cudaIpc-mapped)
+    unsigned long long* tl = nullptr; // VAEASSOC_PEER_TIMELINE: phase stamps summed on the device, printed at detach
   } peer;
 
   // Own bounds check (compute-sanitizer is closed on the GPU pool): every device buffer is followed by a 256-byte guard
@@ -266,6 +271,8 @@ struct vaeassoc_ctx {
 namespace {
 
 using Ctx = vaeassoc_ctx;
+void build_ops(Ctx* c);
+void peer_quiesce(Ctx* c);
 void peer_detach(Ctx* c);
 void refresh_peer_slots(Ctx* c);
 
@@ -1267,9 +1274,20 @@ void enqueue_peer_adam(Ctx* c, cudaStream_t s) {
     a.ptf_peer[r] = shadow ? b + (c->p_tf32 - c->arena) : nullptr;
     a.flag_peer[r] = reinterpret_cast<uint32_t*>(b + (reinterpret_cast<float*>(c->peer.flags) - c->arena));
   }
+  if (c->peer.mc) {
+    a.g_mc = c->peer.mc + (c->g - c->arena);
+    a.p_mc = c->peer.mc + (c->p - c->arena);
+    a.ptf_mc = shadow ? c->peer.mc + (c->p_tf32 - c->arena) : nullptr;
+  }
   a.sync = c->peer.flags + 2 * kMaxPeers;
   peer_shard(c, c->rank, &a.shard_lo, &a.shard_hi);
+  a.tl = c->peer.tl;
   launch_peer_adam(a, s);
+  c->launches += 1;
+}
+// every rank's parameter stores of the previous peer step have landed here, and every rank has read our gradients
+void enqueue_peer_wait(Ctx* c, cudaStream_t s) {
+  launch_peer_wait(c->peer.flags, c->peer.flags + 2 * kMaxPeers, c->world, s);
   c->launches += 1;
 }
 void allreduce(Ctx* c, float* buf, int64_t count, cudaStream_t s);
@@ -1397,11 +1415,14 @@ void run_step(Ctx* c, bool with_adam) {
     if (c->cfg.use_graph) {
       if (!c->peer.graph)
         c->peer.graph_nodes = capture(c, &c->peer.graph, [&](cudaStream_t cs) {
-          enqueue_a1(c, cs); enqueue_a2(c, cs, 1); enqueue_peer_adam(c, cs);
+          enqueue_peer_wait(c, cs); enqueue_a1(c, cs); enqueue_a2(c, cs, 1); enqueue_peer_adam(c, cs);
         });
       CUDA_OK(cudaGraphLaunch(c->peer.graph, s));
       c->launches += c->peer.graph_nodes;
+      c->peer.pending = true;
     } else {
+      enqueue_peer_wait(c, s);
+      c->peer.pending = true;
       enqueue_a1(c, s);
       enqueue_a2(c, s, 1);
       enqueue_peer_adam(c, s);
@@ -1494,10 +1515,15 @@ void validate_config(const vaeassoc_config* cfg) {
 // =======================================================================================================
 // C-ABI
 // =======================================================================================================
-#define API_BEGIN(h)                          \
+// (every entry point first makes the peers' parameter stores of the last data-parallel step visible -- peer_quiesce --
+// except the training entry points, whose step graph starts with that wait so that it overlaps the input staging)
+#define API_BEGIN_TRAIN(h)                    \
   try {                                       \
     check_handle(h);                          \
     std::lock_guard<std::mutex> lock__(h->mu);
+#define API_BEGIN(h)                          \
+  API_BEGIN_TRAIN(h)                          \
+    peer_quiesce(h);
 #define API_END(h)                            \
     return 0;                                 \
   } catch (const std::exception& e) {         \
@@ -1706,7 +1732,7 @@ int vaeassoc_step_set(vaeassoc_handle h, int64_t step) {
 }
 
 int vaeassoc_train_step(vaeassoc_handle h, const float* const* x_dev, const int64_t* ld, const float* eps_dev) {
-  API_BEGIN(h)
+  API_BEGIN_TRAIN(h)
   if (!x_dev) fail("x_dev is null");
   for (int m = 0; m < h->cfg.n_modalities; ++m) if (!x_dev[m]) fail("x_dev[%d] is null", m);
   stage_inputs(h, x_dev, ld, eps_dev, h->stream);
@@ -1766,7 +1792,7 @@ static void upload_host(Ctx* h, const float* const* x_host, const float* eps_hos
 }
 
 int vaeassoc_partial_fit_host(vaeassoc_handle h, const float* const* x_host, const float* eps_host, float* cost_host) {
-  API_BEGIN(h)
+  API_BEGIN_TRAIN(h)
   if (!x_host) fail("x_host is null");
   upload_host(h, x_host, eps_host, 0, h->stream);
   const float* xd[VAEASSOC_MAX_MODALITIES];
@@ -1779,7 +1805,7 @@ int vaeassoc_partial_fit_host(vaeassoc_handle h, const float* const* x_host, con
 }
 
 int vaeassoc_submit_host(vaeassoc_handle h, const float* const* x_host, const float* eps_host) {
-  API_BEGIN(h)
+  API_BEGIN_TRAIN(h)
   if (!x_host) fail("x_host is null");
   const int slot = (int)(h->submit_count & 1);
   // the upload of batch k+1 overlaps the compute of batch k; slot reuse waits for the stage kernel of batch k-1
@@ -1801,7 +1827,7 @@ int vaeassoc_submit_host(vaeassoc_handle h, const float* const* x_host, const fl
 
 int vaeassoc_submit_indexed(vaeassoc_handle h, const float* data_dev, int64_t ld, int64_t n_rows,
                             const int64_t* index_host, const float* eps_host) {
-  API_BEGIN(h)
+  API_BEGIN_TRAIN(h)
   if (!data_dev || !index_host) fail("data_dev / index_host is null");
   int64_t width = 0;
   for (int m = 0; m < h->cfg.n_modalities; ++m) width += h->mods[m].ni;
@@ -2214,15 +2240,52 @@ struct PeerBlob {                 // what a rank publishes: VAEASSOC_PEER_BLOB_B
 };
 static_assert(sizeof(PeerBlob) <= VAEASSOC_PEER_BLOB_BYTES, "peer blob must fit the ABI constant");
 
+void peer_quiesce(Ctx* c) {
+  if (!c->peer.on || !c->peer.pending) return;
+  enqueue_peer_wait(c, c->stream);
+  c->peer.pending = false;
+}
+
 void peer_detach(Ctx* c) {
   if (!c->peer.on) return;
+  peer_quiesce(c);
   cudaStreamSynchronize(c->stream);
+  if (c->peer.tl) {
+    unsigned long long h[5] = {0, 0, 0, 0, 0};
+    cudaMemcpy(h, c->peer.tl, sizeof h, cudaMemcpyDeviceToHost);
+    if (h[0])
+      fprintf(stderr, "[peer timeline] rank %d: %llu steps; per step (us): wait for all ranks %.2f | loads + Adam + stores (CTA 0) %.2f | "
+              "system fence %.2f | kernel entry -> last CTA out %.2f\n", c->rank, h[0], h[1] * 1e-3 / h[0], h[2] * 1e-3 / h[0],
+              h[3] * 1e-3 / h[0], h[4] * 1e-3 / h[0]);
+    cudaMemset(c->peer.tl, 0, sizeof h);
+  }
   if (c->peer.graph) { cudaGraphExecDestroy(c->peer.graph); c->peer.graph = nullptr; }
   for (int r = 0; r < kMaxPeers; ++r) {
-    if (c->peer.base[r] && r != c->rank) cudaIpcCloseMemHandle(c->peer.mapped[r]);
+    if (c->peer.mapped[r] && r != c->rank) cudaIpcCloseMemHandle(c->peer.mapped[r]);
     c->peer.base[r] = nullptr; c->peer.mapped[r] = nullptr;
   }
+  c->peer.mc = nullptr;
   c->peer.on = false;
+}
+
+// moves the flat buffers (and the arrival words) into `new_arena`, memory provided by the caller (symmetric memory that
+// every rank of the job has mapped): contents are copied, every schedule is rebuilt around the new addresses
+void arena_adopt(Ctx* c, float* new_arena) {
+  if (new_arena == c->arena) return;
+  if (reinterpret_cast<uintptr_t>(new_arena) & 255) fail("the arena must be 256-byte aligned");
+  CUDA_OK(cudaDeviceSynchronize());
+  CUDA_OK(cudaMemcpy(new_arena, c->arena, (size_t)c->arena_floats * sizeof(float), cudaMemcpyDeviceToDevice));
+  const ptrdiff_t delta = reinterpret_cast<char*>(new_arena) - reinterpret_cast<char*>(c->arena);
+  char* lo = reinterpret_cast<char*>(c->arena);
+  char* hi = lo + (size_t)c->arena_floats * sizeof(float);
+  for (auto& g : c->guards)
+    if (g.first >= lo && g.first < hi) g.first += delta;        // the guards between the flat buffers travel with them
+  c->p += delta / 4; c->g += delta / 4; c->m += delta / 4; c->v += delta / 4; c->p_tf32 += delta / 4;
+  c->peer.flags = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(c->peer.flags) + delta);
+  c->arena = new_arena;
+  c->shadow_dirty = true;
+  build_ops(c);
+  CUDA_OK(cudaDeviceSynchronize());
 }
 
 // m / v of the shards owned by the peers, pulled through the peer mapping (one-sided: the caller's stream is idle and
@@ -2300,10 +2363,41 @@ int vaeassoc_peer_attach(vaeassoc_handle h, const void* all_blobs) {
   CUDA_OK(cudaMemset(h->peer.flags, 0, (2 * kMaxPeers + 2) * sizeof(uint32_t)));
   CUDA_OK(cudaDeviceSynchronize());
   h->peer.on = true;
+  h->peer.pending = false;
   h->peer.slots_stale = false;
+  if (getenv("VAEASSOC_PEER_TIMELINE") && !h->peer.tl) h->peer.tl = h->dalloc<unsigned long long>(8);
   destroy_graphs(h);       // the captured launches bake in the task-queue mode
   API_END(h)
 }
+
+int64_t vaeassoc_arena_floats(vaeassoc_handle h) { return h ? h->arena_floats : -1; }
+
+int vaeassoc_peer_attach_symmetric(vaeassoc_handle h, void* local_arena, const void* const* rank_arenas, void* multicast_arena) {
+  API_BEGIN(h)
+  if (!h->comm || h->world < 2) fail("vaeassoc_peer_attach_symmetric needs an initialised communicator with world >= 2");
+  if (h->world > kMaxPeers) fail("the peer-memory step serves at most %d ranks (one NVSwitch box)", kMaxPeers);
+  if (!local_arena || !rank_arenas) fail("null arena pointers");
+  if (rank_arenas[h->rank] != local_arena) fail("rank_arenas[%d] must be this rank's own arena", h->rank);
+  peer_detach(h);
+  arena_adopt(h, reinterpret_cast<float*>(local_arena));
+  for (int r = 0; r < h->world; ++r) {
+    if (!rank_arenas[r]) fail("rank_arenas[%d] is null", r);
+    h->peer.base[r] = reinterpret_cast<float*>(const_cast<void*>(rank_arenas[r]));
+    h->peer.mapped[r] = nullptr;
+  }
+  h->peer.mc = getenv("VAEASSOC_DP_NO_MULTICAST") ? nullptr : reinterpret_cast<float*>(multicast_arena);
+  h->peer.symmetric = true;
+  CUDA_OK(cudaMemset(h->peer.flags, 0, (2 * kMaxPeers + 2) * sizeof(uint32_t)));
+  CUDA_OK(cudaDeviceSynchronize());
+  h->peer.on = true;
+  h->peer.pending = false;
+  h->peer.slots_stale = false;
+  if (getenv("VAEASSOC_PEER_TIMELINE") && !h->peer.tl) h->peer.tl = h->dalloc<unsigned long long>(8);
+  destroy_graphs(h);
+  API_END(h)
+}
+
+int vaeassoc_peer_multicast(vaeassoc_handle h) { return (h && h->peer.on && h->peer.mc) ? 1 : 0; }
 
 int vaeassoc_peer_detach(vaeassoc_handle h) {
   API_BEGIN(h)

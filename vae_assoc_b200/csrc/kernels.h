@@ -227,10 +227,20 @@ struct PeerAdamArgs {
   float* p_peer[kMaxPeers] = {};
   float* ptf_peer[kMaxPeers] = {};       // tf32 shadow of every rank (entries null in fp32 mode)
   uint32_t* flag_peer[kMaxPeers] = {};   // [2][kMaxPeers] arrival words of every rank: [phase][source rank] = epoch
+  // NVLS (NVSwitch multicast) form: one address that names the same offset of EVERY rank's arena.  multimem.ld_reduce on it
+  // returns the sum over all ranks computed inside the switch (1/world of the inbound bytes); multimem.st on it stores to
+  // every rank at once (1/world of the outbound bytes).  Null: plain peer loads / stores through the tables above.
+  const float* g_mc = nullptr;
+  float* p_mc = nullptr;
+  float* ptf_mc = nullptr;
   uint32_t* sync = nullptr;              // local: [0] epoch of the last completed step, [1] CTAs done
   int64_t shard_lo = 0, shard_hi = 0;    // float4 units
+  unsigned long long* tl = nullptr;      // debug (VAEASSOC_PEER_TIMELINE): [0] steps, [1..4] summed ns of the phases
 };
 void launch_peer_adam(const PeerAdamArgs& a, cudaStream_t s);
+// waits until every rank's phase-B arrival word ([1][r] of `flags`) has reached the epoch of the last completed step
+// (sync[0]): the peers' parameter stores have landed in this rank's memory and the peers have read its gradients
+void launch_peer_wait(const uint32_t* flags, const uint32_t* sync, int world, cudaStream_t s);
 void launch_round_copy(const float* src, float* dst, int64_t n, cudaStream_t s);   // dst = round_tf32(src)
 void launch_publish_cost(const float* cost_slot, float* last_cost, cudaStream_t s);
 

@@ -12,9 +12,11 @@
 //            [0][me] of every rank (st.release.sys).  Every CTA polls its OWN rank's words [0][*] (local L2) until all
 //            ranks have arrived, then reads the peers' gradients.
 //   phase B  "my stores into your p / p_tf32 are performed": each CTA fences (fence.sc.sys) after its last store and
-//            counts itself done; the last CTA stores the epoch into word [1][me] of every rank and waits for all
-//            ranks' [1][*], so that the kernel -- and therefore the next forward pass of this rank -- completes only
-//            when every shard has landed here, and no rank zeroes its `g` while a peer still reads it.
+//            counts itself done; the last CTA stores the epoch into word [1][me] of every rank and leaves.  The wait
+//            for all ranks' [1][*] is a one-warp kernel at the head of the NEXT step's graph (peer_wait_kernel; any
+//            other entry point of the library runs it first, api.cu: peer_quiesce): the next forward pass starts only
+//            when every shard has landed here, no rank zeroes its `g` while a peer still reads it, and the wait
+//            overlaps the next step's input staging instead of ending this kernel.
 // Epochs only grow, so the words need no reset.  Every wait is bounded (~4 s) and traps: a dead peer surfaces as a
 // launch failure of this rank, never as a hung GPU.  A CTA never waits for another CTA of its own grid (only for
 // peers' kernels, which start independently of this rank), so no co-residency is assumed.
@@ -50,7 +52,25 @@ __device__ __forceinline__ float ld_sys_f(const float* p) {
   asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void fence_sys() { asm volatile("fence.sc.sys;" ::: "memory"); }
+// NVLS: the switch adds the W ranks' values of this address and returns one float4
+__device__ __forceinline__ float4 multimem_ld_reduce_f4(const float4* p) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+// NVLS: one store, replicated by the switch into every rank's copy
+__device__ __forceinline__ void multimem_st_f4(float4* p, const float4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+               ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// message passing needs release / acquire ordering only (data stores -> fence -> flag store): acq_rel, not sc
+__device__ __forceinline__ void fence_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 __device__ __forceinline__ void wait_epoch(const uint32_t* word, uint32_t epoch) {
   const long long t0 = clock64();
@@ -60,11 +80,13 @@ __device__ __forceinline__ void wait_epoch(const uint32_t* word, uint32_t epoch)
   }
 }
 
-template <int W>
+template <int W, bool MC>
 __global__ void __launch_bounds__(256) peer_adam_kernel(const PeerAdamArgs a) {
   __shared__ float s_lr_t;
   __shared__ uint32_t s_epoch, s_last;
   const AdamArgs& ad = a.adam;
+  const bool stamp = a.tl != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  const unsigned long long t_entry = a.tl ? gtimer() : 0ull;
   const int me = a.rank;
   uint32_t* my_flags = a.flag_peer[me];
   if (threadIdx.x == 0) {
@@ -82,6 +104,7 @@ __global__ void __launch_bounds__(256) peer_adam_kernel(const PeerAdamArgs a) {
     (void)ld_acquire_sys(my_flags + threadIdx.x);     // acquire: the peers' gradient stores happen-before our loads
   }
   __syncthreads();
+  const unsigned long long t_a = stamp ? gtimer() : 0ull;
 
   const float lr_t = s_lr_t;
   const float b1 = ad.beta1, b2 = ad.beta2, ob1 = 1.0f - ad.beta1, ob2 = 1.0f - ad.beta2, eps = ad.eps;
@@ -91,13 +114,18 @@ __global__ void __launch_bounds__(256) peer_adam_kernel(const PeerAdamArgs a) {
   const bool shadow = ad.p_tf32 != nullptr;
   for (int64_t i = a.shard_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.shard_hi;
        i += (int64_t)gridDim.x * blockDim.x) {
-    float4 gr[W];
+    float4 g;
+    if (MC) {
+      g = multimem_ld_reduce_f4(reinterpret_cast<const float4*>(a.g_mc) + i);   // summed inside the NVSwitch
+    } else {
+      float4 gr[W];
 #pragma unroll
-    for (int r = 0; r < W; ++r) gr[r] = ld_sys_f4(reinterpret_cast<const float4*>(a.g_peer[r]) + i);   // W loads in flight
+      for (int r = 0; r < W; ++r) gr[r] = ld_sys_f4(reinterpret_cast<const float4*>(a.g_peer[r]) + i);   // W loads in flight
+      g = gr[0];
+#pragma unroll
+      for (int r = 1; r < W; ++r) { g.x += gr[r].x; g.y += gr[r].y; g.z += gr[r].z; g.w += gr[r].w; }   // rank order: deterministic
+    }
     float4 p = p4[i], m = m4[i], v = v4[i];
-    float4 g = gr[0];
-#pragma unroll
-    for (int r = 1; r < W; ++r) { g.x += gr[r].x; g.y += gr[r].y; g.z += gr[r].z; g.w += gr[r].w; }   // rank order: deterministic
 #define VAEASSOC_ADAM_LANE(c)                               \
     m.c = b1 * m.c + ob1 * g.c;                             \
     v.c = b2 * v.c + ob2 * g.c * g.c;                       \
@@ -106,10 +134,15 @@ __global__ void __launch_bounds__(256) peer_adam_kernel(const PeerAdamArgs a) {
 #undef VAEASSOC_ADAM_LANE
     m4[i] = m; v4[i] = v;
     const float4 ps = make_float4(round_tf32(p.x), round_tf32(p.y), round_tf32(p.z), round_tf32(p.w));
+    if (MC) {
+      multimem_st_f4(reinterpret_cast<float4*>(a.p_mc) + i, p);
+      if (shadow) multimem_st_f4(reinterpret_cast<float4*>(a.ptf_mc) + i, ps);
+    } else {
 #pragma unroll
-    for (int r = 0; r < W; ++r) {
-      reinterpret_cast<float4*>(a.p_peer[r])[i] = p;
-      if (shadow) reinterpret_cast<float4*>(a.ptf_peer[r])[i] = ps;
+      for (int r = 0; r < W; ++r) {
+        reinterpret_cast<float4*>(a.p_peer[r])[i] = p;
+        if (shadow) reinterpret_cast<float4*>(a.ptf_peer[r])[i] = ps;
+      }
     }
   }
   // cost of the step = sum over ranks of the local cost slots (every rank computes the same sum in rank order)
@@ -122,21 +155,28 @@ __global__ void __launch_bounds__(256) peer_adam_kernel(const PeerAdamArgs a) {
   }
   // ---- phase B: all stores of this rank performed -> tell every rank; leave only when every rank has told us ----
   __syncthreads();
+  const unsigned long long t_d = stamp ? gtimer() : 0ull;
   if (threadIdx.x == 0) {
     fence_sys();                                       // cumulative over the CTA's stores (ordered by the barrier above)
     s_last = (atomicAdd(a.sync + 1, 1u) == gridDim.x - 1) ? 1u : 0u;
+  }
+  if (stamp) {
+    const unsigned long long t_f = gtimer();
+    atomicAdd(a.tl + 0, 1ull);
+    atomicAdd(a.tl + 1, t_a - t_entry);                // waiting for the slowest rank's gradients
+    atomicAdd(a.tl + 2, t_d - t_a);                    // reduce-scatter loads, Adam, all-gather stores (CTA 0)
+    atomicAdd(a.tl + 3, t_f - t_d);                    // system fence of CTA 0
   }
   __syncthreads();
   if (s_last) {
     if (threadIdx.x == 0) fence_sys();                 // the other CTAs' fenced stores -> before our release below
     __syncthreads();
-    if (threadIdx.x < W) {
-      st_release_sys(a.flag_peer[threadIdx.x] + kMaxPeers + me, epoch);
-      wait_epoch(my_flags + kMaxPeers + threadIdx.x, epoch);
-      (void)ld_acquire_sys(my_flags + kMaxPeers + threadIdx.x);
-    }
+    // (the wait for the OTHER ranks' phase-B words is the first node of the next step's graph -- peer_wait_kernel --
+    // where it overlaps that step's input staging instead of ending this kernel)
+    if (threadIdx.x < W) st_release_sys(a.flag_peer[threadIdx.x] + kMaxPeers + me, epoch);
     __syncthreads();
     if (threadIdx.x == 0) {
+      if (a.tl) atomicAdd(a.tl + 4, gtimer() - t_entry);   // whole kernel as seen by the last CTA
       // block 0 may not be the last CTA: the summed cost goes to the local slot here only if this CTA computed it; the
       // slot itself is rewritten by the rank's own finalize kernel every step, so publishing through last_cost /
       // cost_hist (above) is what the host reads
@@ -144,6 +184,14 @@ __global__ void __launch_bounds__(256) peer_adam_kernel(const PeerAdamArgs a) {
       a.sync[0] = epoch;
       __threadfence();
     }
+  }
+}
+
+__global__ void peer_wait_kernel(const uint32_t* __restrict__ flags, const uint32_t* __restrict__ sync, int world) {
+  const uint32_t epoch = ld_relaxed_sys(sync);
+  if ((int)threadIdx.x < world) {
+    wait_epoch(flags + kMaxPeers + threadIdx.x, epoch);
+    (void)ld_acquire_sys(flags + kMaxPeers + threadIdx.x);
   }
 }
 
@@ -157,18 +205,24 @@ inline int peer_grid(int64_t n4) {
 
 }  // namespace
 
+void launch_peer_wait(const uint32_t* flags, const uint32_t* sync, int world, cudaStream_t s) {
+  peer_wait_kernel<<<1, 32, 0, s>>>(flags, sync, world);
+}
+
 void launch_peer_adam(const PeerAdamArgs& a, cudaStream_t s) {
   const int grid = peer_grid(a.shard_hi - a.shard_lo);
+  const bool mc = a.g_mc != nullptr;
+#define VAEASSOC_PEER_CASE(W)                                                        \
+    case W:                                                                          \
+      if (mc) peer_adam_kernel<W, true><<<grid, 256, 0, s>>>(a);                     \
+      else peer_adam_kernel<W, false><<<grid, 256, 0, s>>>(a);                       \
+      break;
   switch (a.world) {
-    case 2: peer_adam_kernel<2><<<grid, 256, 0, s>>>(a); break;
-    case 3: peer_adam_kernel<3><<<grid, 256, 0, s>>>(a); break;
-    case 4: peer_adam_kernel<4><<<grid, 256, 0, s>>>(a); break;
-    case 5: peer_adam_kernel<5><<<grid, 256, 0, s>>>(a); break;
-    case 6: peer_adam_kernel<6><<<grid, 256, 0, s>>>(a); break;
-    case 7: peer_adam_kernel<7><<<grid, 256, 0, s>>>(a); break;
-    case 8: peer_adam_kernel<8><<<grid, 256, 0, s>>>(a); break;
+    VAEASSOC_PEER_CASE(2) VAEASSOC_PEER_CASE(3) VAEASSOC_PEER_CASE(4) VAEASSOC_PEER_CASE(5)
+    VAEASSOC_PEER_CASE(6) VAEASSOC_PEER_CASE(7) VAEASSOC_PEER_CASE(8)
     default: break;   // world 1 never reaches here (run_step)
   }
+#undef VAEASSOC_PEER_CASE
 }
 
 }  // namespace vaeassoc

@@ -626,9 +626,43 @@ class AssocVariationalAutoEncoder(object):
             self._attach_peers(dist, world)
 
     def _attach_peers(self, dist, world):
-        """Peer-memory data-parallel step (csrc/peer_adam.cu): exchange the cudaIpc blobs of the flat buffers and map
-        every rank's.  All ranks end up in the same mode: if any rank cannot map a peer (no NVLink / P2P, IPC refused)
-        every rank stays on the NCCL all-reduce schedule."""
+        """Peer-memory data-parallel step (csrc/peer_adam.cu).  First choice: symmetric memory from
+        torch.distributed._symmetric_memory (every rank's flat buffers mapped everywhere + an NVSwitch multicast address:
+        the gradients are reduced INSIDE the switch, the parameters broadcast with one store); second: cudaIpc handles of
+        the library's own allocation (plain peer loads / stores); else the NCCL all-reduce schedule.  All ranks end up in
+        the same mode: each stage is agreed on by an all-gather of the per-rank outcome."""
+        def agreed(ok):
+            oks = [None] * world
+            dist.all_gather_object(oks, bool(ok))      # also the barrier between attach and the first step
+            return all(oks)
+
+        self._peer_error = None
+        # measured on B200 (profiles/r2_dp_modes.md): the NVLS form moves 1/world of the bytes but its multimem stores and
+        # the system fence behind them take longer than the plain peer stores at this size (5.7 MB of gradients): 0.350
+        # against 0.334 ms per step at 2 ranks, equal at 8 -- so the plain peer form is the default, NVLS is opt-in
+        if os.environ.get("VAEASSOC_DP_SYMMETRIC", "0") != "0":
+            ok = False
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                t = self._torch
+                n = int(self._lib.vaeassoc_arena_floats(self._h))
+                buf = symm_mem.empty(n, dtype=t.float32, device=self._dev)
+                hdl = symm_mem.rendezvous(buf, dist.group.WORLD)
+                ptrs = (C.c_void_p * 8)(*[int(p) for p in hdl.buffer_ptrs])      # kMaxPeers slots, rank order
+                mc = int(hdl.multicast_ptr or 0)
+                t.cuda.synchronize()
+                ok = self._lib.vaeassoc_peer_attach_symmetric(self._h, C.c_void_p(buf.data_ptr()), ptrs,
+                                                              C.c_void_p(mc) if mc else None) == 0
+                if not ok:
+                    self._peer_error = self._lib.vaeassoc_last_error(self._h).decode()
+                self._symm = (buf, hdl)        # the library's flat buffers now live here: keep it until close()
+            except Exception as e:             # no symmetric-memory support in this torch / driver / topology
+                self._peer_error = "symmetric memory: %r" % (e,)
+            if agreed(ok):
+                self._peer = True
+                return
+            if ok:
+                self._check(self._lib.vaeassoc_peer_detach(self._h))
         blob = (C.c_ubyte * L.PEER_BLOB_BYTES)()
         ok = self._lib.vaeassoc_peer_export(self._h, blob) == 0
         blobs = [None] * world
@@ -638,10 +672,9 @@ class AssocVariationalAutoEncoder(object):
             ok = self._lib.vaeassoc_peer_attach(self._h, allb) == 0
         else:
             ok = False
-        self._peer_error = None if ok else self._lib.vaeassoc_last_error(self._h).decode()
-        oks = [None] * world
-        dist.all_gather_object(oks, bool(ok))          # also the barrier between attach and the first step
-        if all(oks):
+        if not ok:
+            self._peer_error = self._lib.vaeassoc_last_error(self._h).decode()
+        if agreed(ok):
             self._peer = True
         elif ok:
             self._check(self._lib.vaeassoc_peer_detach(self._h))
@@ -660,7 +693,9 @@ class AssocVariationalAutoEncoder(object):
     def dp_mode(self):
         if getattr(self, "_world", 1) < 2:
             return "single"
-        return "peer" if self._lib.vaeassoc_peer_active(self._h) else "nccl"
+        if not self._lib.vaeassoc_peer_active(self._h):
+            return "nccl"
+        return "peer-nvls" if self._lib.vaeassoc_peer_multicast(self._h) else "peer"
 
     def sync_replicas(self):
         """Broadcast rank 0's parameters / Adam state to every rank (call on ALL ranks, e.g. after a rank-0 restore_model)."""
