@@ -182,10 +182,17 @@ struct vaeassoc_ctx {
   // decoder forward are one launch and decoder + latent + encoder backward another (build_segments)
   Seg seg_fwd, seg_bwd;
   bool elt_built = false;
+  // one-launch form: forward, reconstruction losses (in the output-layer epilogues), cost finalize and backward as ONE
+  // launch of the tile kernel; x_hat / per-row reconstruction losses are then produced on demand (probe_get)
+  Seg seg_step;
+  bool one_built = false;
+  unsigned recon_stale = 0;           // bit m: the last step ran the loss-fused form, d.xh / d.rec_loss of modality m are not current
+  FinalizeArgs fin_one;
   int lat_blocks_elt = 0;
   bool lat_mode_elt = false;          // which latent kernel wrote lat_partials last (layout of the block partials)
   LatentArgs lat_fwd_args;
   LatentBwdArgs lat_bwd_args;
+  bool recon_round_da[VAEASSOC_MAX_MODALITIES] = {false, false, false, false};
   bool masks_in_use[VAEASSOC_MAX_MODALITIES] = {false, false, false, false};   // relu sign masks written / read this schedule
   int dp_single = -1;                                 // VAEASSOC_DP_SINGLE=0/1; default (-1): one all-reduce per step iff fused and world > 4
   bool force_dynamic = false;                         // VAEASSOC_DYNAMIC_FIRST: the data-parallel task-queue mode on one GPU (tests)
@@ -272,6 +279,7 @@ namespace {
 
 using Ctx = vaeassoc_ctx;
 void build_ops(Ctx* c);
+FinalizeArgs finalize_args(Ctx* c, int advance);
 void peer_quiesce(Ctx* c);
 void peer_detach(Ctx* c);
 void refresh_peer_slots(Ctx* c);
@@ -471,7 +479,7 @@ void alloc_buffers(Ctx* c) {
   {
     // row-block counters: 12 activation / gradient tensors per modality x row blocks of 256; then the launch sites
     const int64_t rb = (B + 255) / 256;
-    c->n_ctr = (int)(c->cfg.n_modalities * 12 * rb);
+    c->n_ctr = (int)(c->cfg.n_modalities * 13 * rb);
     c->max_sites = 1024;
     c->gsync = c->dalloc<uint32_t>(c->n_ctr + 2 * c->max_sites);
   }
@@ -788,6 +796,7 @@ void build_ops(Ctx* c) {
     a.x = d.xs; a.ldx = d.nip; a.xhat = d.xh; a.ldxh = d.nip; a.da = d.da; a.ldda = d.nip;
     a.row_loss = d.rec_loss; a.partials = d.partials;
     a.round_tf32 = round_da ? 1 : 0;
+    c->recon_round_da[m] = round_da;
     d.recon_blocks = (int)std::min<int64_t>(std::max<int64_t>((B + 7) / 8, 1), kMaxPartialBlocks);
     op.bytes = 4.0 * 3 * B * d.ni;
     op.run = [a](cudaStream_t s) { launch_recon_loss(a, s); };
@@ -916,8 +925,8 @@ void build_ops(Ctx* c) {
 // row-block counters (tensor T of modality m over rows [256 rb, +256) is complete when its counter reaches
 // 16 x (N-tiles of the producing layer)).  Counter index = (T * n_modalities + m) * RB + rb.
 // (forward tensors first, then backward ones: a launch rewinds one contiguous range of counters when it leaves)
-enum { T_H1 = 0, T_H2, T_HD, T_Z, T_G1, T_G2, T_DG2, T_DG1, T_DZ, T_DHD, T_DH2, T_DH1, T_COUNT };
-static_assert(T_COUNT == 12, "alloc_buffers sizes the counter array for 12 tensors per modality");
+enum { T_H1 = 0, T_H2, T_HD, T_Z, T_G1, T_G2, T_DG2, T_DG1, T_DZ, T_DHD, T_DH2, T_DH1, T_DA, T_COUNT };
+static_assert(T_COUNT == 13, "alloc_buffers sizes the counter array for 13 tensors per modality");
 
 void build_segments(Ctx* c) {
   const int M = c->cfg.n_modalities;
@@ -937,10 +946,11 @@ void build_segments(Ctx* c) {
     GroupPlan* g = c->gplan;
     auto ctr = [&](int m, int T, int rb) { return (T * M + m) * RB + rb; };
     // tiles of a row-wise layer (NN / NT): one task per (row block, column tile)
-    auto add_rowwise = [&](const Op& op, int m, int inT, int in_tn, int outT, float* colsum, int in_m = -1) -> int {
+    auto add_rowwise = [&](const Op& op, int m, int inT, int in_tn, int outT, float* colsum, int in_m = -1,
+                           const GemmArgs* override_args = nullptr) -> int {
       if (nodeps) { inT = -1; outT = -1; }
       if (in_m < 0) in_m = m;
-      GemmArgs a = op.gargs;
+      GemmArgs a = override_args ? *override_args : op.gargs;
       a.bias_grad = colsum;
       const int prob = group_add_problem(g, op.kind, a, err, sizeof err);
       if (prob < 0) fail("segment plan for %s failed: %s", op.name.c_str(), err);
@@ -952,8 +962,8 @@ void build_segments(Ctx* c) {
       return tn;
     };
     // weight gradient (TN): the batch contraction is cut into row-block ranges; a task waits for dY over its range
-    auto add_wgrad = [&](const Op& op, int m, int dyT, int dy_tn, int dy_m = -1) {
-      const bool external = dyT < 0;
+    auto add_wgrad = [&](const Op& op, int m, int dyT, int dy_tn, int dy_m = -1, bool want_colsum_op = true) {
+      const bool external = dyT < 0 && want_colsum_op;
       if (nodeps) dyT = -1;
       if (dy_m < 0) dy_m = m;
       GemmArgs a = op.gargs;
@@ -1062,14 +1072,68 @@ void build_segments(Ctx* c) {
       for (int m = 0; m < M; ++m) add_wgrad(c->ops_bwd_enc_mod[m][4], m, T_DH1, tn2[m]);
       end(c->seg_bwd);
       c->elt_built = true;
+      // ---- one-launch form: the whole gradient step (forward, losses, cost, backward) is ONE launch ----
+      // The output layer of each decoder turns its accumulator straight into the reconstruction loss and d cost / d a
+      // (target tile through the epilogue's aux boxes), also summing the output bias gradient; the decoder backward
+      // waits on those tiles (T_DA).  The cost reduction is one more elementwise task.
+      c->one_built = false;
+      if (!getenv("VAEASSOC_NO_ONE") && 17 * M <= 36) {
+        std::vector<int> tno(M);
+        begin(c->seg_step, T_H1, T_COUNT);
+        for (int m = 0; m < M; ++m) tn1[m] = add_rowwise(c->ops_enc_mod[m][0], m, -1, 0, T_H1, nullptr);
+        for (int m = 0; m < M; ++m) tn2[m] = add_rowwise(c->ops_enc_mod[m][1], m, T_H1, tn1[m], T_H2, nullptr);
+        for (int m = 0; m < M; ++m) tnh[m] = add_rowwise(c->ops_enc_mod[m][2], m, T_H2, tn2[m], T_HD, nullptr);
+        for (int rb = 0; rb < RB; ++rb)
+          group_add_elt_task(g, 0, rb, B, ctr(0, T_HD, rb), 1, S * tnh[0], M > 1 ? ctr(1, T_HD, rb) : -1, M > 1 ? S * tnh[1] : 0,
+                             ctr(0, T_Z, rb));
+        for (int m = 0; m < M; ++m) tn1[m] = add_rowwise(c->ops_dec_mod[m][0], m, T_Z, 1, T_G1, nullptr, 0);
+        for (int m = 0; m < M; ++m) tn2[m] = add_rowwise(c->ops_dec_mod[m][1], m, T_G1, tn1[m], T_G2, nullptr);
+        FinalizeArgs fin = finalize_args(c, 0);
+        fin.partials_latent = c->lat_partials; fin.blocks_latent = c->lat_blocks_elt;
+        for (int m = 0; m < M; ++m) {
+          Mod& d = c->mods[m];
+          GemmArgs a = c->ops_dec_mod[m][2].gargs;           // x_hat = act(g2 Vo + co)  ->  d a, loss
+          const GemmArgs& w_o = c->ops_bwd_dec_mod[m][0].gargs;
+          const int tiles = (d.ni + 63) / 64 * RB;             // upper bound of the tile count (narrowest tile)
+          float* parts = c->op_ws((int64_t)tiles * kGroupSignalsPerTile);
+          a.C = d.da; a.ldc = d.nip; a.act = ACT_NONE;
+          a.round_out = c->recon_round_da[m] ? 1 : 0;
+          a.loss_x = d.xs; a.ld_loss_x = d.nip; a.loss_partials = parts;
+          a.loss_scale = d.cfg.binary ? d.cfg.weight * (1.0f / (float)global_batch(c)) : d.cfg.weight;
+          a.loss_binary = d.cfg.binary ? 1 : 0;
+          tno[m] = add_rowwise(c->ops_dec_mod[m][2], m, T_G2, tn2[m], T_DA, w_o.bias_grad, -1, &a);
+          fin.partials_recon[m] = parts; fin.blocks_recon[m] = RB * tno[m] * kGroupSignalsPerTile;
+          fin.stride_recon[m] = 1; fin.off_recon[m] = 0;
+        }
+        c->fin_one = fin;
+        el.fin = fin;
+        group_set_elem(g, el);
+        for (int m = 0; m < M; ++m) { auto& bd = c->ops_bwd_dec_mod[m]; tn1[m] = add_rowwise(bd[1], m, T_DA, tno[m], T_DG2, bd[2].gargs.bias_grad); }
+        for (int m = 0; m < M; ++m) add_wgrad(c->ops_bwd_dec_mod[m][0], m, T_DA, tno[m]);
+        for (int m = 0; m < M; ++m) { auto& bd = c->ops_bwd_dec_mod[m]; tn2[m] = add_rowwise(bd[3], m, T_DG2, tn1[m], T_DG1, bd[4].gargs.bias_grad); }
+        group_add_elt_task(g, 2, 0, B, ctr(0, T_DA, 0), RB, S * tno[0], M > 1 ? ctr(1, T_DA, 0) : -1, M > 1 ? S * tno[1] : 0, -1, RB);
+        for (int m = 0; m < M; ++m) add_wgrad(c->ops_bwd_dec_mod[m][2], m, T_DG2, tn1[m]);
+        for (int m = 0; m < M; ++m) tnz[m] = add_rowwise(c->ops_bwd_dec_mod[m][5], m, T_DG1, tn2[m], T_DZ, nullptr);
+        for (int m = 0; m < M; ++m) add_wgrad(c->ops_bwd_dec_mod[m][4], m, T_DG1, tn2[m]);
+        for (int rb = 0; rb < RB; ++rb)
+          group_add_elt_task(g, 1, rb, B, ctr(0, T_DZ, rb), 1, S * tnz[0], M > 1 ? ctr(1, T_DZ, rb) : -1, M > 1 ? S * tnz[1] : 0,
+                             ctr(0, T_DHD, rb));
+        for (int m = 0; m < M; ++m) { auto& be = c->ops_bwd_enc_mod[m]; tn1[m] = add_rowwise(be[1], m, T_DHD, 1, T_DH2, be[2].gargs.bias_grad, 0); }
+        for (int m = 0; m < M; ++m) add_wgrad(c->ops_bwd_enc_mod[m][0], m, T_DHD, 1, 0);
+        for (int m = 0; m < M; ++m) { auto& be = c->ops_bwd_enc_mod[m]; tn2[m] = add_rowwise(be[3], m, T_DH2, tn1[m], T_DH1, be[4].gargs.bias_grad); }
+        for (int m = 0; m < M; ++m) add_wgrad(c->ops_bwd_enc_mod[m][2], m, T_DH2, tn1[m]);
+        for (int m = 0; m < M; ++m) add_wgrad(c->ops_bwd_enc_mod[m][4], m, T_DH1, tn2[m]);
+        end(c->seg_step);
+        c->one_built = true;
+      }
     }
   }
   group_set_counters(c->gplan, c->gsync, c->n_ctr);
   if (!group_upload(c->gplan, err, sizeof err)) fail("%s", err);
 }
 
-void launch_seg(Ctx* c, const Ctx::Seg& sg, cudaStream_t s) {
-  group_launch(c->gplan, sg.site, c->gsync + c->n_ctr + 2 * sg.site, sg.reset_first, sg.reset_count, dyn_first(c), s);
+void launch_seg(Ctx* c, const Ctx::Seg& sg, cudaStream_t s, int advance = 0) {
+  group_launch(c->gplan, sg.site, c->gsync + c->n_ctr + 2 * sg.site, sg.reset_first, sg.reset_count, dyn_first(c), s, advance);
   c->launches += 1;
 }
 
@@ -1111,6 +1175,7 @@ bool dp_two_buckets(const Ctx* c) {
   return !(c->dp_single >= 0 ? c->dp_single != 0 : (c->fused && c->world > 4));
 }
 bool elt_mode(const Ctx* c) { return c->fused && c->elt_built && !dp_two_buckets(c); }
+bool one_mode(const Ctx* c) { return elt_mode(c) && c->one_built; }
 
 FinalizeArgs finalize_args(Ctx* c, int advance) {
   FinalizeArgs a;
@@ -1168,6 +1233,13 @@ void join_colsums(Ctx* c, std::vector<Op>& ops, cudaStream_t s) {
 void enqueue_a1(Ctx* c, cudaStream_t s) {
   const int M = c->cfg.n_modalities;
   c->lat_mode_elt = false;
+  if (one_mode(c)) {
+    // ONE launch of the persistent tile kernel carries the gradient step (enqueue_a2); the gradient buffer it accumulates
+    // into (TMA reduce-add, bias-gradient REDs) is cleared here
+    c->lat_mode_elt = true;
+    CUDA_OK(cudaMemsetAsync(c->g, 0, (size_t)(c->n_flat + 32) * sizeof(float), s));
+    return;
+  }
   if (elt_mode(c)) {
     // two launches of the persistent tile kernel carry the step: forward (encoders, latent stage, decoders) here,
     // backward in enqueue_a2; the gradient memset runs as a parallel branch of the forward
@@ -1217,6 +1289,11 @@ void enqueue_a1(Ctx* c, cudaStream_t s) {
 }
 // segment A2: latent + encoder backward, cost finalize (bucket 1 + cost slot complete at its end)
 void enqueue_a2(Ctx* c, cudaStream_t s, int advance) {
+  if (one_mode(c)) {
+    c->lat_mode_elt = true;
+    launch_seg(c, c->seg_step, s, advance);
+    return;
+  }
   if (elt_mode(c)) {
     c->lat_mode_elt = true;
     CUDA_OK(cudaEventRecord(c->ev_aux_fork, s));
@@ -1293,6 +1370,7 @@ void enqueue_peer_wait(Ctx* c, cudaStream_t s) {
 void allreduce(Ctx* c, float* buf, int64_t count, cudaStream_t s);
 void enqueue_forward_loss(Ctx* c, cudaStream_t s) {   // evaluate_cost: no gradients
   c->lat_mode_elt = false;
+  c->recon_stale = 0;
   run_ops(c, c->ops_fwd_enc, s);
   {
     // latent forward without the gradient stash
@@ -1407,6 +1485,7 @@ void run_step(Ctx* c, bool with_adam) {
   cudaStream_t s = c->stream;
   refresh_shadow(c, s);
   ensure_graphs(c);
+  if (one_mode(c)) c->recon_stale = (1u << c->cfg.n_modalities) - 1u;
   const bool dp = c->comm != nullptr && c->world > 1;
   if (dp && c->peer.on && with_adam) {
     // peer-memory step: forward, backward and ONE kernel that reduce-scatters the gradients over NVLink, runs Adam on
@@ -1975,6 +2054,15 @@ int vaeassoc_probe_get(vaeassoc_handle h, int kind, int modality, float* dst_hos
     default: fail("unknown probe kind %d", kind);
   }
   if (rows * cols > capacity) fail("probe needs %lld floats, capacity %lld", (long long)(rows * cols), (long long)capacity);
+  if ((kind == VAEASSOC_PROBE_X_RECONSTR_MEAN || (kind == VAEASSOC_PROBE_RECONSTR_LOSS && d->cfg.binary)) &&
+      (h->recon_stale >> modality) & 1u) {
+    // the one-launch step turns the decoder's accumulator straight into loss and gradient: x_hat and the per-row losses
+    // are produced on demand from the retained decoder activations (same batch, same eps, current weights)
+    refresh_shadow(h, h->stream);
+    run_ops(h, h->ops_dec_mod[modality], h->stream);     // (dec1, dec2 recomputed as well: identical values)
+    run_ops(h, h->ops_loss_mod[modality], h->stream);
+    h->recon_stale &= ~(1u << modality);
+  }
   CUDA_OK(cudaStreamSynchronize(h->stream));
   CUDA_OK(cudaMemcpy2D(dst_host, (size_t)cols * 4, src, (size_t)ld * 4, (size_t)cols * 4, (size_t)rows, cudaMemcpyDeviceToHost));
   if (n_written) *n_written = rows * cols;
@@ -2595,7 +2683,14 @@ int vaeassoc_profile_step(vaeassoc_handle h, const float* const* x_dev, const in
       all.push_back(z);
     }
     h->lat_mode_elt = elt_mode(h);
-    if (elt_mode(h)) {
+    if (one_mode(h)) {
+      Ctx* c = h;
+      Op o; o.name = "seg_step";
+      for (auto* v : {&h->ops_fwd_enc, &h->ops_fwd_dec, &h->ops_bwd_dec, &h->ops_bwd_enc}) for (auto& op : *v) o.flops += op.flops;
+      o.run = [c](cudaStream_t st) { launch_seg(c, c->seg_step, st, 0); c->launches -= 1; };
+      all.push_back(o);
+      h->recon_stale = (1u << h->cfg.n_modalities) - 1u;
+    } else if (elt_mode(h)) {
       Ctx* c = h;
       auto seg_op = [&](const char* name, const Ctx::Seg* sg, std::initializer_list<std::vector<Op>*> members) {
         Op o; o.name = name;
@@ -2631,7 +2726,12 @@ int vaeassoc_profile_step(vaeassoc_handle h, const float* const* x_dev, const in
     }
     {
       Ctx* c = h;
-      Op f; f.name = "finalize"; f.run = [c](cudaStream_t st) { launch_finalize(finalize_args(c, 1), st); };
+      Op f; f.name = "finalize";
+      f.run = [c](cudaStream_t st) {
+        FinalizeArgs fa = one_mode(c) ? c->fin_one : finalize_args(c, 1);
+        fa.advance = 1;
+        launch_finalize(fa, st);
+      };
       all.push_back(f);
       Op a; a.name = "adam"; a.bytes = (c->cfg.precision == VAEASSOC_TF32 ? 32.0 : 28.0) * c->n_flat;
       a.run = [c](cudaStream_t st) { launch_adam(adam_args(c), st); };
@@ -2641,6 +2741,7 @@ int vaeassoc_profile_step(vaeassoc_handle h, const float* const* x_dev, const in
       CUDA_OK(cudaStreamSynchronize(s));
       std::vector<const Ctx::Seg*> segs = {&h->seg_enc, &h->seg_dec, &h->seg_bwd_dec, &h->seg_bwd_enc};
       if (elt_mode(h)) segs = {&h->seg_fwd, &h->seg_bwd};
+      if (one_mode(h)) segs = {&h->seg_step};
       for (const Ctx::Seg* sg : segs)
         group_debug_timeline(h->gplan, sg->site, h->gsync + h->n_ctr + 2 * sg->site, sg->reset_first, sg->reset_count, s);
     }

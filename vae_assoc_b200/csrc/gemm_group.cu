@@ -322,7 +322,8 @@ struct alignas(64) GProblem {
   int a_mn, b_mn;            // operand is MN-major (M / N index contiguous in HBM)
   int reduce;                // epilogue adds into C (TMA reduce-add): wgrad tasks share an output tile
   int act, round_out, has_aux;
-  int pad0, pad1;
+  int loss_binary;           // loss-fused output layer: Bernoulli cross-entropy (else Gaussian l2)
+  float loss_scale;
   const float* bias;
   float* colsum;             // epilogue adds the column sums of its output tile here (bias gradient), or null
   float* c_ptr;              // output matrix for the direct (non-TMA) stores of the NN / NT epilogue
@@ -330,6 +331,7 @@ struct alignas(64) GProblem {
   uint32_t* mask_out;        // relu forward: bit (row, col) = output > 0, 32 columns per word, or null
   const uint32_t* mask_in;   // relu dgrad: the same words replace the aux tile, or null
   long long ldmask;          // words per mask row
+  float* loss_partials;      // loss-fused output layer (aux tile = target x, C = d a): per-warp loss sums, or null
 };
 static_assert(sizeof(GProblem) % 64 == 0, "tensor maps must stay 64-byte aligned inside the array");
 
@@ -349,7 +351,12 @@ static_assert(sizeof(GTask) == 64, "GTask is loaded as four 16-byte words");
 enum { TF_A_MN = 1, TF_B_MN = 2, TF_REDUCE = 4, TF_AUX = 8, TF_ROUND = 16, TF_COLSUM = 32, TF_MASK_OUT = 64, TF_MASK_IN = 128,
        // elementwise tasks (no contraction: nkb = 0; the epilogue warps of the pair execute them over the 256 rows of
        // row block m_blk; the producer and the MMA issuer skip them): latent forward / backward (latent.cuh)
-       TF_ELT_LATENT_FWD = 256, TF_ELT_LATENT_BWD = 512, TF_ELT = TF_ELT_LATENT_FWD | TF_ELT_LATENT_BWD };
+       TF_ELT_LATENT_FWD = 256, TF_ELT_LATENT_BWD = 512,
+       // NN task of a decoder's output layer with the reconstruction loss fused into its epilogue (aux tile = target)
+       TF_LOSS = 1024,
+       // elementwise task: cost finalize (one warp sums the block partials of the loss / latent tasks; kb0 = number of
+       // counters behind wait2_ctr)
+       TF_ELT_FINALIZE = 2048, TF_ELT = TF_ELT_LATENT_FWD | TF_ELT_LATENT_BWD | TF_ELT_FINALIZE };
 
 
 namespace {
@@ -417,6 +424,7 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
   const bool bias_smem = (mode & 2) != 0, tma_store = (mode & 4) != 0;
   // timing experiments only (wrong results): VAEASSOC_DEBUG_SKIP_MATH / _SKIP_STORE drop parts of the NN / NT epilogue
   const bool dbg_skip_math = (mode & 8) != 0, dbg_skip_store = (mode & 16) != 0;
+  const int fin_advance = (mode >> 5) & 1;               // the finalize task bumps the Adam step counter
   const uint32_t stagger_ns = (uint32_t)mode >> 8;      // VAEASSOC_EPI_STAGGER_NS: the odd chunk slots start this much later
   // barriers: full[s] (leader CTA only), empty[s], tmem_full[2], tmem_empty[2] (leader CTA only), aux[epilogue warp],
   // sched_full[kSched], sched_empty[kSched] (leader CTA only); then the TMEM slot and the task-index ring
@@ -628,11 +636,34 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
         // ---- elementwise task: rows [256 m_blk + 128 rank, +128) of the batch, one thread per row (warps 0..3) ----
         if (lane == 0) {
           for (int c = 0; c < tk.wait_cnt; ++c) wait_counter(counters + tk.wait_ctr + c, (uint32_t)tk.wait_val);
-          if (tk.wait2_ctr >= 0) wait_counter(counters + tk.wait2_ctr, (uint32_t)tk.wait2_val);
+          if (tk.wait2_ctr >= 0)
+            for (int c = 0; c < max(tk.kb0, 1); ++c) wait_counter(counters + tk.wait2_ctr + c, (uint32_t)tk.wait2_val);
           fence_acq_rel_gpu();               // pairs with the producers' red.release.gpu (inputs are read with ld.cg)
         }
         __syncwarp();
-        if (e < 4) {
+        if (tk.flags & TF_ELT_FINALIZE) {
+          // ---- cost finalize: one warp, lanes stride the block partials, fixed-order sums (finalize_kernel's arithmetic) ----
+          if (e == 0 && rank == 0) {
+            const FinalizeArgs& f = elem.fin;
+            float sums[9];
+#pragma unroll
+            for (int qi = 0; qi < 9; ++qi) sums[qi] = 0.f;
+            const int nq = 2 * f.n_mod + 1;
+            for (int qi = 0; qi < nq; ++qi) {
+              const float* src; int nblk, slot, stride = kCostSlots, off;
+              if (qi == 2 * f.n_mod) { src = f.partials_latent; nblk = f.blocks_latent; slot = 8; off = 8; }
+              else if (qi & 1) { src = f.partials_latent; nblk = f.blocks_latent; slot = qi; off = qi; }
+              else { src = f.partials_recon[qi >> 1]; nblk = f.blocks_recon[qi >> 1]; slot = qi; stride = f.stride_recon[qi >> 1]; off = f.off_recon[qi >> 1]; }
+              float acc = 0.f;
+#pragma unroll 8
+              for (int b = lane; b < nblk; b += 32) acc += __ldcg(src + (int64_t)b * stride + off);
+              acc = warp_sum(acc);
+#pragma unroll
+              for (int k = 0; k < 9; ++k) if (k == slot) sums[k] = acc;
+            }
+            if (lane == 0) finalize_combine(f, sums, fin_advance);
+          }
+        } else if (e < 4) {
           const int64_t r = (int64_t)tk.m_blk * BM + (int64_t)rank * BM_CTA + e * 32 + lane;
           const bool live = r < (int64_t)tk.M;
           if (tk.flags & TF_ELT_LATENT_FWD) {
@@ -678,6 +709,8 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
       const int BN = tk.bn, N = tk.N, act = tk.act;
       const bool reduce = (tk.flags & TF_REDUCE) != 0, use_aux = (tk.flags & TF_AUX) != 0, round_out = (tk.flags & TF_ROUND) != 0;
       const float* __restrict__ bias = p->bias;
+      const bool loss_task = (tk.flags & TF_LOSS) != 0;
+      float loss_acc = 0.0f;                 // this lane's row: reconstruction loss over the warp's chunks
       float* __restrict__ colsum = (tk.flags & TF_COLSUM) ? p->colsum : nullptr;
       const int row0 = tk.m_blk * BM + (int)rank * BM_CTA + q * 32;    // first output row of this warp
       const int n0 = tk.n_blk * BN;
@@ -761,6 +794,45 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] &= (uint32_t)((int32_t)(mw << (31 - j)) >> 31);
+          }
+        } else if (loss_task) {
+          // output layer of a decoder: pre-activation -> reconstruction loss (:321-328) and d cost / d pre-activation;
+          // the aux box holds the target tile x (rows / columns past M / N zero-filled by TMA and masked here)
+          mbar_wait(aux_bar(e, b), (aux_phase >> b) & 1u);
+          aux_phase ^= 1u << b;
+          if (bias != nullptr) {
+            const float b_cur = i == 0 ? bv0 : i == 1 ? bv1 : i == 2 ? bv2 : bv3;
+            const uint32_t strip = strip_base + (uint32_t)e * kBiasStrip;
+            __syncwarp();
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(strip + (uint32_t)lane * 4u), "f"(b_cur) : "memory");
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 bq = lds128(strip + (uint32_t)j * 16u);
+              v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + bq.x);
+              v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + bq.y);
+              v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + bq.z);
+              v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + bq.w);
+            }
+          }
+          const int ncols = (row0 + lane < tk.M) ? min(32, N - (n0 + c * 32)) : 0;    // live columns of this lane's row
+          const float lscale = p->loss_scale;
+          const bool lbin = p->loss_binary != 0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 xv = lds128(ob + swz(lane, j));
+            const float xs4[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              float da;
+              const float av = __uint_as_float(v[4 * j + k]);
+              const float l = lbin ? recon_logit_binary(av, xs4[k], lscale, da) : recon_logit_gaussian(av, xs4[k], lscale, da);
+              const bool live = 4 * j + k < ncols;
+              loss_acc += live ? l : 0.0f;
+              uint32_t bits = __float_as_uint(da);
+              if (round_out) bits = (bits + 0x1000u) & 0xffffe000u;
+              v[4 * j + k] = live ? bits : 0u;           // dead rows / columns: exact zeros (the column sums read them)
+            }
           }
         } else if (use_aux) {
           mbar_wait(aux_bar(e, b), (aux_phase >> b) & 1u);
@@ -932,6 +1004,12 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
       // every tcgen05.ld of this accumulator has completed (wait::ld): hand it back to the MMA issuer; the global
       // stores of all lanes are ordered before the elected lane's release by the warp barrier
       if (tl && rank == 0 && warp == 2 && lane == 0) tl[kTL * t + 8] = gtimer();
+      if (loss_task) {
+        loss_acc = warp_sum(loss_acc);
+        const int tiles_n = (N + BN - 1) / BN;
+        if (lane == 0)
+          p->loss_partials[(size_t)((tk.m_blk * tiles_n + tk.n_blk) * 2 + (int)rank) * kEpiWarps + e] = loss_acc;
+      }
       tc_fence_before();
       __syncwarp();
       if (elect_one()) {
@@ -1037,7 +1115,7 @@ bool make_map_mn(CUtensorMap* map, const float* ptr, int64_t dim_mn, int64_t dim
 }  // namespace
 
 // ---- group plan: the problems / tasks of a handle, cut into launch sites ---------------------------------------------
-constexpr int kSiteProblemsSmall = 2, kSiteProblemsLarge = 24;
+constexpr int kSiteProblemsSmall = 2, kSiteProblemsLarge = 24, kSiteProblemsStep = 36;
 
 struct GroupSite { int first_problem = 0, n_problems = 0, first_task = 0, n_tasks = 0; };
 
@@ -1076,8 +1154,8 @@ bool group_end(GroupPlan* g, char* err, int errlen) {
   st.n_problems = (int)g->problems.size() - st.first_problem;
   st.n_tasks = (int)g->tasks.size() - st.first_task;
   g->open = false;
-  if (st.n_problems > kSiteProblemsLarge) {
-    snprintf(err, errlen, "a launch site holds %d contractions, at most %d fit the kernel parameter", st.n_problems, kSiteProblemsLarge);
+  if (st.n_problems > kSiteProblemsStep) {
+    snprintf(err, errlen, "a launch site holds %d contractions, at most %d fit the kernel parameter", st.n_problems, kSiteProblemsStep);
     return false;
   }
   for (int i = 0; i < st.n_tasks; ++i) g->tasks[st.first_task + i].problem -= st.first_problem;
@@ -1139,8 +1217,10 @@ int group_add_problem(GroupPlan* g, int kind, const GemmArgs& a, char* err, int 
   }
   ok = ok && make_map(&p.map_c, a.C, a.N, a.M, a.ldc, 32, false, err, errlen);
   const bool mask_in = kind != 2 && a.mask_in != nullptr && a.act == ACT_RELU && a.aux != nullptr;
-  const bool has_aux = kind != 2 && a.aux != nullptr && !mask_in;
-  if (ok && has_aux) ok = make_map(&p.map_aux, a.aux, a.N, a.M, a.ldaux, 32, false, err, errlen);
+  const bool loss = kind == 0 && a.loss_x != nullptr && a.loss_partials != nullptr;
+  const bool has_aux = (kind != 2 && a.aux != nullptr && !mask_in) || loss;
+  if (ok && loss) ok = make_map(&p.map_aux, a.loss_x, a.N, a.M, a.ld_loss_x, 32, false, err, errlen);
+  else if (ok && has_aux) ok = make_map(&p.map_aux, a.aux, a.N, a.M, a.ldaux, 32, false, err, errlen);
   else if (ok) p.map_aux = p.map_c;
   if (!ok) return -1;
   p.M = a.M; p.N = a.N; p.K = a.K; p.BN = BN;
@@ -1152,6 +1232,8 @@ int group_add_problem(GroupPlan* g, int kind, const GemmArgs& a, char* err, int 
   p.mask_in = mask_in ? a.mask_in : nullptr;
   p.mask_out = (kind == 0 && a.act == ACT_RELU && !a.aux) ? a.mask_out : nullptr;
   p.ldmask = a.ldmask;
+  p.loss_partials = loss ? a.loss_partials : nullptr;
+  p.loss_scale = a.loss_scale; p.loss_binary = a.loss_binary;
   g->problems.push_back(p);
   g->uploaded = false;
   return (int)g->problems.size() - 1;
@@ -1172,7 +1254,7 @@ int group_add_task(GroupPlan* g, int prob, int m_blk, int n_blk, int kb0, int nk
   t.bn = p.BN;
   t.flags = (p.a_mn ? TF_A_MN : 0) | (p.b_mn ? TF_B_MN : 0) | (p.reduce ? TF_REDUCE : 0) | (p.has_aux ? TF_AUX : 0) |
             (p.round_out ? TF_ROUND : 0) | (p.colsum ? TF_COLSUM : 0) | (p.mask_out ? TF_MASK_OUT : 0) |
-            (p.mask_in ? TF_MASK_IN : 0);
+            (p.mask_in ? TF_MASK_IN : 0) | (p.loss_partials ? TF_LOSS : 0);
   t.act = p.act; t.M = p.M; t.N = p.N;
   g->tasks.push_back(t);
   g->uploaded = false;
@@ -1181,15 +1263,15 @@ int group_add_task(GroupPlan* g, int prob, int m_blk, int n_blk, int kb0, int nk
 
 // an elementwise task over row block m_blk (kind 0: latent forward, 1: latent backward; arguments: group_set_elem)
 int group_add_elt_task(GroupPlan* g, int kind, int m_blk, int batch, int wait_ctr, int wait_cnt, int wait_val,
-                       int wait2_ctr, int wait2_val, int signal_ctr) {
+                       int wait2_ctr, int wait2_val, int signal_ctr, int wait2_cnt) {
   GTask t;
   memset(&t, 0, sizeof t);
   t.problem = (int)g->problems.size() > 0 ? g->sites.back().first_problem : 0;   // unused; keeps the site-relative rebase >= 0
-  t.m_blk = m_blk; t.nkb = 0;
+  t.m_blk = m_blk; t.nkb = 0; t.kb0 = wait2_cnt;
   t.wait_ctr = wait_ctr; t.wait_cnt = wait_cnt; t.wait_val = wait_val;
   t.wait2_ctr = wait2_ctr; t.wait2_val = wait2_val; t.signal_ctr = signal_ctr;
   t.bn = 64;
-  t.flags = kind == 0 ? TF_ELT_LATENT_FWD : TF_ELT_LATENT_BWD;
+  t.flags = kind == 0 ? TF_ELT_LATENT_FWD : kind == 1 ? TF_ELT_LATENT_BWD : TF_ELT_FINALIZE;
   t.M = batch;
   g->tasks.push_back(t);
   g->uploaded = false;
@@ -1214,6 +1296,8 @@ bool group_upload(GroupPlan* g, char* err, int errlen) {
       e = cudaFuncSetAttribute(gemm_group_kernel<kSiteProblemsSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
       if (e == cudaSuccess)
         e = cudaFuncSetAttribute(gemm_group_kernel<kSiteProblemsLarge>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(gemm_group_kernel<kSiteProblemsStep>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
       attr_done = (e == cudaSuccess);
     }
   }
@@ -1224,23 +1308,28 @@ bool group_upload(GroupPlan* g, char* err, int errlen) {
 
 namespace {
 void launch_site(const GroupPlan* g, int site, uint32_t* queue, int reset_first, int reset_count, int dynamic_first,
-                 unsigned long long* tl, cudaStream_t s) {
+                 unsigned long long* tl, cudaStream_t s, int advance = 0) {
   const GroupSite& st = g->sites[site];
   if (st.n_tasks <= 0) return;
   static const int env_mode = (getenv("VAEASSOC_EPI_BIAS_SHFL") ? 0 : 2) | (getenv("VAEASSOC_EPI_TMA_STORE") ? 4 : 0) |
                               (getenv("VAEASSOC_DEBUG_SKIP_MATH") ? 8 : 0) | (getenv("VAEASSOC_DEBUG_SKIP_STORE") ? 16 : 0) |
                               (getenv("VAEASSOC_EPI_STAGGER_NS") ? (std::max(0, std::min(4000, atoi(getenv("VAEASSOC_EPI_STAGGER_NS")))) << 8) : 0);
-  const int mode = (dynamic_first ? 1 : 0) | env_mode;
+  const int mode = (dynamic_first ? 1 : 0) | env_mode | (advance ? 32 : 0);
   const int clusters = std::min(st.n_tasks, kNumSMs / 2);
   if (st.n_problems <= kSiteProblemsSmall) {
     GParams<kSiteProblemsSmall> prm;
     memcpy(prm.p, g->problems.data() + st.first_problem, (size_t)st.n_problems * sizeof(GProblem));
     gemm_group_kernel<kSiteProblemsSmall><<<2 * clusters, kThreads, SMEM_BYTES, s>>>(
         prm, g->elem, g->d_tasks + st.first_task, st.n_tasks, g->d_counters, queue, reset_first, reset_count, mode, tl);
-  } else {
+  } else if (st.n_problems <= kSiteProblemsLarge) {
     GParams<kSiteProblemsLarge> prm;
     memcpy(prm.p, g->problems.data() + st.first_problem, (size_t)st.n_problems * sizeof(GProblem));
     gemm_group_kernel<kSiteProblemsLarge><<<2 * clusters, kThreads, SMEM_BYTES, s>>>(
+        prm, g->elem, g->d_tasks + st.first_task, st.n_tasks, g->d_counters, queue, reset_first, reset_count, mode, tl);
+  } else {
+    GParams<kSiteProblemsStep> prm;
+    memcpy(prm.p, g->problems.data() + st.first_problem, (size_t)st.n_problems * sizeof(GProblem));
+    gemm_group_kernel<kSiteProblemsStep><<<2 * clusters, kThreads, SMEM_BYTES, s>>>(
         prm, g->elem, g->d_tasks + st.first_task, st.n_tasks, g->d_counters, queue, reset_first, reset_count, mode, tl);
   }
 }
@@ -1250,8 +1339,8 @@ void launch_site(const GroupPlan* g, int site, uint32_t* queue, int reset_first,
 // launch site (task-queue head, clusters-left count; the kernel rewinds them and the counters
 // [reset_first, +reset_count) when its last cluster leaves)
 void group_launch(const GroupPlan* g, int site, uint32_t* queue, int reset_first, int reset_count, int dynamic_first,
-                  cudaStream_t s) {
-  launch_site(g, site, queue, reset_first, reset_count, dynamic_first, nullptr, s);
+                  cudaStream_t s, int advance) {
+  launch_site(g, site, queue, reset_first, reset_count, dynamic_first, nullptr, s, advance);
 }
 
 // debug only (VAEASSOC_TC_TIMELINE): one more run of the range with %globaltimer stamps per task; prints, relative to

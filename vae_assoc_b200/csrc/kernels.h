@@ -30,6 +30,13 @@ struct GemmArgs {
   uint32_t* mask_out = nullptr;
   const uint32_t* mask_in = nullptr;
   int64_t ldmask = 0;
+  // NN on the tcgen05 path, output layer of a decoder: the epilogue turns the pre-activation straight into the
+  // reconstruction loss and d cost / d pre-activation (vae_assoc.py:321-328): C receives d a, `loss_x` is the target,
+  // every epilogue warp leaves its loss sum in loss_partials[((m_blk * tiles_n + n_blk) * 2 + CTA) * warps + warp]
+  const float* loss_x = nullptr; int64_t ld_loss_x = 0;
+  float* loss_partials = nullptr;
+  float loss_scale = 0.f;   // binary: w / B_global ; Gaussian: w
+  int loss_binary = 0;
 };
 
 void launch_gemm_nn_simt(const GemmArgs& a, cudaStream_t s);
@@ -66,8 +73,9 @@ int group_add_task(GroupPlan* g, int prob, int m_blk, int n_blk, int kb0, int nk
 int group_num_tasks(const GroupPlan* g);
 // elementwise task over the 256 rows of row block m_blk, executed by the epilogue warps of whichever CTA pair pops it
 // (kind 0: latent forward, 1: latent backward -- arguments from group_set_elem); waits / signals like a tile task
+// kind 2: cost finalize (sums the block partials of the loss / latent tasks; arguments: GElem::fin), one per launch
 int group_add_elt_task(GroupPlan* g, int kind, int m_blk, int batch, int wait_ctr, int wait_cnt, int wait_val,
-                       int wait2_ctr, int wait2_val, int signal_ctr);
+                       int wait2_ctr, int wait2_val, int signal_ctr, int wait2_cnt = 1);
 struct GElem;
 void group_set_elem(GroupPlan* g, const GElem& e);
 // a launch site = the problems / tasks added between group_begin() and group_end(): ONE kernel launch (<= 24 problems)
@@ -78,8 +86,9 @@ void group_set_counters(GroupPlan* g, uint32_t* d_counters, int n);
 bool group_upload(GroupPlan* g, char* err, int errlen);
 // dynamic_first: every task (the first one included) comes from the atomic queue -- required whenever a kernel that
 // waits on a peer GPU (NCCL) may hold SMs while this launch is resident
+// advance: the finalize task of the launch (if any) bumps the Adam step counter
 void group_launch(const GroupPlan* g, int site, uint32_t* queue, int reset_first, int reset_count, int dynamic_first,
-                  cudaStream_t s);
+                  cudaStream_t s, int advance = 0);
 void group_debug_timeline(const GroupPlan* g, int site, uint32_t* queue, int reset_first, int reset_count,
                           cudaStream_t s);   // debug: per-task %globaltimer stamps to stderr
 #ifndef VAEASSOC_EPI_WARPS
@@ -168,12 +177,28 @@ struct LatentBwdArgs {
 };
 void launch_latent_bwd(const LatentBwdArgs& a, cudaStream_t s);
 
+struct FinalizeArgs {
+  int n_mod = 0;
+  int binary[4] = {0, 0, 0, 0};
+  float weight[4] = {0, 0, 0, 0};
+  float inv_global_batch = 0.f, lambda = 0.f;
+  const float* partials_latent = nullptr; int blocks_latent = 0;
+  // reconstruction partials of modality m: blocks_recon[m] values at partials_recon[m][i * stride_recon[m] + off_recon[m]]
+  const float* partials_recon[4] = {nullptr, nullptr, nullptr, nullptr}; int blocks_recon[4] = {0, 0, 0, 0};
+  int stride_recon[4] = {kCostSlots, kCostSlots, kCostSlots, kCostSlots}; int off_recon[4] = {0, 2, 4, 6};
+  float* scalars = nullptr;         // [16]: [m] vae_cost_m, [4+m] recon sum, [8] assoc sum, [9] cost (local)
+  float* cost_slot = nullptr;       // spare slot of the flat gradient buffer (all-reduced with the grads)
+  int64_t* step_dev = nullptr;      // incremented when `advance`
+  int advance = 0;
+};
+
 // arguments of the elementwise tasks of a tile-kernel plan (kernel parameter of gemm_group_kernel)
 struct GElem {
   LatentArgs lf;             // partials: [(row block * 2 + CTA) * 4 + warp][kCostSlots]
   LatentBwdArgs lb;
   float* bh_grad[4] = {nullptr, nullptr, nullptr, nullptr};   // bias gradient of the heads layer per modality
                                                               // (column sums of d mu | d log sigma^2), or null
+  FinalizeArgs fin;          // one-launch form: the cost reduction is a task of the tile kernel as well
 };
 
 struct ReconArgs {
@@ -188,18 +213,6 @@ struct ReconArgs {
 };
 int launch_recon_loss(const ReconArgs& a, cudaStream_t s);        // returns number of blocks
 
-struct FinalizeArgs {
-  int n_mod = 0;
-  int binary[4] = {0, 0, 0, 0};
-  float weight[4] = {0, 0, 0, 0};
-  float inv_global_batch = 0.f, lambda = 0.f;
-  const float* partials_latent = nullptr; int blocks_latent = 0;
-  const float* partials_recon[4] = {nullptr, nullptr, nullptr, nullptr}; int blocks_recon[4] = {0, 0, 0, 0};
-  float* scalars = nullptr;         // [16]: [m] vae_cost_m, [4+m] recon sum, [8] assoc sum, [9] cost (local)
-  float* cost_slot = nullptr;       // spare slot of the flat gradient buffer (all-reduced with the grads)
-  int64_t* step_dev = nullptr;      // incremented when `advance`
-  int advance = 0;
-};
 void launch_finalize(const FinalizeArgs& a, cudaStream_t s);
 
 // ------------------------------------------------------------------------------------------------------

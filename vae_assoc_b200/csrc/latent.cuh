@@ -83,4 +83,42 @@ __device__ __forceinline__ void latent_bwd_elem(const LatentBwdArgs& a, int m, i
   a.dheads[m][r * 2 * nz + nz + k] = dl;
 }
 
+// ---- reconstruction loss of one element from the decoder's pre-activation `a` (fused into the output-layer epilogue
+// of the tile kernel; tf32 mode, tolerance 2e-3: ex2 / lg2 / rcp approximations, five MUFU operations per element) ----
+constexpr float kCeEps = 1e-3f;   // vae_assoc.py:322-323 (the comment there says 1e-10; the code says 1e-3)
+
+// Bernoulli cross-entropy with the reference's clamp: x_hat = sigmoid(a), loss = -(x log(1e-3 + x_hat) +
+// (1 - x) log(1e-3 + 1 - x_hat))  (:321-324); da = scale * d loss / d a, the two quotients over one reciprocal
+__device__ __forceinline__ float recon_logit_binary(float a, float x, float scale, float& da) {
+  const float xh = __fdividef(1.0f, 1.0f + __expf(-a));
+  const float p = kCeEps + xh;
+  const float q = (kCeEps + 1.0f) - xh;              // evaluation order of :323
+  da = scale * ((1.0f - x) * p - x * q) * __fdividef(xh * (1.0f - xh), p * q);
+  return -(x * __logf(p) + (1.0f - x) * __logf(q));
+}
+// Gaussian: tf.nn.l2_loss(x_hat - x) (:327-328), x_hat = a
+__device__ __forceinline__ float recon_logit_gaussian(float a, float x, float scale, float& da) {
+  const float d = a - x;
+  da = scale * d;
+  return 0.5f * d * d;
+}
+
+// sums[2m] = reconstruction sum of modality m, sums[2m+1] = its prior-KL sum, sums[8] = association-KL sum (this rank's
+// rows): per-modality cost :340, total :368-371; one thread
+__device__ __forceinline__ void finalize_combine(const FinalizeArgs& a, const float* sums, int advance) {
+  float cost = 0.f;
+  for (int m = 0; m < a.n_mod; ++m) {
+    const float rec = a.binary[m] ? sums[2 * m] * a.inv_global_batch : sums[2 * m];   // :324 per-row | :328 scalar
+    const float c = (rec + sums[2 * m + 1] * a.inv_global_batch) * a.weight[m];       // :340
+    a.scalars[m] = c;
+    a.scalars[4 + m] = sums[2 * m];
+    cost += c;
+  }
+  a.scalars[8] = sums[8];
+  cost += a.lambda * sums[8];                                                          // :369
+  a.scalars[9] = cost;
+  if (a.cost_slot) *a.cost_slot = cost;
+  if (advance && a.step_dev) *a.step_dev += 1;
+}
+
 }  // namespace vaeassoc

@@ -17,8 +17,6 @@ namespace vaeassoc {
 
 namespace {
 
-constexpr float kCeEps = 1e-3f;   // vae_assoc.py:322-323 (the comment there says 1e-10; the code says 1e-3)
-
 // ---------------------------------------------------------------------------------------------------
 // staging: copy caller rows into the library's padded input buffers (rounding to tf32 when they feed
 // tcgen05 GEMMs) and produce this step's eps (copy of injected noise, or Philox).
@@ -244,31 +242,17 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinalizeArgs a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int nq = 2 * a.n_mod + 1;
   for (int qi = warp; qi < nq; qi += nwarps) {
-    const float* src; int nblk, slot;
-    if (qi == 2 * a.n_mod) { src = a.partials_latent; nblk = a.blocks_latent; slot = 8; }
-    else if (qi & 1) { src = a.partials_latent; nblk = a.blocks_latent; slot = qi; }
-    else { src = a.partials_recon[qi >> 1]; nblk = a.blocks_recon[qi >> 1]; slot = qi; }
+    const float* src; int nblk, slot, stride = kCostSlots, off;
+    if (qi == 2 * a.n_mod) { src = a.partials_latent; nblk = a.blocks_latent; slot = 8; off = 8; }
+    else if (qi & 1) { src = a.partials_latent; nblk = a.blocks_latent; slot = qi; off = qi; }
+    else { src = a.partials_recon[qi >> 1]; nblk = a.blocks_recon[qi >> 1]; slot = qi; stride = a.stride_recon[qi >> 1]; off = a.off_recon[qi >> 1]; }
     float acc = 0.f;
-    for (int b = lane; b < nblk; b += 32) acc += src[(int64_t)b * kCostSlots + slot];
+    for (int b = lane; b < nblk; b += 32) acc += src[(int64_t)b * stride + off];
     acc = warp_sum(acc);
     if (lane == 0) sums[slot] = acc;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    float cost = 0.f;
-    for (int m = 0; m < a.n_mod; ++m) {
-      const float rec = a.binary[m] ? sums[2 * m] * a.inv_global_batch : sums[2 * m];   // :324 per-row | :328 scalar
-      const float c = (rec + sums[2 * m + 1] * a.inv_global_batch) * a.weight[m];       // :340
-      a.scalars[m] = c;
-      a.scalars[4 + m] = sums[2 * m];
-      cost += c;
-    }
-    a.scalars[8] = sums[8];
-    cost += a.lambda * sums[8];                                                          // :369
-    a.scalars[9] = cost;
-    if (a.cost_slot) *a.cost_slot = cost;
-    if (a.advance && a.step_dev) *a.step_dev += 1;
-  }
+  if (threadIdx.x == 0) finalize_combine(a, sums, a.advance);
 }
 
 inline int grid_for_elems(int64_t n, int per_block) {
