@@ -108,5 +108,9 @@ def build(force=False, verbose=True):
 if __name__ == "__main__":
     if "--w16" in sys.argv:
         build_variant("w16", ["VAEASSOC_EPI_WARPS=16"])
+    elif "--timeline" in sys.argv:
+        build_variant("tl", ["VAEASSOC_TIMELINE=1"])
+    elif "--epi-debug" in sys.argv:
+        build_variant("dbg", ["VAEASSOC_EPI_DEBUG=1"])
     else:
         build(force="--force" in sys.argv)

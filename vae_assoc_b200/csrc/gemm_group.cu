@@ -62,7 +62,10 @@ constexpr int UMMA_K = 8;        // tf32: 32 bytes per instruction
 constexpr int kEpiWarps = VAEASSOC_EPI_WARPS;   // kSlots warps per TMEM lane quarter; slot s takes chunks s, s + kSlots, ...
 constexpr int kSlots = kEpiWarps / 4;
 static_assert(kEpiWarps % 4 == 0 && kSlots >= 1 && kSlots <= 4, "epilogue warps come in groups of four (one per TMEM lane quarter)");
-constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int kThreads = 64 + 32 * kEpiWarps + 32;   // producer, MMA issuer, epilogue warps, signal warp
+constexpr int kSignalWarp = 2 + kEpiWarps;
+constexpr int kDoneRing = 4;                          // tile-completion barriers between the epilogue warps and the signal warp
+constexpr int kBarRegion = 640;                       // bytes: barriers, TMEM slot, task ring, signal-warp sequence word
 constexpr int kStages = 4;
 constexpr int A_BYTES = BM_CTA * BK * 4;          // 16 KB
 constexpr int B_BYTES_MAX = 128 * BK * 4;         // BN/2 <= 128 columns
@@ -72,10 +75,18 @@ constexpr int kEpiBufs = kEpiWarps <= 8 ? 3 : 1;  // rotating boxes per epilogue
 constexpr int EPI_WARP_BYTES = kEpiBufs * CHUNK_BYTES;
 constexpr int kAccCols = 256;                     // TMEM columns per accumulator
 constexpr int kTmemCols = 2 * kAccCols;
+#ifndef VAEASSOC_TIMELINE
+#define VAEASSOC_TIMELINE 0            // per-task %globaltimer stamps (VAEASSOC_TC_TIMELINE): `python -m vae_assoc_b200.build --timeline`
+#endif
+constexpr bool kTimeline = VAEASSOC_TIMELINE != 0;
+#ifndef VAEASSOC_EPI_DEBUG
+#define VAEASSOC_EPI_DEBUG 0
+#endif
+constexpr bool kEpiDebug = VAEASSOC_EPI_DEBUG != 0;   // (compiled out by default: the stamps cost registers in every role)
 constexpr int kTL = 16;                          // debug timeline: 64-bit stamps per task
 constexpr int kSched = 8;                        // depth of the task-index ring
 constexpr int kBiasStrip = 128;                  // bytes per epilogue warp: the 32 bias values of the current chunk
-constexpr int SMEM_BYTES = kStages * STAGE_BYTES + kEpiWarps * EPI_WARP_BYTES + 512 /*barriers, task ring*/ +
+constexpr int SMEM_BYTES = kStages * STAGE_BYTES + kEpiWarps * EPI_WARP_BYTES + kBarRegion /*barriers, task ring*/ +
                            kEpiWarps * kBiasStrip + 1024 /*align*/;
 static_assert(SMEM_BYTES <= 232448, "more than the 227 KB a CTA may opt into");
 
@@ -389,6 +400,53 @@ __device__ __forceinline__ bool elect_one() {
 // value of lane 0 in every lane
 __device__ __forceinline__ int bcast(int v) { return __shfl_sync(0xffffffffu, v, 0); }
 
+// one 32-column chunk of a loss-fused output tile, this lane's row: v[j] = pre-activation bits in, d cost / d a bits out
+// (rounded to tf32 when `round`); x = the target row in the swizzled aux box (16-byte column j at xrow + ((j ^ xsw) << 4));
+// returns the row's loss over the chunk.  Columns >= ncols (past N, or the whole row past M) contribute nothing and
+// leave exact zeros (the column sums of the bias gradient read the staged tile).
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+template <bool BINARY, bool FULL>
+__device__ __forceinline__ float loss_chunk(uint32_t (&v)[32], uint32_t xrow, uint32_t xsw, float scale, bool round, int ncols) {
+  float acc0 = 0.0f, acc1 = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 xv = lds128(xrow + (((uint32_t)j ^ xsw) << 4));
+    const float xs4[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float a = __uint_as_float(v[4 * j + k]), x = xs4[k];
+      float da, l;
+      if (BINARY) {
+        // x_hat = sigmoid(a); loss = -(x log(1e-3 + x_hat) + (1 - x) log(1e-3 + 1 - x_hat))   vae_assoc.py:321-324
+        // (in log2 units here, scaled once per task); d loss / d a over ONE reciprocal
+        const float xh = rcp_approx(1.0f + ex2_approx(a * -1.4426950408889634f));
+        const float pp = kCeEps + xh;
+        const float qq = (kCeEps + 1.0f) - xh;            // evaluation order of :323
+        const float omx = 1.0f - x;
+        l = x * lg2_approx(pp) + omx * lg2_approx(qq);
+        da = (scale * (omx * pp - x * qq)) * ((xh * (1.0f - xh)) * rcp_approx(pp * qq));
+      } else {
+        const float d = a - x;                            // tf.nn.l2_loss(x_hat - x), x_hat = a   :327-328
+        da = scale * d;
+        l = d * d;
+      }
+      uint32_t bits = __float_as_uint(da);
+      if (round) bits = (bits + 0x1000u) & 0xffffe000u;
+      if (FULL) {
+        v[4 * j + k] = bits;
+      } else {
+        const bool live = 4 * j + k < ncols;
+        l = live ? l : 0.0f;
+        v[4 * j + k] = live ? bits : 0u;
+      }
+      if (k & 1) acc1 += l; else acc0 += l;
+    }
+  }
+  return (BINARY ? -0.6931471805599453f : 0.5f) * (acc0 + acc1);
+}
+
 __device__ __forceinline__ GTask load_task(const GTask* __restrict__ tasks, int t) {
   GTask tk;
   if (t >= 0) {
@@ -419,13 +477,15 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t epi_base = base + kStages * STAGE_BYTES;
   const uint32_t bar_base = epi_base + kEpiWarps * EPI_WARP_BYTES;
-  const uint32_t strip_base = bar_base + 512u;
+  const uint32_t strip_base = bar_base + (uint32_t)kBarRegion;
   const int dynamic_first = mode & 1;
-  const bool bias_smem = (mode & 2) != 0, tma_store = (mode & 4) != 0;
-  // timing experiments only (wrong results): VAEASSOC_DEBUG_SKIP_MATH / _SKIP_STORE drop parts of the NN / NT epilogue
-  const bool dbg_skip_math = (mode & 8) != 0, dbg_skip_store = (mode & 16) != 0;
+  // epilogue variants behind environment switches (bias by 32 shuffles, TMA stores, timing experiments that drop parts of
+  // the epilogue) exist only in the debug build (-DVAEASSOC_EPI_DEBUG=1): each costs a live register or predicate in the
+  // chunk loop, whose allocation sits at the 168-register limit
+  const bool bias_smem = !kEpiDebug || (mode & 2) != 0, tma_store = kEpiDebug && (mode & 4) != 0;
+  const bool dbg_skip_math = kEpiDebug && (mode & 8) != 0, dbg_skip_store = kEpiDebug && (mode & 16) != 0;
   const int fin_advance = (mode >> 5) & 1;               // the finalize task bumps the Adam step counter
-  const uint32_t stagger_ns = (uint32_t)mode >> 8;      // VAEASSOC_EPI_STAGGER_NS: the odd chunk slots start this much later
+  const uint32_t stagger_ns = kEpiDebug ? (uint32_t)mode >> 8 : 0u;      // VAEASSOC_EPI_STAGGER_NS: the odd chunk slots start this much later
   // barriers: full[s] (leader CTA only), empty[s], tmem_full[2], tmem_empty[2] (leader CTA only), aux[epilogue warp],
   // sched_full[kSched], sched_empty[kSched] (leader CTA only); then the TMEM slot and the task-index ring
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -438,13 +498,18 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
   auto sched_empty_bar = [&](int r) { return bar_base + 8u * (2 * kStages + 4 + kAuxBars + kSched + r); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4 + kAuxBars + 2 * kSched);
   auto sched_task = [&](int r) { return tmem_slot + 8u + 4u * r; };
+  // done[i]: the kEpiWarps epilogue warps of THIS CTA have stored their part of the i-th (mod kDoneRing) signalling tile
+  auto done_bar = [&](uint32_t i) { return tmem_slot + 8u + 4u * kSched + 8u * (i % kDoneRing); };
+  const uint32_t sig_seq_addr = tmem_slot + 8u + 4u * kSched + 8u * 2 * kDoneRing;   // signalling tiles published so far
+  static_assert(8 * (2 * kStages + 4 + kEpiBufs * kEpiWarps + 2 * kSched) + 8 + 4 * kSched + 16 * kDoneRing + 8 <= kBarRegion,
+                "barrier region too small");
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   // consumers of a published task index: leader MMA lane + peer producer lane + 2 x kEpiWarps epilogue lanes
-  constexpr uint32_t kSchedConsumers = 2 + 2 * kEpiWarps;
+  constexpr uint32_t kSchedConsumers = 2 + 2 * kEpiWarps + 2;     // ... + the signal warp of either CTA
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -452,6 +517,8 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
     for (int e = 0; e < kEpiWarps; ++e)
       for (int b = 0; b < kEpiBufs; ++b) mbar_init(aux_bar(e, b), 1);
     for (int r = 0; r < kSched; ++r) { mbar_init(sched_full_bar(r), 1); mbar_init(sched_empty_bar(r), kSchedConsumers); }
+    for (int i = 0; i < kDoneRing; ++i) mbar_init(done_bar(i), kEpiWarps);
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(sig_seq_addr), "r"(0u) : "memory");
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_pair(tmem_slot, kTmemCols);
@@ -459,7 +526,7 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  const unsigned long long t_entry = tl ? gtimer() : 0ull;
+  const unsigned long long t_entry = (kTimeline && tl) ? gtimer() : 0ull;
 
   // consumer side of the task ring: next task index (or -1 when the queue is drained); one calling lane per role
   uint32_t fetches = 0;
@@ -533,7 +600,7 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
           fence_acq_rel_gpu();               // pairs with the producers' red.release.gpu
           fence_proxy_async_all();           // their generic-proxy stores -> our TMA (async proxy) loads
         }
-        if (tl && rank == 0) { tl[kTL * t + 0] = gtimer(); tl[kTL * t + 5] = blockIdx.x >> 1; tl[kTL * t + 6] = t_entry; }
+        if (kTimeline && tl && rank == 0) { tl[kTL * t + 0] = gtimer(); tl[kTL * t + 5] = blockIdx.x >> 1; tl[kTL * t + 6] = t_entry; }
       }
       __syncwarp();
       int t_after = -1;
@@ -545,7 +612,7 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
         const int k0 = (tk.kb0 + i) * BK;
         if (elect_one()) {
           mbar_wait(empty_bar(s), ((it / kStages) & 1) ^ 1);
-          if (tl && t == 0 && i < 64) tl[kTL * ntasks + (rank ? 128 : 0) + i] = gtimer();
+          if (kTimeline && tl && t == 0 && i < 64) tl[kTL * ntasks + (rank ? 128 : 0) + i] = gtimer();
           if (rank == 0) mbar_arrive_expect_tx(full_bar(s), stage_tx);
           // MN-major operands: one 3-D box {32 mn, 32 k, chunks} lands as [chunk][k][32 mn] (see make_map_mn)
           if (a_mn) tma_load_3d_pair(sa, &p->map_a, full_leader, 0, k0, m0 >> 5);
@@ -585,7 +652,7 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
         if (lane == 0) {
           mbar_wait(tmem_empty_bar(acc), ((tcount >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator
           tc_fence_after();
-          if (tl) { tl[kTL * t + 1] = gtimer(); tl[kTL * t + 7] = clock64(); }
+          if (kTimeline && tl) { tl[kTL * t + 1] = gtimer(); tl[kTL * t + 7] = clock64(); }
         }
         __syncwarp();
         for (int i = 0; i < tk.nkb; ++i, ++it) {
@@ -594,7 +661,7 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
           if (elect_one()) {
             mbar_wait(full_bar(s), (it / kStages) & 1);
             tc_fence_after();
-            if (tl && t == 0 && i < 64) tl[kTL * ntasks + 64 + i] = gtimer();
+            if (kTimeline && tl && t == 0 && i < 64) tl[kTL * ntasks + 64 + i] = gtimer();
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint64_t da = a_mn ? desc_mn_major(sa + k * 1024) : desc_k_major(sa + k * 32);
@@ -608,12 +675,35 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
         }
         if (elect_one()) {
           umma_commit_pair(tmem_full_bar(acc)); // accumulator complete (both CTAs)
-          if (tl) { tl[kTL * t + 2] = gtimer(); tl[kTL * t + 7] = clock64() - tl[kTL * t + 7]; }
+          if (kTimeline && tl) { tl[kTL * t + 2] = gtimer(); tl[kTL * t + 7] = clock64() - tl[kTL * t + 7]; }
         }
         t = bcast(t_after);
         tk = load_task(tasks, t);
       }
     }
+  } else if (warp == kSignalWarp) {
+    // ===================== signal warp (both CTAs): publishes finished tiles to the other clusters =====================
+    // Making a tile's stores visible GPU-wide costs a MEMBAR.GPU (~0.9 us: every outstanding store of the SM must be
+    // acknowledged by L2).  The epilogue warps used to pay it at the end of every tile (red.release.gpu), 5 % of their
+    // time; now they only arrive on a CTA-local barrier and this warp releases: its acquire of the barrier makes their
+    // stores cumulative with its fence.acq_rel.gpu, and the counter add carries the CTA's kEpiWarps arrivals at once.
+    if (lane == 0) {
+      uint32_t seq = 0;
+      int t = next_task();
+      while (t >= 0) {
+        const GTask* tp = tasks + t;
+        const int flags = __ldg(&tp->flags), sig = __ldg(&tp->signal_ctr);
+        if (!(flags & TF_ELT) && sig >= 0) {
+          mbar_wait(done_bar(seq), (seq / kDoneRing) & 1);
+          fence_acq_rel_gpu();
+          asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(counters + sig), "r"((uint32_t)kEpiWarps) : "memory");
+          ++seq;
+          asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(sig_seq_addr), "r"(seq) : "memory");
+        }
+        t = next_task();
+      }
+    }
+    __syncwarp();
   } else {
     // ===================== epilogue (warps 2..9 of both CTAs) =====================
     const int e = warp - 2;                 // epilogue warp index
@@ -622,6 +712,7 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
     const uint32_t ebuf = epi_base + e * EPI_WARP_BYTES;         // kEpiBufs rotating 32 x 32 boxes
     const uint32_t tmem_empty_leader0 = mapa(tmem_empty_bar(0), 0), tmem_empty_leader1 = mapa(tmem_empty_bar(1), 0);
     uint32_t tcount = 0, cidx = 0, aux_phase = 0, red_pending = 0;   // cidx: chunks processed so far (box = cidx % 3)
+    uint32_t sig_count = 0;                 // signalling tiles finished so far (index into the done-barrier ring)
     auto next_task_warp = [&]() -> int {
       int t = 0;
       if (lane == 0) t = next_task();
@@ -752,7 +843,7 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
       }
       mbar_wait(tmem_full_bar(acc), (tcount >> 1) & 1);
       tc_fence_after();
-      if (tl && rank == 0 && warp == 2 && lane == 0) { tl[kTL * t + 3] = gtimer(); tl[kTL * t + 15] = (unsigned long long)clock64(); }
+      if (kTimeline && tl && rank == 0 && warp == 2 && lane == 0) { tl[kTL * t + 3] = gtimer(); tl[kTL * t + 15] = (unsigned long long)clock64(); }
       // a bulk reduce-add of an earlier task may still be reading one of the boxes: drain those reads once, here,
       // instead of polling in every chunk (reduce tasks themselves keep the per-chunk wait below)
       if (!reduce && !tma_store && red_pending) {
@@ -779,7 +870,7 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
         const uint32_t b = cidx % kEpiBufs;
         const uint32_t ob = ebuf + b * CHUNK_BYTES;
         tmem_ld_wait(v);
-        if (tl && rank == 0 && warp == 2 && lane == 0 && i == 0) tl[kTL * t + 9] = (unsigned long long)clock64();
+        if (kTimeline && tl && rank == 0 && warp == 2 && lane == 0 && i == 0) tl[kTL * t + 9] = (unsigned long long)clock64();
         if (dbg_skip_math) {
         } else if (mask_in != nullptr) {
           // relu': one bit per element, already in registers; the tf32 rounding (round-to-nearest, ties away = add half
@@ -816,23 +907,15 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
             }
           }
           const int ncols = (row0 + lane < tk.M) ? min(32, N - (n0 + c * 32)) : 0;    // live columns of this lane's row
-          const float lscale = p->loss_scale;
-          const bool lbin = p->loss_binary != 0;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 xv = lds128(ob + swz(lane, j));
-            const float xs4[4] = {xv.x, xv.y, xv.z, xv.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              float da;
-              const float av = __uint_as_float(v[4 * j + k]);
-              const float l = lbin ? recon_logit_binary(av, xs4[k], lscale, da) : recon_logit_gaussian(av, xs4[k], lscale, da);
-              const bool live = 4 * j + k < ncols;
-              loss_acc += live ? l : 0.0f;
-              uint32_t bits = __float_as_uint(da);
-              if (round_out) bits = (bits + 0x1000u) & 0xffffe000u;
-              v[4 * j + k] = live ? bits : 0u;           // dead rows / columns: exact zeros (the column sums read them)
-            }
+          const uint32_t xrow = ob + (uint32_t)lane * 128u, xsw = (uint32_t)(lane & 7);
+          // (the four variants are separate straight-line loops: a per-element select of the loss form serialised the 32
+          // independent MUFU chains of a chunk behind branches -- 18 us per tile instead of 7)
+          if (p->loss_binary) {
+            if (ncols == 32) loss_acc += loss_chunk<true, true>(v, xrow, xsw, p->loss_scale, round_out, 32);
+            else loss_acc += loss_chunk<true, false>(v, xrow, xsw, p->loss_scale, round_out, ncols);
+          } else {
+            if (ncols == 32) loss_acc += loss_chunk<false, true>(v, xrow, xsw, p->loss_scale, round_out, 32);
+            else loss_acc += loss_chunk<false, false>(v, xrow, xsw, p->loss_scale, round_out, ncols);
           }
         } else if (use_aux) {
           mbar_wait(aux_bar(e, b), (aux_phase >> b) & 1u);
@@ -911,7 +994,7 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = (n0 + c * 32 + j < N) ? v[j] : 0u;
         }
-        if (tl && rank == 0 && warp == 2 && lane == 0 && i == 0) tl[kTL * t + 11] = (unsigned long long)clock64();
+        if (kTimeline && tl && rank == 0 && warp == 2 && lane == 0 && i == 0) tl[kTL * t + 11] = (unsigned long long)clock64();
         if (mask_out != nullptr && !dbg_skip_math) {
           // bit j = (output j > 0); relu outputs are >= +0, so "bits != 0": sign of the negated bits, shifted in from
           // the right, two independent chains of 16
@@ -924,13 +1007,13 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
           if (interior_rows || row0 + lane < tk.M)
             mask_out[(size_t)(row0 + lane) * (size_t)p->ldmask + (n0 >> 5) + c] = (wh << 16) | wl;
         }
-        if (tl && rank == 0 && warp == 2 && lane == 0 && i == 0) tl[kTL * t + 12] = (unsigned long long)clock64();
+        if (kTimeline && tl && rank == 0 && warp == 2 && lane == 0 && i == 0) tl[kTL * t + 12] = (unsigned long long)clock64();
         if (reduce || tma_store) {
           // box b was handed to a bulk store / reduce-add three chunks ago: wait until that one has read it
           if (elect_one()) bulk_wait_read<kEpiBufs - 1>();
           __syncwarp();
         }
-        if (tl && rank == 0 && warp == 2 && lane == 0 && i == 0) tl[kTL * t + 13] = (unsigned long long)clock64();
+        if (kTimeline && tl && rank == 0 && warp == 2 && lane == 0 && i == 0) tl[kTL * t + 13] = (unsigned long long)clock64();
         // (in the aux case the lane overwrites exactly the 128 bytes it has just read: in place, no hazard)
         {
           const uint32_t sb = sts_base + b * CHUNK_BYTES;
@@ -939,7 +1022,7 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sb + (((uint32_t)j ^ sts_x) << 4)), "r"(v[4 * j]),
                          "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3]) : "memory");
         }
-        if (tl && rank == 0 && warp == 2 && lane == 0 && i == 0) tl[kTL * t + 14] = (unsigned long long)clock64();
+        if (kTimeline && tl && rank == 0 && warp == 2 && lane == 0 && i == 0) tl[kTL * t + 14] = (unsigned long long)clock64();
         if (i + 1 < nmine) tmem_ld32_issue(tmem_row + (uint32_t)((c + kSlots) * 32), v);
         if (reduce || tma_store) {
           fence_proxy_async_smem();
@@ -992,7 +1075,7 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
           const int col = n0 + c * 32 + lane;
           if (col < N) atomicAdd(colsum + col, (cs0 + cs1) + (cs2 + cs3));
         }
-        if (tl && rank == 0 && warp == 2 && lane == 0 && i == 0) tl[kTL * t + 10] = (unsigned long long)clock64();
+        if (kTimeline && tl && rank == 0 && warp == 2 && lane == 0 && i == 0) tl[kTL * t + 10] = (unsigned long long)clock64();
         if (use_aux && i + kEpiBufs < nmine) {
           __syncwarp();                    // every lane has finished with box b: refill it with the aux tile 3 chunks ahead
           if (elect_one()) {
@@ -1003,7 +1086,7 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
       }
       // every tcgen05.ld of this accumulator has completed (wait::ld): hand it back to the MMA issuer; the global
       // stores of all lanes are ordered before the elected lane's release by the warp barrier
-      if (tl && rank == 0 && warp == 2 && lane == 0) tl[kTL * t + 8] = gtimer();
+      if (kTimeline && tl && rank == 0 && warp == 2 && lane == 0) tl[kTL * t + 8] = gtimer();
       if (loss_task) {
         loss_acc = warp_sum(loss_acc);
         const int tiles_n = (N + BN - 1) / BN;
@@ -1016,10 +1099,16 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
         mbar_arrive_cluster_relaxed(acc ? tmem_empty_leader1 : tmem_empty_leader0, 0u);
         if (tk.signal_ctr >= 0) {
           if (reduce || tma_store) { bulk_wait_complete(); fence_proxy_async_all(); }   // bulk stores performed, then publish
-          red_release_gpu_add(counters + tk.signal_ctr, 1u);
+          // the signal warp must have consumed this ring slot's previous use (it lags by microseconds at most)
+          if (sig_count >= (uint32_t)kDoneRing) {
+            uint32_t done;
+            do { asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(done) : "r"(sig_seq_addr) : "memory"); } while (done + kDoneRing <= sig_count);
+          }
+          asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(done_bar(sig_count)) : "memory");
         }
       }
-      if (tl && rank == 0 && warp == 2 && lane == 0) tl[kTL * t + 4] = gtimer();
+      if (tk.signal_ctr >= 0) ++sig_count;
+      if (kTimeline && tl && rank == 0 && warp == 2 && lane == 0) tl[kTL * t + 4] = gtimer();
       t = t_after;
       tk = tk_after;
     }
@@ -1348,6 +1437,7 @@ void group_launch(const GroupPlan* g, int site, uint32_t* queue, int reset_first
 void group_debug_timeline(const GroupPlan* g, int site, uint32_t* queue, int reset_first, int reset_count, cudaStream_t s) {
   const int first = g->sites[site].first_task, count = g->sites[site].n_tasks;
   if (count <= 0) return;
+  if (!kTimeline) { fprintf(stderr, "[group timeline] not compiled in: python -m vae_assoc_b200.build --timeline, VAEASSOC_LIB=.../libvaeassoc_tl.so\n"); return; }
   unsigned long long* dev = nullptr;
   if (cudaMalloc(&dev, (size_t)count * kTL * 8 + 192 * 8) != cudaSuccess) return;
   cudaMemsetAsync(dev, 0, (size_t)count * kTL * 8 + 192 * 8, s);
