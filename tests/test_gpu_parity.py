@@ -388,7 +388,7 @@ def test_fused_schedules_match_four_launch(va, monkeypatch, batch):
     stand-alone latent kernels (same device code: csrc/latent.cuh).  All three must agree: every gradient of a first
     step, then the costs of 5 training steps.  "two" vs "four" differ by summation order only (2e-5); the fused loss
     epilogue forms d a over one reciprocal instead of two quotients, so a few d a entries land on the neighbouring tf32
-    value (1e-4).  Batch 700 = three row blocks of 256, the last one ragged."""
+    value (1e-4; 1e-3 at batch 2048, see below).  Batch 700 = three row blocks of 256, the last one ragged."""
     archs = vo.reference_archs(4)
     X = [x.astype(np.float32) for x in synth.synth_batch(archs, [True, False], 0, 1, 0, batch)]
     eps = philox.eps_rows(3, 0, 0, batch, 4).astype(np.float32)
@@ -409,16 +409,20 @@ def test_fused_schedules_match_four_launch(va, monkeypatch, batch):
         costs = [float(model.partial_fit(X, eps)) for _ in range(4)]
         out[mode] = (costs, c, grads, lat, dzm, launches, xh, rl)
         model.close()
-    for mode, tol in (("one", 1e-4), ("two", 2e-5)):
+    # (from four row blocks on, "one" hands tiles over by halves between dependent layers: its consumers sum their k-blocks in
+    # another order, a few activations land on the neighbouring tf32 value and a few relu masks flip -- the schedules then
+    # agree like two tf32 implementations do, not to summation order)
+    for mode, tol in (("one", 1e-4 if batch < 1024 else 1e-3), ("two", 2e-5)):
         np.testing.assert_allclose(out[mode][0], out["four"][0], rtol=tol)
         assert abs(out[mode][1] - out["four"][1]) <= tol * abs(out["four"][1])
         for a, b, n in zip(out[mode][2], out["four"][2], range(100)):
             assert rel_l2(a, b) < tol, (mode, n, rel_l2(a, b))   # same masks (the forward is bit-identical)
+        fwd_tol = 1e-5 if tol < 1e-3 else 5e-4      # forward quantities: bit-identical activations, or tf32-level agreement
         for m in range(2):
-            assert rel(out[mode][3][m], out["four"][3][m]) < 1e-5
+            assert rel(out[mode][3][m], out["four"][3][m]) < fwd_tol
             assert rel(out[mode][4][m], out["four"][4][m]) < 5 * tol
-            assert rel(out[mode][6][m], out["four"][6][m]) < 1e-6
-            assert rel(out[mode][7][m], out["four"][7][m]) < 1e-5
+            assert rel(out[mode][6][m], out["four"][6][m]) < fwd_tol
+            assert rel(out[mode][7][m], out["four"][7][m]) < fwd_tol
     assert out["one"][5] < out["two"][5] < out["four"][5], [out[k][5] for k in ("one", "two", "four")]   # launches per step
     assert out["one"][5] <= 4, out["one"][5]        # staging, gradient memset, the tile kernel, Adam
 

@@ -174,7 +174,7 @@ struct vaeassoc_ctx {
   // launch site (queue head, clusters-left), all self-cleaning (zero between launches)
   GroupPlan* gplan = nullptr;
   uint32_t* gsync = nullptr;
-  int n_ctr = 0, max_sites = 0;
+  int n_ctr = 0, n_ctr_half = 0, max_sites = 0;
   struct Seg { int site = 0, reset_first = 0, reset_count = 0; };
   Seg seg_enc, seg_dec, seg_bwd_dec, seg_bwd_enc;     // fused segments of the train step (dense modalities, tf32)
   bool fused = false;
@@ -479,7 +479,8 @@ void alloc_buffers(Ctx* c) {
   {
     // row-block counters: 12 activation / gradient tensors per modality x row blocks of 256; then the launch sites
     const int64_t rb = (B + 255) / 256;
-    c->n_ctr = (int)(c->cfg.n_modalities * 13 * rb);
+    c->n_ctr_half = (int)(c->cfg.n_modalities * 13 * rb);    // full counters, then the half-tile counters of the same tensors
+    c->n_ctr = 2 * c->n_ctr_half;
     c->max_sites = 1024;
     c->gsync = c->dalloc<uint32_t>(c->n_ctr + 2 * c->max_sites);
   }
@@ -934,6 +935,7 @@ void build_segments(Ctx* c) {
   const int RB = (B + 255) / 256;
   bool ok = c->cfg.precision == VAEASSOC_TF32 && !getenv("VAEASSOC_NO_FUSE");
   const bool nodeps = getenv("VAEASSOC_DEBUG_NODEPS") != nullptr;   // timing experiments only: wrong results
+  const bool half_ok = getenv("VAEASSOC_NO_HALF") == nullptr;       // half-tile hand-over between dependent layers (one-launch form)
   for (int m = 0; m < M && ok; ++m) {
     if (c->mods[m].conv) { ok = false; break; }
     if (c->ops_enc_mod[m].size() != 3 || c->ops_dec_mod[m].size() != 3 || c->ops_bwd_dec_mod[m].size() != 6 ||
@@ -946,8 +948,12 @@ void build_segments(Ctx* c) {
     GroupPlan* g = c->gplan;
     auto ctr = [&](int m, int T, int rb) { return (T * M + m) * RB + rb; };
     // tiles of a row-wise layer (NN / NT): one task per (row block, column tile)
+    // in_w > 0: the input tensor comes from row-wise tiles in_w k-blocks wide that publish their first half early
+    // (half-tile hand-over, gemm_group.cu TF_HALF); sig_half: this layer's tiles do so for their consumer; *out_w = this
+    // layer's tile width in k-blocks of its consumer when the hand-over pays (tiles of >= 4 chunks), else 0
     auto add_rowwise = [&](const Op& op, int m, int inT, int in_tn, int outT, float* colsum, int in_m = -1,
-                           const GemmArgs* override_args = nullptr) -> int {
+                           const GemmArgs* override_args = nullptr, int in_w = 0, bool sig_half = false,
+                           int* out_w = nullptr) -> int {
       if (nodeps) { inT = -1; outT = -1; }
       if (in_m < 0) in_m = m;
       GemmArgs a = override_args ? *override_args : op.gargs;
@@ -955,10 +961,15 @@ void build_segments(Ctx* c) {
       const int prob = group_add_problem(g, op.kind, a, err, sizeof err);
       if (prob < 0) fail("segment plan for %s failed: %s", op.name.c_str(), err);
       const int tm = group_problem_tiles_m(g, prob), tn = group_problem_tiles_n(g, prob), kb = group_problem_kblocks(g, prob);
+      const int bn = group_problem_bn(g, prob);
+      const bool sig = sig_half && outT >= 0 && bn >= 128 && half_ok;
+      const bool half = in_w > 0 && inT >= 0 && half_ok;
+      if (out_w) *out_w = sig ? bn / 32 : 0;
       for (int i = 0; i < tm; ++i)
         for (int j = 0; j < tn; ++j)
           group_add_task(g, prob, i, j, 0, kb, inT >= 0 ? ctr(in_m, inT, i) : -1, inT >= 0 ? 1 : 0,
-                         kGroupSignalsPerTile * in_tn, -1, 0, outT >= 0 ? ctr(m, outT, i) : -1);
+                         kGroupSignalsPerTile * in_tn, half ? ctr(in_m, inT, i) + c->n_ctr_half : -1, half ? in_w : 0,
+                         outT >= 0 ? ctr(m, outT, i) : -1, (half ? kTaskHalf : 0) | (sig ? kTaskSigHalf : 0));
       return tn;
     };
     // weight gradient (TN): the batch contraction is cut into row-block ranges; a task waits for dY over its range
@@ -1079,18 +1090,25 @@ void build_segments(Ctx* c) {
       c->one_built = false;
       if (!getenv("VAEASSOC_NO_ONE") && 17 * M <= 36) {
         std::vector<int> tno(M);
+        // modalities in order of increasing width: within a layer the short tasks come first, so that the narrow modality's
+        // chain (which the latent stage needs as much as the wide one's) never queues behind a wave of long main loops
+        std::vector<int> mord(M);
+        for (int m = 0; m < M; ++m) mord[m] = m;
+        if (!getenv("VAEASSOC_ORDER_DECLARED"))
+          std::stable_sort(mord.begin(), mord.end(), [&](int x, int y) { return c->mods[x].ni < c->mods[y].ni; });
         begin(c->seg_step, T_H1, T_COUNT);
-        for (int m = 0; m < M; ++m) tn1[m] = add_rowwise(c->ops_enc_mod[m][0], m, -1, 0, T_H1, nullptr);
-        for (int m = 0; m < M; ++m) tn2[m] = add_rowwise(c->ops_enc_mod[m][1], m, T_H1, tn1[m], T_H2, nullptr);
-        for (int m = 0; m < M; ++m) tnh[m] = add_rowwise(c->ops_enc_mod[m][2], m, T_H2, tn2[m], T_HD, nullptr);
+        std::vector<int> w1(M), w2(M), wo(M);
+        for (int m : mord) tn1[m] = add_rowwise(c->ops_enc_mod[m][0], m, -1, 0, T_H1, nullptr, -1, nullptr, 0, true, &w1[m]);
+        for (int m : mord) tn2[m] = add_rowwise(c->ops_enc_mod[m][1], m, T_H1, tn1[m], T_H2, nullptr, -1, nullptr, w1[m], true, &w2[m]);
+        for (int m : mord) tnh[m] = add_rowwise(c->ops_enc_mod[m][2], m, T_H2, tn2[m], T_HD, nullptr, -1, nullptr, w2[m]);
         for (int rb = 0; rb < RB; ++rb)
           group_add_elt_task(g, 0, rb, B, ctr(0, T_HD, rb), 1, S * tnh[0], M > 1 ? ctr(1, T_HD, rb) : -1, M > 1 ? S * tnh[1] : 0,
                              ctr(0, T_Z, rb));
-        for (int m = 0; m < M; ++m) tn1[m] = add_rowwise(c->ops_dec_mod[m][0], m, T_Z, 1, T_G1, nullptr, 0);
-        for (int m = 0; m < M; ++m) tn2[m] = add_rowwise(c->ops_dec_mod[m][1], m, T_G1, tn1[m], T_G2, nullptr);
+        for (int m : mord) tn1[m] = add_rowwise(c->ops_dec_mod[m][0], m, T_Z, 1, T_G1, nullptr, 0, nullptr, 0, true, &w1[m]);
+        for (int m : mord) tn2[m] = add_rowwise(c->ops_dec_mod[m][1], m, T_G1, tn1[m], T_G2, nullptr, -1, nullptr, w1[m], true, &w2[m]);
         FinalizeArgs fin = finalize_args(c, 0);
         fin.partials_latent = c->lat_partials; fin.blocks_latent = c->lat_blocks_elt;
-        for (int m = 0; m < M; ++m) {
+        for (int m : mord) {
           Mod& d = c->mods[m];
           GemmArgs a = c->ops_dec_mod[m][2].gargs;           // x_hat = act(g2 Vo + co)  ->  d a, loss
           const GemmArgs& w_o = c->ops_bwd_dec_mod[m][0].gargs;
@@ -1101,34 +1119,34 @@ void build_segments(Ctx* c) {
           a.loss_x = d.xs; a.ld_loss_x = d.nip; a.loss_partials = parts;
           a.loss_scale = d.cfg.binary ? d.cfg.weight * (1.0f / (float)global_batch(c)) : d.cfg.weight;
           a.loss_binary = d.cfg.binary ? 1 : 0;
-          tno[m] = add_rowwise(c->ops_dec_mod[m][2], m, T_G2, tn2[m], T_DA, w_o.bias_grad, -1, &a);
+          tno[m] = add_rowwise(c->ops_dec_mod[m][2], m, T_G2, tn2[m], T_DA, w_o.bias_grad, -1, &a, w2[m], true, &wo[m]);
           fin.partials_recon[m] = parts; fin.blocks_recon[m] = RB * tno[m] * kGroupSignalsPerTile;
           fin.stride_recon[m] = 1; fin.off_recon[m] = 0;
         }
         c->fin_one = fin;
         el.fin = fin;
         group_set_elem(g, el);
-        for (int m = 0; m < M; ++m) { auto& bd = c->ops_bwd_dec_mod[m]; tn1[m] = add_rowwise(bd[1], m, T_DA, tno[m], T_DG2, bd[2].gargs.bias_grad); }
-        for (int m = 0; m < M; ++m) add_wgrad(c->ops_bwd_dec_mod[m][0], m, T_DA, tno[m]);
-        for (int m = 0; m < M; ++m) { auto& bd = c->ops_bwd_dec_mod[m]; tn2[m] = add_rowwise(bd[3], m, T_DG2, tn1[m], T_DG1, bd[4].gargs.bias_grad); }
+        for (int m : mord) { auto& bd = c->ops_bwd_dec_mod[m]; tn1[m] = add_rowwise(bd[1], m, T_DA, tno[m], T_DG2, bd[2].gargs.bias_grad, -1, nullptr, wo[m], true, &w1[m]); }
+        for (int m : mord) add_wgrad(c->ops_bwd_dec_mod[m][0], m, T_DA, tno[m]);
+        for (int m : mord) { auto& bd = c->ops_bwd_dec_mod[m]; tn2[m] = add_rowwise(bd[3], m, T_DG2, tn1[m], T_DG1, bd[4].gargs.bias_grad, -1, nullptr, w1[m], true, &w2[m]); }
         group_add_elt_task(g, 2, 0, B, ctr(0, T_DA, 0), RB, S * tno[0], M > 1 ? ctr(1, T_DA, 0) : -1, M > 1 ? S * tno[1] : 0, -1, RB);
-        for (int m = 0; m < M; ++m) add_wgrad(c->ops_bwd_dec_mod[m][2], m, T_DG2, tn1[m]);
-        for (int m = 0; m < M; ++m) tnz[m] = add_rowwise(c->ops_bwd_dec_mod[m][5], m, T_DG1, tn2[m], T_DZ, nullptr);
-        for (int m = 0; m < M; ++m) add_wgrad(c->ops_bwd_dec_mod[m][4], m, T_DG1, tn2[m]);
+        for (int m : mord) add_wgrad(c->ops_bwd_dec_mod[m][2], m, T_DG2, tn1[m]);
+        for (int m : mord) tnz[m] = add_rowwise(c->ops_bwd_dec_mod[m][5], m, T_DG1, tn2[m], T_DZ, nullptr, -1, nullptr, w2[m]);
+        for (int m : mord) add_wgrad(c->ops_bwd_dec_mod[m][4], m, T_DG1, tn2[m]);
         for (int rb = 0; rb < RB; ++rb)
           group_add_elt_task(g, 1, rb, B, ctr(0, T_DZ, rb), 1, S * tnz[0], M > 1 ? ctr(1, T_DZ, rb) : -1, M > 1 ? S * tnz[1] : 0,
                              ctr(0, T_DHD, rb));
-        for (int m = 0; m < M; ++m) { auto& be = c->ops_bwd_enc_mod[m]; tn1[m] = add_rowwise(be[1], m, T_DHD, 1, T_DH2, be[2].gargs.bias_grad, 0); }
-        for (int m = 0; m < M; ++m) add_wgrad(c->ops_bwd_enc_mod[m][0], m, T_DHD, 1, 0);
-        for (int m = 0; m < M; ++m) { auto& be = c->ops_bwd_enc_mod[m]; tn2[m] = add_rowwise(be[3], m, T_DH2, tn1[m], T_DH1, be[4].gargs.bias_grad); }
-        for (int m = 0; m < M; ++m) add_wgrad(c->ops_bwd_enc_mod[m][2], m, T_DH2, tn1[m]);
-        for (int m = 0; m < M; ++m) add_wgrad(c->ops_bwd_enc_mod[m][4], m, T_DH1, tn2[m]);
+        for (int m : mord) { auto& be = c->ops_bwd_enc_mod[m]; tn1[m] = add_rowwise(be[1], m, T_DHD, 1, T_DH2, be[2].gargs.bias_grad, 0, nullptr, 0, true, &w1[m]); }
+        for (int m : mord) add_wgrad(c->ops_bwd_enc_mod[m][0], m, T_DHD, 1, 0);
+        for (int m : mord) { auto& be = c->ops_bwd_enc_mod[m]; tn2[m] = add_rowwise(be[3], m, T_DH2, tn1[m], T_DH1, be[4].gargs.bias_grad, -1, nullptr, w1[m]); }
+        for (int m : mord) add_wgrad(c->ops_bwd_enc_mod[m][2], m, T_DH2, tn1[m]);
+        for (int m : mord) add_wgrad(c->ops_bwd_enc_mod[m][4], m, T_DH1, tn2[m]);
         end(c->seg_step);
         c->one_built = true;
       }
     }
   }
-  group_set_counters(c->gplan, c->gsync, c->n_ctr);
+  group_set_counters(c->gplan, c->gsync, c->n_ctr, c->n_ctr_half);
   if (!group_upload(c->gplan, err, sizeof err)) fail("%s", err);
 }
 

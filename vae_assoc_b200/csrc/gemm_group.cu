@@ -367,7 +367,16 @@ enum { TF_A_MN = 1, TF_B_MN = 2, TF_REDUCE = 4, TF_AUX = 8, TF_ROUND = 16, TF_CO
        TF_LOSS = 1024,
        // elementwise task: cost finalize (one warp sums the block partials of the loss / latent tasks; kb0 = number of
        // counters behind wait2_ctr)
-       TF_ELT_FINALIZE = 2048, TF_ELT = TF_ELT_LATENT_FWD | TF_ELT_LATENT_BWD | TF_ELT_FINALIZE };
+       TF_ELT_FINALIZE = 2048, TF_ELT = TF_ELT_LATENT_FWD | TF_ELT_LATENT_BWD | TF_ELT_FINALIZE,
+       // half-tile hand-over between dependent row-wise layers: a producing tile publishes its first half of 32-column
+       // chunks (counter + half_off) before its second half is out of TMEM; the consuming tile streams the k-blocks of
+       // every producing tile's first half, then waits for the full counters and streams the rest (k order is free in a
+       // contraction).  TF_HALF: consumer (wait2_ctr = half counter, wait2_val = k-blocks per producing tile);
+       // TF_SIG_HALF: producer
+       TF_HALF = kTaskHalf, TF_SIG_HALF = kTaskSigHalf };
+// first-half chunk count of a tile with `n` chunks (both epilogue slots take the same number of first-half chunks)
+__host__ __device__ __forceinline__ int half_chunks(int n) { const int h = (((n + 1) >> 1) + 1) & ~1; return h < n ? h : n; }
+static_assert(VAEASSOC_EPI_WARPS == 8, "half_chunks() assumes two epilogue slots per TMEM lane quarter");
 
 
 namespace {
@@ -472,7 +481,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_constant__ GElem elem,
                   const GTask* __restrict__ tasks, int ntasks,
                   uint32_t* __restrict__ counters, uint32_t* __restrict__ queue, int reset_first, int reset_count,
-                  int mode, unsigned long long* __restrict__ tl) {
+                  int mode, unsigned long long* __restrict__ tl, int half_off) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t epi_base = base + kStages * STAGE_BYTES;
@@ -500,6 +509,7 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
   auto sched_task = [&](int r) { return tmem_slot + 8u + 4u * r; };
   // done[i]: the kEpiWarps epilogue warps of THIS CTA have stored their part of the i-th (mod kDoneRing) signalling tile
   auto done_bar = [&](uint32_t i) { return tmem_slot + 8u + 4u * kSched + 8u * (i % kDoneRing); };
+  auto half_bar = [&](uint32_t i) { return tmem_slot + 8u + 4u * kSched + 8u * kDoneRing + 8u * (i % kDoneRing); };
   const uint32_t sig_seq_addr = tmem_slot + 8u + 4u * kSched + 8u * 2 * kDoneRing;   // signalling tiles published so far
   static_assert(8 * (2 * kStages + 4 + kEpiBufs * kEpiWarps + 2 * kSched) + 8 + 4 * kSched + 16 * kDoneRing + 8 <= kBarRegion,
                 "barrier region too small");
@@ -517,7 +527,7 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
     for (int e = 0; e < kEpiWarps; ++e)
       for (int b = 0; b < kEpiBufs; ++b) mbar_init(aux_bar(e, b), 1);
     for (int r = 0; r < kSched; ++r) { mbar_init(sched_full_bar(r), 1); mbar_init(sched_empty_bar(r), kSchedConsumers); }
-    for (int i = 0; i < kDoneRing; ++i) mbar_init(done_bar(i), kEpiWarps);
+    for (int i = 0; i < kDoneRing; ++i) { mbar_init(done_bar(i), kEpiWarps); mbar_init(half_bar(i), kEpiWarps); }
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(sig_seq_addr), "r"(0u) : "memory");
     fence_barrier_init();
   }
@@ -593,11 +603,17 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
       const int m0 = tk.m_blk * BM + (int)rank * BM_CTA;      // this CTA's rows of A
       const int nb0 = tk.n_blk * BN + (int)rank * BNH;        // this CTA's slice of B
       const uint32_t stage_tx = 2u * (A_BYTES + (uint32_t)BNH * BK * 4);
+      const bool half = (tk.flags & TF_HALF) != 0;
+      const int W = half ? tk.wait2_val : tk.nkb;              // k-blocks per producing tile
       if (lane == 0) {
-        if (tk.wait_cnt > 0 || tk.wait2_ctr >= 0) {
+        if (half) {
+          wait_counter(counters + tk.wait2_ctr, (uint32_t)tk.wait_val);    // first halves of the producing tiles
+          fence_acq_rel_gpu();
+          fence_proxy_async_all();
+        } else if (tk.wait_cnt > 0 || tk.wait2_ctr >= 0) {
           for (int c = 0; c < tk.wait_cnt; ++c) wait_counter(counters + tk.wait_ctr + c, (uint32_t)tk.wait_val);
           if (tk.wait2_ctr >= 0) wait_counter(counters + tk.wait2_ctr, (uint32_t)tk.wait2_val);
-          fence_acq_rel_gpu();               // pairs with the producers' red.release.gpu
+          fence_acq_rel_gpu();               // pairs with the signal warps' fence + counter add
           fence_proxy_async_all();           // their generic-proxy stores -> our TMA (async proxy) loads
         }
         if (kTimeline && tl && rank == 0) { tl[kTL * t + 0] = gtimer(); tl[kTL * t + 5] = blockIdx.x >> 1; tl[kTL * t + 6] = t_entry; }
@@ -605,24 +621,40 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
       __syncwarp();
       int t_after = -1;
       const int announce = min(tk.nkb, kStages) - 1;
-      for (int i = 0; i < tk.nkb; ++i, ++it) {
-        const int s = (int)(it % kStages);
-        const uint32_t sa = base + s * STAGE_BYTES, sb = sa + A_BYTES;
-        const uint32_t full_leader = full_leader0 + 8u * s;
-        const int k0 = (tk.kb0 + i) * BK;
-        if (elect_one()) {
-          mbar_wait(empty_bar(s), ((it / kStages) & 1) ^ 1);
-          if (kTimeline && tl && t == 0 && i < 64) tl[kTL * ntasks + (rank ? 128 : 0) + i] = gtimer();
-          if (rank == 0) mbar_arrive_expect_tx(full_bar(s), stage_tx);
-          // MN-major operands: one 3-D box {32 mn, 32 k, chunks} lands as [chunk][k][32 mn] (see make_map_mn)
-          if (a_mn) tma_load_3d_pair(sa, &p->map_a, full_leader, 0, k0, m0 >> 5);
-          else tma_load_2d_pair(sa, &p->map_a, full_leader, k0, m0);
-          if (b_mn) tma_load_3d_pair(sb, &p->map_b, full_leader, 0, k0, nb0 >> 5);
-          else tma_load_2d_pair(sb, &p->map_b, full_leader, k0, nb0);
-          if (i == announce)                 // the next task: known to every role while this one streams
-            t_after = (rank == 0) ? publish(queue_base + raw) : next_task();
+      int i = 0;
+      for (int pass = 0; pass < (half ? 2 : 1); ++pass) {
+        if (pass == 1) {                     // the rest of the producing tiles
+          if (lane == 0) {
+            for (int c = 0; c < tk.wait_cnt; ++c) wait_counter(counters + tk.wait_ctr + c, (uint32_t)tk.wait_val);
+            fence_acq_rel_gpu();
+            fence_proxy_async_all();
+          }
+          __syncwarp();
         }
-        __syncwarp();
+        for (int j0 = 0; j0 < tk.nkb; j0 += W) {
+          const int nch = min(W, tk.nkb - j0);
+          const int hc = half ? half_chunks(nch) : nch;
+          const int c_lo = pass == 0 ? 0 : hc, c_hi = pass == 0 ? hc : nch;
+          for (int c = c_lo; c < c_hi; ++c, ++i, ++it) {
+            const int s = (int)(it % kStages);
+            const uint32_t sa = base + s * STAGE_BYTES, sb = sa + A_BYTES;
+            const uint32_t full_leader = full_leader0 + 8u * s;
+            const int k0 = (tk.kb0 + j0 + c) * BK;
+            if (elect_one()) {
+              mbar_wait(empty_bar(s), ((it / kStages) & 1) ^ 1);
+              if (kTimeline && tl && t == 0 && i < 64) tl[kTL * ntasks + (rank ? 128 : 0) + i] = gtimer();
+              if (rank == 0) mbar_arrive_expect_tx(full_bar(s), stage_tx);
+              // MN-major operands: one 3-D box {32 mn, 32 k, chunks} lands as [chunk][k][32 mn] (see make_map_mn)
+              if (a_mn) tma_load_3d_pair(sa, &p->map_a, full_leader, 0, k0, m0 >> 5);
+              else tma_load_2d_pair(sa, &p->map_a, full_leader, k0, m0);
+              if (b_mn) tma_load_3d_pair(sb, &p->map_b, full_leader, 0, k0, nb0 >> 5);
+              else tma_load_2d_pair(sb, &p->map_b, full_leader, k0, nb0);
+              if (i == announce)               // the next task: known to every role while this one streams
+                t_after = (rank == 0) ? publish(queue_base + raw) : next_task();
+            }
+            __syncwarp();
+          }
+        }
       }
       t = bcast(t_after);
       tk = load_task(tasks, t);
@@ -694,6 +726,12 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
         const GTask* tp = tasks + t;
         const int flags = __ldg(&tp->flags), sig = __ldg(&tp->signal_ctr);
         if (!(flags & TF_ELT) && sig >= 0) {
+          // (every signalling tile cycles both barriers of its ring slot, so that their phases stay in step)
+          mbar_wait(half_bar(seq), (seq / kDoneRing) & 1);
+          if (flags & TF_SIG_HALF) {
+            fence_acq_rel_gpu();
+            asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(counters + sig + half_off), "r"((uint32_t)kEpiWarps) : "memory");
+          }
           mbar_wait(done_bar(seq), (seq / kDoneRing) & 1);
           fence_acq_rel_gpu();
           asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(counters + sig), "r"((uint32_t)kEpiWarps) : "memory");
@@ -801,6 +839,7 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
       const bool reduce = (tk.flags & TF_REDUCE) != 0, use_aux = (tk.flags & TF_AUX) != 0, round_out = (tk.flags & TF_ROUND) != 0;
       const float* __restrict__ bias = p->bias;
       const bool loss_task = (tk.flags & TF_LOSS) != 0;
+      const int sig_hc = (tk.flags & TF_SIG_HALF) ? half_chunks(min(tk.bn / 32, (tk.N - tk.n_blk * tk.bn + 31) / 32)) : 0;
       float loss_acc = 0.0f;                 // this lane's row: reconstruction loss over the warp's chunks
       float* __restrict__ colsum = (tk.flags & TF_COLSUM) ? p->colsum : nullptr;
       const int row0 = tk.m_blk * BM + (int)rank * BM_CTA + q * 32;    // first output row of this warp
@@ -808,6 +847,15 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
       const int nchunks = (row0 < tk.M) ? min(BN / 32, (N - n0 + 31) / 32) : 0;   // warp-uniform
       const int nmine = nchunks > slot ? (nchunks - slot + kSlots - 1) / kSlots : 0;   // chunks slot, slot + kSlots, ... of this warp
       const uint32_t acc = tcount & 1;
+      if (sig_hc > 0 && (nmine == 0 || slot >= sig_hc)) {      // no first-half chunk of this warp: nothing to wait for
+        if (elect_one()) {
+          if (sig_count >= (uint32_t)kDoneRing) {
+            uint32_t done;
+            do { asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(done) : "r"(sig_seq_addr) : "memory"); } while (done + kDoneRing <= sig_count);
+          }
+          asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(half_bar(sig_count)) : "memory");
+        }
+      }
       // everything the chunk loop needs from global memory is requested NOW, while the main loop of this task runs
       // (a fresh L2 round trip costs ~1.5 us while the operand streams of 148 SMs are in flight): the bias values of all
       // chunks of this warp (lane <-> column), the relu mask words of this lane's row, and up to three aux boxes
@@ -1076,6 +1124,17 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
           if (col < N) atomicAdd(colsum + col, (cs0 + cs1) + (cs2 + cs3));
         }
         if (kTimeline && tl && rank == 0 && warp == 2 && lane == 0 && i == 0) tl[kTL * t + 10] = (unsigned long long)clock64();
+        if (c < sig_hc && c + kSlots >= sig_hc) {
+          // this warp's last chunk of the tile's first half is on its way to L2: let the signal warp publish the half
+          __syncwarp();
+          if (elect_one()) {
+            if (sig_count >= (uint32_t)kDoneRing) {
+              uint32_t done;
+              do { asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(done) : "r"(sig_seq_addr) : "memory"); } while (done + kDoneRing <= sig_count);
+            }
+            asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(half_bar(sig_count)) : "memory");
+          }
+        }
         if (use_aux && i + kEpiBufs < nmine) {
           __syncwarp();                    // every lane has finished with box b: refill it with the aux tile 3 chunks ahead
           if (elect_one()) {
@@ -1104,6 +1163,7 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
             uint32_t done;
             do { asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(done) : "r"(sig_seq_addr) : "memory"); } while (done + kDoneRing <= sig_count);
           }
+          if (sig_hc == 0) asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(half_bar(sig_count)) : "memory");
           asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(done_bar(sig_count)) : "memory");
         }
       }
@@ -1133,7 +1193,10 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
   }
   __syncthreads();
   if (s_last) {
-    for (int i = threadIdx.x; i < reset_count; i += kThreads) counters[reset_first + i] = 0u;
+    for (int i = threadIdx.x; i < reset_count; i += kThreads) {
+      counters[reset_first + i] = 0u;
+      if (half_off > 0) counters[reset_first + half_off + i] = 0u;
+    }
     if (threadIdx.x == 0) { queue[0] = 0u; queue[1] = 0u; }
     __threadfence();
   }
@@ -1217,6 +1280,7 @@ struct GroupPlan {
   GTask* d_tasks = nullptr;
   uint32_t* d_counters = nullptr;    // row-block completion counters of the step (not owned; self-cleaning)
   int n_counters = 0;
+  int half_off = 0;                  // offset of the half-tile counters (0: none)
   bool uploaded = false;
 };
 
@@ -1333,7 +1397,7 @@ int group_problem_tiles_n(const GroupPlan* g, int prob) { const GProblem& p = g-
 int group_problem_kblocks(const GroupPlan* g, int prob) { return (g->problems[prob].K + BK - 1) / BK; }
 
 int group_add_task(GroupPlan* g, int prob, int m_blk, int n_blk, int kb0, int nkb, int wait_ctr, int wait_cnt,
-                   int wait_val, int wait2_ctr, int wait2_val, int signal_ctr) {
+                   int wait_val, int wait2_ctr, int wait2_val, int signal_ctr, int extra_flags) {
   const GProblem& p = g->problems[prob];
   GTask t;
   memset(&t, 0, sizeof t);
@@ -1343,7 +1407,7 @@ int group_add_task(GroupPlan* g, int prob, int m_blk, int n_blk, int kb0, int nk
   t.bn = p.BN;
   t.flags = (p.a_mn ? TF_A_MN : 0) | (p.b_mn ? TF_B_MN : 0) | (p.reduce ? TF_REDUCE : 0) | (p.has_aux ? TF_AUX : 0) |
             (p.round_out ? TF_ROUND : 0) | (p.colsum ? TF_COLSUM : 0) | (p.mask_out ? TF_MASK_OUT : 0) |
-            (p.mask_in ? TF_MASK_IN : 0) | (p.loss_partials ? TF_LOSS : 0);
+            (p.mask_in ? TF_MASK_IN : 0) | (p.loss_partials ? TF_LOSS : 0) | (extra_flags & (TF_HALF | TF_SIG_HALF));
   t.act = p.act; t.M = p.M; t.N = p.N;
   g->tasks.push_back(t);
   g->uploaded = false;
@@ -1371,7 +1435,10 @@ void group_set_elem(GroupPlan* g, const GElem& e) { g->elem = e; }
 
 int group_num_tasks(const GroupPlan* g) { return (int)g->tasks.size(); }
 
-void group_set_counters(GroupPlan* g, uint32_t* d_counters, int n) { g->d_counters = d_counters; g->n_counters = n; }
+void group_set_counters(GroupPlan* g, uint32_t* d_counters, int n, int half_off) {
+  g->d_counters = d_counters; g->n_counters = n; g->half_off = half_off;
+}
+int group_problem_bn(const GroupPlan* g, int prob) { return g->problems[prob].BN; }
 
 bool group_upload(GroupPlan* g, char* err, int errlen) {
   if (g->uploaded) return true;
@@ -1409,17 +1476,17 @@ void launch_site(const GroupPlan* g, int site, uint32_t* queue, int reset_first,
     GParams<kSiteProblemsSmall> prm;
     memcpy(prm.p, g->problems.data() + st.first_problem, (size_t)st.n_problems * sizeof(GProblem));
     gemm_group_kernel<kSiteProblemsSmall><<<2 * clusters, kThreads, SMEM_BYTES, s>>>(
-        prm, g->elem, g->d_tasks + st.first_task, st.n_tasks, g->d_counters, queue, reset_first, reset_count, mode, tl);
+        prm, g->elem, g->d_tasks + st.first_task, st.n_tasks, g->d_counters, queue, reset_first, reset_count, mode, tl, g->half_off);
   } else if (st.n_problems <= kSiteProblemsLarge) {
     GParams<kSiteProblemsLarge> prm;
     memcpy(prm.p, g->problems.data() + st.first_problem, (size_t)st.n_problems * sizeof(GProblem));
     gemm_group_kernel<kSiteProblemsLarge><<<2 * clusters, kThreads, SMEM_BYTES, s>>>(
-        prm, g->elem, g->d_tasks + st.first_task, st.n_tasks, g->d_counters, queue, reset_first, reset_count, mode, tl);
+        prm, g->elem, g->d_tasks + st.first_task, st.n_tasks, g->d_counters, queue, reset_first, reset_count, mode, tl, g->half_off);
   } else {
     GParams<kSiteProblemsStep> prm;
     memcpy(prm.p, g->problems.data() + st.first_problem, (size_t)st.n_problems * sizeof(GProblem));
     gemm_group_kernel<kSiteProblemsStep><<<2 * clusters, kThreads, SMEM_BYTES, s>>>(
-        prm, g->elem, g->d_tasks + st.first_task, st.n_tasks, g->d_counters, queue, reset_first, reset_count, mode, tl);
+        prm, g->elem, g->d_tasks + st.first_task, st.n_tasks, g->d_counters, queue, reset_first, reset_count, mode, tl, g->half_off);
   }
 }
 }  // namespace

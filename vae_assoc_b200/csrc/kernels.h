@@ -68,8 +68,12 @@ int group_problem_tiles_n(const GroupPlan* g, int prob);
 int group_problem_kblocks(const GroupPlan* g, int prob);      // k-blocks of 32
 // operands ready when counters[wait_ctr .. +wait_cnt) >= wait_val (and counters[wait2_ctr] >= wait2_val); every
 // epilogue warp (16 per tile) bumps counters[signal_ctr] once the tile is globally visible; -1 / 0 = none
+// extra_flags: kTaskHalf (consumer of half-tile hand-overs: wait2_ctr = half counter, wait2_val = k-blocks per producing
+// tile, the half counter's target is wait_val as well) | kTaskSigHalf (producer: publishes its first half early)
+constexpr int kTaskHalf = 4096, kTaskSigHalf = 8192;
 int group_add_task(GroupPlan* g, int prob, int m_blk, int n_blk, int kb0, int nkb, int wait_ctr, int wait_cnt,
-                   int wait_val, int wait2_ctr, int wait2_val, int signal_ctr);
+                   int wait_val, int wait2_ctr, int wait2_val, int signal_ctr, int extra_flags = 0);
+int group_problem_bn(const GroupPlan* g, int prob);
 int group_num_tasks(const GroupPlan* g);
 // elementwise task over the 256 rows of row block m_blk, executed by the epilogue warps of whichever CTA pair pops it
 // (kind 0: latent forward, 1: latent backward -- arguments from group_set_elem); waits / signals like a tile task
@@ -82,7 +86,8 @@ void group_set_elem(GroupPlan* g, const GElem& e);
 int group_begin(GroupPlan* g);
 bool group_end(GroupPlan* g, char* err, int errlen);
 int group_site_tasks(const GroupPlan* g, int site);
-void group_set_counters(GroupPlan* g, uint32_t* d_counters, int n);
+// half_off: the half-tile counter of counter i is counter i + half_off (0: the plan uses none)
+void group_set_counters(GroupPlan* g, uint32_t* d_counters, int n, int half_off = 0);
 bool group_upload(GroupPlan* g, char* err, int errlen);
 // dynamic_first: every task (the first one included) comes from the atomic queue -- required whenever a kernel that
 // waits on a peer GPU (NCCL) may hold SMs while this launch is resident
