@@ -1,4 +1,4 @@
-"""One small train step through every kernel family of the tf32 schedule (two-launch form) -- the target of
+"""One small train step through every kernel family of the tf32 schedule (one-launch form) -- the target of
 scripts/sanitize.sh (compute-sanitizer memcheck / racecheck / synccheck)."""
 import sys
 import numpy as np
