@@ -44,6 +44,9 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamArgs a) {
 #undef VAEASSOC_ADAM_LANE
     p4[i] = p; m4[i] = m; v4[i] = v;
     if (s4) s4[i] = make_float4(round_tf32(p.x), round_tf32(p.y), round_tf32(p.z), round_tf32(p.w));
+    // the gradient buffer is an accumulator (TMA reduce-add, bias-gradient REDs): consumed here, it is handed back
+    // cleared, so that the next step's graph needs no memset ahead of the tile kernel
+    if (a.zero_g) reinterpret_cast<float4*>(a.zero_g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 

@@ -186,6 +186,9 @@ struct vaeassoc_ctx {
   // launch of the tile kernel; x_hat / per-row reconstruction losses are then produced on demand (probe_get)
   Seg seg_step;
   bool one_built = false;
+  // single-GPU one-launch schedule: Adam hands the gradient buffer back cleared, the train graph has no memset
+  bool g_zero = false;                // the gradient buffer holds zeros (stream order)
+  cudaGraphExec_t graph_train_nz = nullptr; int graph_train_nz_nodes = 0;
   unsigned recon_stale = 0;           // bit m: the last step ran the loss-fused form, d.xh / d.rec_loss of modality m are not current
   FinalizeArgs fin_one;
   int lat_blocks_elt = 0;
@@ -642,7 +645,7 @@ GemmArgs gemm_wgrad(int B, int K, int N, const float* X, int64_t ldx, const floa
 }
 
 void destroy_graphs(Ctx* c) {
-  for (cudaGraphExec_t* g : {&c->graph_train, &c->graph_grad, &c->graph_a1, &c->graph_a2, &c->graph_adam, &c->peer.graph}) {
+  for (cudaGraphExec_t* g : {&c->graph_train, &c->graph_train_nz, &c->graph_grad, &c->graph_a1, &c->graph_a2, &c->graph_adam, &c->peer.graph}) {
     if (*g) cudaGraphExecDestroy(*g);
     *g = nullptr;
   }
@@ -1248,14 +1251,14 @@ void join_colsums(Ctx* c, std::vector<Op>& ops, cudaStream_t s) {
 }
 
 // segment A1: zero grads, forward, losses, decoder backward   (gradient bucket 0 complete at its end)
-void enqueue_a1(Ctx* c, cudaStream_t s) {
+void enqueue_a1(Ctx* c, cudaStream_t s, bool with_memset = true) {
   const int M = c->cfg.n_modalities;
   c->lat_mode_elt = false;
   if (one_mode(c)) {
     // ONE launch of the persistent tile kernel carries the gradient step (enqueue_a2); the gradient buffer it accumulates
-    // into (TMA reduce-add, bias-gradient REDs) is cleared here
+    // into (TMA reduce-add, bias-gradient REDs) is cleared here -- unless the previous step's Adam left it cleared
     c->lat_mode_elt = true;
-    CUDA_OK(cudaMemsetAsync(c->g, 0, (size_t)(c->n_flat + 32) * sizeof(float), s));
+    if (with_memset) CUDA_OK(cudaMemsetAsync(c->g, 0, (size_t)(c->n_flat + 32) * sizeof(float), s));
     return;
   }
   if (elt_mode(c)) {
@@ -1346,8 +1349,10 @@ void enqueue_a2(Ctx* c, cudaStream_t s, int advance) {
   launch_finalize(finalize_args(c, advance), s);
   c->launches += 1;
 }
-void enqueue_adam(Ctx* c, cudaStream_t s) {
-  launch_adam(adam_args(c), s);
+void enqueue_adam(Ctx* c, cudaStream_t s, bool zero_g = false) {
+  AdamArgs a = adam_args(c);
+  if (zero_g) a.zero_g = c->g;
+  launch_adam(a, s);
   c->launches += 1;
 }
 // rank r owns float4 indices [lo, hi) of the flat buffers: equal shards, multiples of 8 float4 (128 bytes)
@@ -1445,6 +1450,10 @@ void ensure_graphs(Ctx* c) {
   c->graph_train_nodes = capture(c, &c->graph_train, [&](cudaStream_t s) {
     enqueue_a1(c, s); enqueue_a2(c, s, 1); enqueue_adam(c, s);
   });
+  if (one_mode(c))
+    c->graph_train_nz_nodes = capture(c, &c->graph_train_nz, [&](cudaStream_t s) {
+      enqueue_a1(c, s, false); enqueue_a2(c, s, 1); enqueue_adam(c, s, true);
+    });
   c->graph_grad_nodes = capture(c, &c->graph_grad, [&](cudaStream_t s) {
     enqueue_a1(c, s); enqueue_a2(c, s, 0);
     launch_publish_cost(c->g + c->n_flat, c->last_cost, s); c->launches += 1;
@@ -1526,8 +1535,17 @@ void run_step(Ctx* c, bool with_adam) {
     }
     return;
   }
+  const bool was_zero = c->g_zero;
+  c->g_zero = false;
   if (!dp) {
-    if (c->cfg.use_graph) {
+    if (c->cfg.use_graph && with_adam && c->graph_train_nz && !getenv("VAEASSOC_KEEP_GRADS")) {
+      // the train graph without a memset: Adam clears the gradients it has consumed (get_grads() after a train step
+      // therefore reads zeros; compute_gradients keeps them)
+      if (!was_zero) CUDA_OK(cudaMemsetAsync(c->g, 0, (size_t)(c->n_flat + 32) * sizeof(float), s));
+      CUDA_OK(cudaGraphLaunch(c->graph_train_nz, s));
+      c->launches += c->graph_train_nz_nodes;
+      c->g_zero = true;
+    } else if (c->cfg.use_graph) {
       CUDA_OK(cudaGraphLaunch(with_adam ? c->graph_train : c->graph_grad, s));
       c->launches += with_adam ? c->graph_train_nodes : c->graph_grad_nodes;
     } else {
@@ -1781,7 +1799,7 @@ void* vaeassoc_flat_ptr(vaeassoc_handle h, int which) {
   if (!h) return nullptr;
   switch (which) {
     case VAEASSOC_PARAMS: return h->p;
-    case VAEASSOC_GRADS: return h->g;
+    case VAEASSOC_GRADS: h->g_zero = false; return h->g;      // (the caller may write through the pointer)
     case VAEASSOC_ADAM_M: return h->m;
     case VAEASSOC_ADAM_V: return h->v;
     default: return nullptr;
@@ -2693,6 +2711,7 @@ int vaeassoc_profile_step(vaeassoc_handle h, const float* const* x_dev, const in
     cudaStream_t s = h->stream;
     stage_inputs(h, x_dev, ld, eps_dev, s);
     refresh_shadow(h, s);
+    h->g_zero = false;
     std::vector<Op> all;
     {
       Op z; z.name = "zero_grads"; z.bytes = 4.0 * (h->n_flat + 32);

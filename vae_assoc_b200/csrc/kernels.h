@@ -231,6 +231,7 @@ struct AdamArgs {
   const int64_t* step_dev = nullptr;
   const float* cost_slot = nullptr; float* cost_hist = nullptr; int hist_cap = 0;   // publish cost of step t
   float* last_cost = nullptr;
+  float* zero_g = nullptr;          // = g: clear the gradients once consumed (single-GPU one-launch schedule), or null
 };
 void launch_adam(const AdamArgs& a, cudaStream_t s);
 
