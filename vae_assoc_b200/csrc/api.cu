@@ -938,7 +938,7 @@ void build_segments(Ctx* c) {
   const int RB = (B + 255) / 256;
   bool ok = c->cfg.precision == VAEASSOC_TF32 && !getenv("VAEASSOC_NO_FUSE");
   const bool nodeps = getenv("VAEASSOC_DEBUG_NODEPS") != nullptr;   // timing experiments only: wrong results
-  const bool half_ok = getenv("VAEASSOC_NO_HALF") == nullptr;       // half-tile hand-over between dependent layers (one-launch form)
+  const bool half_ok = kGroupHalfOk && getenv("VAEASSOC_NO_HALF") == nullptr;       // half-tile hand-over between dependent layers (one-launch form)
   for (int m = 0; m < M && ok; ++m) {
     if (c->mods[m].conv) { ok = false; break; }
     if (c->ops_enc_mod[m].size() != 3 || c->ops_dec_mod[m].size() != 3 || c->ops_bwd_dec_mod[m].size() != 6 ||

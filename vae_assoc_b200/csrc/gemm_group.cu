@@ -377,7 +377,7 @@ enum { TF_A_MN = 1, TF_B_MN = 2, TF_REDUCE = 4, TF_AUX = 8, TF_ROUND = 16, TF_CO
        TF_HALF = kTaskHalf, TF_SIG_HALF = kTaskSigHalf };
 // first-half chunk count of a tile with `n` chunks (both epilogue slots take the same number of first-half chunks)
 __host__ __device__ __forceinline__ int half_chunks(int n) { const int h = (((n + 1) >> 1) + 1) & ~1; return h < n ? h : n; }
-static_assert(VAEASSOC_EPI_WARPS == 8, "half_chunks() assumes two epilogue slots per TMEM lane quarter");
+// (half_chunks() assumes two epilogue slots per TMEM lane quarter: the host only plans hand-overs when kGroupHalfOk)
 
 
 namespace {
@@ -827,6 +827,9 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
             }
           } else {
             const int nz = elem.lb.n_z;
+            if (nz == 4) {
+              for (int m = 0; m < elem.lb.n_mod; ++m) latent_bwd_row4<true>(elem.lb, m, r, live, elem.bh_grad[m], lane);
+            } else
             for (int m = 0; m < elem.lb.n_mod; ++m) {
               for (int k = 0; k < nz; ++k) {
                 float dm = 0.f, dl = 0.f;

@@ -100,6 +100,7 @@ void group_debug_timeline(const GroupPlan* g, int site, uint32_t* queue, int res
 #define VAEASSOC_EPI_WARPS 8            // epilogue warps per CTA of the tile kernel (build-time variant: 16)
 #endif
 constexpr int kGroupSignalsPerTile = 2 * VAEASSOC_EPI_WARPS;   // epilogue warps of a CTA pair
+constexpr bool kGroupHalfOk = VAEASSOC_EPI_WARPS == 8;         // half-tile hand-overs need two epilogue slots per lane quarter
 
 // ------------------------------------------------------------------------------------------------------
 // conv / transposed-conv layers of the hidden_conv=True modality as im2col -> GEMM -> col2im (conv.cu)

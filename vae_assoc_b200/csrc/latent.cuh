@@ -145,6 +145,38 @@ __device__ __forceinline__ void latent_bwd_row(const LatentBwdArgs& a, int m, in
   }
 }
 
+// n_z == 4 (the reference's latent width): every operand of the row is ONE 128-bit L1-bypassing load, so nothing of the
+// row waits behind a store; m = modality.  Same arithmetic as latent_bwd_elem.  REDUCE: see latent_bwd_row.
+template <bool REDUCE>
+__device__ __forceinline__ void latent_bwd_row4(const LatentBwdArgs& a, int m, int64_t r, bool live, float* bh_grad, int lane) {
+  float vm[4] = {0.f, 0.f, 0.f, 0.f}, vl[4] = {0.f, 0.f, 0.f, 0.f};
+  if (live) {
+    const float4 e4 = __ldcg(reinterpret_cast<const float4*>(a.eps + r * 4));
+    const float4 lv4 = __ldcg(reinterpret_cast<const float4*>(a.heads[m] + r * 8 + 4));
+    const float4 dz4 = __ldcg(reinterpret_cast<const float4*>(a.dz[m] + r * 4));
+    const float4 gm4 = __ldcg(reinterpret_cast<const float4*>(a.gstat[m] + r * 8));
+    const float4 gl4 = __ldcg(reinterpret_cast<const float4*>(a.gstat[m] + r * 8 + 4));
+    const float e[4] = {e4.x, e4.y, e4.z, e4.w}, lv[4] = {lv4.x, lv4.y, lv4.z, lv4.w}, dz[4] = {dz4.x, dz4.y, dz4.z, dz4.w};
+    const float gm[4] = {gm4.x, gm4.y, gm4.z, gm4.w}, gl[4] = {gl4.x, gl4.y, gl4.z, gl4.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float s = sqrtf(expf(lv[k]));                                      // d z / d lv = eps * s / 2
+      vm[k] = dz[k] + gm[k];
+      vl[k] = dz[k] * e[k] * 0.5f * s + gl[k];
+      if (a.round_out) { vm[k] = round_tf32(vm[k]); vl[k] = round_tf32(vl[k]); }
+    }
+    *reinterpret_cast<float4*>(a.dheads[m] + r * 8) = make_float4(vm[0], vm[1], vm[2], vm[3]);
+    *reinterpret_cast<float4*>(a.dheads[m] + r * 8 + 4) = make_float4(vl[0], vl[1], vl[2], vl[3]);
+  }
+  if (REDUCE && bh_grad != nullptr) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float sm = warp_sum(vm[k]), sl = warp_sum(vl[k]);
+      if (lane == 0) { atomicAdd(bh_grad + k, sm); atomicAdd(bh_grad + 4 + k, sl); }
+    }
+  }
+}
+
 // ---- reconstruction loss of one element from the decoder's pre-activation `a` (fused into the output-layer epilogue
 // of the tile kernel; tf32 mode, tolerance 2e-3: ex2 / lg2 / rcp approximations, five MUFU operations per element) ----
 constexpr float kCeEps = 1e-3f;   // vae_assoc.py:322-323 (the comment there says 1e-10; the code says 1e-3)
