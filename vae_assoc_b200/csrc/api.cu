@@ -188,6 +188,9 @@ struct vaeassoc_ctx {
   bool one_built = false;
   // single-GPU one-launch schedule: Adam hands the gradient buffer back cleared, the train graph has no memset
   bool g_zero = false;                // the gradient buffer holds zeros (stream order)
+  // one-launch form: the heads layer (N = 2 n_z) and the decoder input layer's dgrad (N = n_z) run as split-K tasks that
+  // add into hd / dz; the staging kernel clears those accumulators
+  bool split_heads = false;
   cudaGraphExec_t graph_train_nz = nullptr; int graph_train_nz_nodes = 0;
   unsigned recon_stale = 0;           // bit m: the last step ran the loss-fused form, d.xh / d.rec_loss of modality m are not current
   FinalizeArgs fin_one;
@@ -1005,6 +1008,31 @@ void build_segments(Ctx* c) {
       }
       return Op();
     };
+    // a row-wise layer with a tiny N and a long K (heads: N = 2 n_z; decoder input dgrad: N = n_z) as split-K tasks: every
+    // k range is its own tile task (raw accumulator, TMA reduce-add into C, which the staging kernel cleared; bias of
+    // the heads: added by the latent task).  The layer's stage costs a quarter of its main loop instead of all of it.
+    // Returns the number of tasks per row block (the consumer waits for kGroupSignalsPerTile x that).
+    auto add_rowwise_splitk = [&](const Op& op, int m, int inT, int in_tn, int outT, int in_w) -> int {
+      GemmArgs a = op.gargs;
+      a.bias = nullptr; a.bias_grad = nullptr; a.force_reduce = 1; a.act = ACT_NONE; a.round_out = 0;
+      a.aux = nullptr; a.mask_in = nullptr; a.mask_out = nullptr;
+      const int prob = group_add_problem(g, op.kind, a, err, sizeof err);
+      if (prob < 0) fail("segment plan for %s failed: %s", op.name.c_str(), err);
+      const int tm = group_problem_tiles_m(g, prob), tn = group_problem_tiles_n(g, prob), kb = group_problem_kblocks(g, prob);
+      const int splits = std::max(1, std::min(4, kb / 3));
+      const int per = (kb + splits - 1) / splits;
+      const bool half = in_w > 0 && inT >= 0 && half_ok && splits == 1;
+      int n_tasks = 0;
+      for (int i = 0; i < tm; ++i) {
+        n_tasks = 0;
+        for (int k0 = 0; k0 < kb; k0 += per)
+          for (int j = 0; j < tn; ++j, ++n_tasks)
+            group_add_task(g, prob, i, j, k0, std::min(per, kb - k0), inT >= 0 ? ctr(m, inT, i) : -1, inT >= 0 ? 1 : 0,
+                           kGroupSignalsPerTile * in_tn, half ? ctr(m, inT, i) + c->n_ctr_half : -1, half ? in_w : 0,
+                           outT >= 0 ? ctr(m, outT, i) : -1, half ? kTaskHalf : 0);
+      }
+      return n_tasks;
+    };
     auto begin = [&](Ctx::Seg& sg, int T0, int n_tensors = 2) {
       sg.site = group_begin(g);
       if (sg.site >= c->max_sites - 1) fail("too many tensor-core launch sites");
@@ -1103,10 +1131,14 @@ void build_segments(Ctx* c) {
         std::vector<int> w1(M), w2(M), wo(M);
         for (int m : mord) tn1[m] = add_rowwise(c->ops_enc_mod[m][0], m, -1, 0, T_H1, nullptr, -1, nullptr, 0, true, &w1[m]);
         for (int m : mord) tn2[m] = add_rowwise(c->ops_enc_mod[m][1], m, T_H1, tn1[m], T_H2, nullptr, -1, nullptr, w1[m], true, &w2[m]);
-        for (int m : mord) tnh[m] = add_rowwise(c->ops_enc_mod[m][2], m, T_H2, tn2[m], T_HD, nullptr, -1, nullptr, w2[m]);
+        c->split_heads = getenv("VAEASSOC_NO_SPLIT_HEADS") == nullptr;
+        for (int m : mord) {
+          if (c->split_heads) { tnh[m] = add_rowwise_splitk(c->ops_enc_mod[m][2], m, T_H2, tn2[m], T_HD, w2[m]); el.lf.head_bias[m] = c->ops_enc_mod[m][2].gargs.bias; }
+          else tnh[m] = add_rowwise(c->ops_enc_mod[m][2], m, T_H2, tn2[m], T_HD, nullptr, -1, nullptr, w2[m]);
+        }
         for (int rb = 0; rb < RB; ++rb)
           group_add_elt_task(g, 0, rb, B, ctr(0, T_HD, rb), 1, S * tnh[0], M > 1 ? ctr(1, T_HD, rb) : -1, M > 1 ? S * tnh[1] : 0,
-                             ctr(0, T_Z, rb));
+                             ctr(0, T_Z, rb), 1, c->split_heads ? 1 : 0);
         for (int m : mord) tn1[m] = add_rowwise(c->ops_dec_mod[m][0], m, T_Z, 1, T_G1, nullptr, 0, nullptr, 0, true, &w1[m]);
         for (int m : mord) tn2[m] = add_rowwise(c->ops_dec_mod[m][1], m, T_G1, tn1[m], T_G2, nullptr, -1, nullptr, w1[m], true, &w2[m]);
         FinalizeArgs fin = finalize_args(c, 0);
@@ -1134,7 +1166,10 @@ void build_segments(Ctx* c) {
         for (int m : mord) { auto& bd = c->ops_bwd_dec_mod[m]; tn2[m] = add_rowwise(bd[3], m, T_DG2, tn1[m], T_DG1, bd[4].gargs.bias_grad, -1, nullptr, w1[m], true, &w2[m]); }
         group_add_elt_task(g, 2, 0, B, ctr(0, T_DA, 0), RB, S * tno[0], M > 1 ? ctr(1, T_DA, 0) : -1, M > 1 ? S * tno[1] : 0, -1, RB);
         for (int m : mord) add_wgrad(c->ops_bwd_dec_mod[m][2], m, T_DG2, tn1[m]);
-        for (int m : mord) tnz[m] = add_rowwise(c->ops_bwd_dec_mod[m][5], m, T_DG1, tn2[m], T_DZ, nullptr, -1, nullptr, w2[m]);
+        for (int m : mord) {
+          if (c->split_heads) tnz[m] = add_rowwise_splitk(c->ops_bwd_dec_mod[m][5], m, T_DG1, tn2[m], T_DZ, w2[m]);
+          else tnz[m] = add_rowwise(c->ops_bwd_dec_mod[m][5], m, T_DG1, tn2[m], T_DZ, nullptr, -1, nullptr, w2[m]);
+        }
         for (int m : mord) add_wgrad(c->ops_bwd_dec_mod[m][4], m, T_DG1, tn2[m]);
         for (int rb = 0; rb < RB; ++rb)
           group_add_elt_task(g, 1, rb, B, ctr(0, T_DZ, rb), 1, S * tnz[0], M > 1 ? ctr(1, T_DZ, rb) : -1, M > 1 ? S * tnz[1] : 0,
@@ -1471,6 +1506,14 @@ void refresh_shadow(Ctx* c, cudaStream_t s) {
 void stage_inputs(Ctx* c, const float* const* x, const int64_t* ld, const float* eps, cudaStream_t s,
                   int only_modality = -1, bool want_eps = true, const int64_t* row_index = nullptr) {
   StageArgs a;
+  if (only_modality < 0 && c->split_heads && one_mode(c)) {     // a train / gradient step follows
+    int z = 0;
+    for (int m = 0; m < c->cfg.n_modalities && z + 1 < 8; ++m) {
+      const Mod& d = c->mods[m];
+      a.zero_ptr[z] = d.hd; a.zero_n[z++] = (int64_t)c->cfg.batch_size * d.nh;
+      a.zero_ptr[z] = d.dz; a.zero_n[z++] = (int64_t)c->cfg.batch_size * c->cfg.n_z;
+    }
+  }
   a.row_index = row_index;
   a.n_mod = c->cfg.n_modalities; a.batch = c->cfg.batch_size;
   for (int m = 0; m < a.n_mod; ++m) {

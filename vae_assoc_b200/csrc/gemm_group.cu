@@ -812,11 +812,11 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
             if (live) {
               if (elem.lf.n_mod == 1) {
                 float rk[1];
-                latent_fwd_row<1, LoadCg>(elem.lf, r, rk, assoc);
+                latent_fwd_row<1, LoadCg>(elem.lf, r, rk, assoc, tk.act != 0);
                 kl0 = rk[0];
               } else {
                 float rk[2];
-                latent_fwd_row<2, LoadCg>(elem.lf, r, rk, assoc);
+                latent_fwd_row<2, LoadCg>(elem.lf, r, rk, assoc, tk.act != 0);
                 kl0 = rk[0]; kl1 = rk[1];
               }
             }
@@ -1392,10 +1392,10 @@ int group_add_problem(GroupPlan* g, int kind, const GemmArgs& a, char* err, int 
   else if (ok) p.map_aux = p.map_c;
   if (!ok) return -1;
   p.M = a.M; p.N = a.N; p.K = a.K; p.BN = BN;
-  p.reduce = (kind == 2) ? 1 : 0;
+  p.reduce = (kind == 2 || a.force_reduce) ? 1 : 0;
   p.act = a.act; p.round_out = a.round_out; p.has_aux = has_aux ? 1 : 0;
-  p.bias = (kind == 0) ? a.bias : nullptr;
-  p.colsum = (kind != 2) ? a.bias_grad : nullptr;   // NN / NT: bias_grad = where the column sums of C go
+  p.bias = (kind == 0 && !a.force_reduce) ? a.bias : nullptr;
+  p.colsum = (kind != 2 && !a.force_reduce) ? a.bias_grad : nullptr;   // NN / NT: bias_grad = where the column sums of C go
   p.c_ptr = a.C; p.ldc = a.ldc;
   p.mask_in = mask_in ? a.mask_in : nullptr;
   p.mask_out = (kind == 0 && a.act == ACT_RELU && !a.aux) ? a.mask_out : nullptr;
@@ -1431,7 +1431,7 @@ int group_add_task(GroupPlan* g, int prob, int m_blk, int n_blk, int kb0, int nk
 
 // an elementwise task over row block m_blk (kind 0: latent forward, 1: latent backward; arguments: group_set_elem)
 int group_add_elt_task(GroupPlan* g, int kind, int m_blk, int batch, int wait_ctr, int wait_cnt, int wait_val,
-                       int wait2_ctr, int wait2_val, int signal_ctr, int wait2_cnt) {
+                       int wait2_ctr, int wait2_val, int signal_ctr, int wait2_cnt, int variant) {
   GTask t;
   memset(&t, 0, sizeof t);
   t.problem = (int)g->problems.size() > 0 ? g->sites.back().first_problem : 0;   // unused; keeps the site-relative rebase >= 0
@@ -1440,6 +1440,7 @@ int group_add_elt_task(GroupPlan* g, int kind, int m_blk, int batch, int wait_ct
   t.wait2_ctr = wait2_ctr; t.wait2_val = wait2_val; t.signal_ctr = signal_ctr;
   t.bn = 64;
   t.flags = kind == 0 ? TF_ELT_LATENT_FWD : kind == 1 ? TF_ELT_LATENT_BWD : TF_ELT_FINALIZE;
+  t.act = variant;           // latent forward: 1 = the heads are split-K sums, add the layer's bias (LatentArgs::head_bias)
   t.M = batch;
   g->tasks.push_back(t);
   g->uploaded = false;

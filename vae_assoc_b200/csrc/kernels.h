@@ -37,6 +37,9 @@ struct GemmArgs {
   float* loss_partials = nullptr;
   float loss_scale = 0.f;   // binary: w / B_global ; Gaussian: w
   int loss_binary = 0;
+  // NN / NT on the tcgen05 path: the tile's raw accumulator is ADDED into C (TMA reduce-add; no bias, activation,
+  // rounding) -- a contraction with a tiny N and a long K is cut into k ranges that run as parallel tasks
+  int force_reduce = 0;
 };
 
 void launch_gemm_nn_simt(const GemmArgs& a, cudaStream_t s);
@@ -79,7 +82,7 @@ int group_num_tasks(const GroupPlan* g);
 // (kind 0: latent forward, 1: latent backward -- arguments from group_set_elem); waits / signals like a tile task
 // kind 2: cost finalize (sums the block partials of the loss / latent tasks; arguments: GElem::fin), one per launch
 int group_add_elt_task(GroupPlan* g, int kind, int m_blk, int batch, int wait_ctr, int wait_cnt, int wait_val,
-                       int wait2_ctr, int wait2_val, int signal_ctr, int wait2_cnt = 1);
+                       int wait2_ctr, int wait2_val, int signal_ctr, int wait2_cnt = 1, int variant = 0);
 struct GElem;
 void group_set_elem(GroupPlan* g, const GElem& e);
 // a launch site = the problems / tasks added between group_begin() and group_end(): ONE kernel launch (<= 24 problems)
@@ -145,6 +148,9 @@ struct StageArgs {
   uint32_t eps_seed = 0;
   int64_t global_row0 = 0;
   const int64_t* step_dev = nullptr;   // Adam step counter t (eps of the step about to run uses t)
+  // accumulators of the step's split-K contractions (heads, d z), cleared here so that no extra launch is needed
+  float* zero_ptr[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int64_t zero_n[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // floats (multiples of 4)
 };
 void launch_stage(const StageArgs& a, cudaStream_t s);
 void launch_philox_normal(float* dst, int64_t n_rows, int n_cols, uint32_t seed, uint32_t tag, int64_t row0,
@@ -169,6 +175,9 @@ struct LatentArgs {
   float* partials = nullptr;                                      // [kMaxPartialBlocks][kCostSlots]
   int with_grad = 1;
   int round_z = 0;                  // z feeds a tcgen05 GEMM (n_z large enough): round to tf32
+  // split-K heads layer (tile-kernel tasks only): `heads` holds the bias-free sums of the k ranges; the latent task adds
+  // the layer's bias (mu | log sigma^2, 2 n_z values) and writes the completed row back
+  const float* head_bias[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 int launch_latent_fwd(const LatentArgs& a, cudaStream_t s);       // returns number of blocks (partials rows)
 

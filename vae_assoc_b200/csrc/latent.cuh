@@ -19,7 +19,8 @@ constexpr int kLatentRegs = 4;    // latent dimensions loaded per batch (every l
 // load placed after them waits for them -- with one L2 round trip (~1 us inside the persistent kernel) per latent
 // dimension the row cost 4-8 us instead of ~1.5
 template <int NMOD, typename LOAD>
-__device__ __forceinline__ void latent_fwd_row(const LatentArgs& a, int64_t r, float (&row_kl)[NMOD], float& row_assoc) {
+__device__ __forceinline__ void latent_fwd_row(const LatentArgs& a, int64_t r, float (&row_kl)[NMOD], float& row_assoc,
+                                               bool add_head_bias = false) {
   const int nz = a.n_z;
 #pragma unroll
   for (int m = 0; m < NMOD; ++m) row_kl[m] = 0.f;
@@ -48,6 +49,13 @@ __device__ __forceinline__ void latent_fwd_row(const LatentArgs& a, int64_t r, f
       for (int m = 0; m < NMOD; ++m) {
         mu[m] = mu_[m][i];
         lv[m] = lv_[m][i];
+        if (add_head_bias) {                             // split-K heads: sums of the k ranges + the layer's bias; the
+          mu[m] += __ldg(a.head_bias[m] + k);            // completed row goes back (probes, latent backward)
+          lv[m] += __ldg(a.head_bias[m] + nz + k);
+          float* hw = const_cast<float*>(a.heads[m]);
+          hw[r * 2 * nz + k] = mu[m];
+          hw[r * 2 * nz + nz + k] = lv[m];
+        }
         ex[m] = expf(lv[m]);
         const float zv = mu[m] + sqrtf(ex[m]) * e;                             // :102-103
         a.z[m][r * nz + k] = a.round_z ? round_tf32(zv) : zv;

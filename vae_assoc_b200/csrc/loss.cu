@@ -54,6 +54,12 @@ __global__ void __launch_bounds__(256) stage_kernel(StageArgs a) {
       }
     }
   }
+  for (int z = 0; z < 8; ++z) {
+    if (a.zero_ptr[z] == nullptr) continue;
+    float4* __restrict__ zp = reinterpret_cast<float4*>(a.zero_ptr[z]);
+    const int64_t n4 = a.zero_n[z] >> 2;
+    for (int64_t i = tid; i < n4; i += nthreads) zp[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   if (a.eps_dst != nullptr) {
     if (a.eps_src != nullptr) {
       const int64_t total = (int64_t)a.batch * a.n_z;
