@@ -388,7 +388,8 @@ def test_fused_schedules_match_four_launch(va, monkeypatch, batch):
     stand-alone latent kernels (same device code: csrc/latent.cuh).  All three must agree: every gradient of a first
     step, then the costs of 5 training steps.  "two" vs "four" differ by summation order only (2e-5); the fused loss
     epilogue forms d a over one reciprocal instead of two quotients, so a few d a entries land on the neighbouring tf32
-    value (1e-4; 1e-3 at batch 2048, see below).  Batch 700 = three row blocks of 256, the last one ragged."""
+    value, and "one" sums some contractions in another order (see below): 1e-3.  Batch 700 = three row blocks of 256, the
+    last one ragged."""
     archs = vo.reference_archs(4)
     X = [x.astype(np.float32) for x in synth.synth_batch(archs, [True, False], 0, 1, 0, batch)]
     eps = philox.eps_rows(3, 0, 0, batch, 4).astype(np.float32)
@@ -412,7 +413,8 @@ def test_fused_schedules_match_four_launch(va, monkeypatch, batch):
     # (from four row blocks on, "one" hands tiles over by halves between dependent layers: its consumers sum their k-blocks in
     # another order, a few activations land on the neighbouring tf32 value and a few relu masks flip -- the schedules then
     # agree like two tf32 implementations do, not to summation order)
-    for mode, tol in (("one", 1e-4 if batch < 1024 else 1e-3), ("two", 2e-5)):
+    # at one to three row blocks its heads layer and decoder-input dgrad run as split-K tasks (another summation order too)
+    for mode, tol in (("one", 1e-3), ("two", 2e-5)):
         np.testing.assert_allclose(out[mode][0], out["four"][0], rtol=tol)
         assert abs(out[mode][1] - out["four"][1]) <= tol * abs(out["four"][1])
         for a, b, n in zip(out[mode][2], out["four"][2], range(100)):
