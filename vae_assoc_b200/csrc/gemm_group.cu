@@ -737,7 +737,7 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
       while (t >= 0) {
         const GTask* tp = tasks + t;
         const int flags = __ldg(&tp->flags), sig = __ldg(&tp->signal_ctr);
-        if (!(flags & TF_ELT) && sig >= 0) {
+        if (sig >= 0) {                    // tile tasks and elementwise tasks alike
           // (every signalling tile cycles both barriers of its ring slot, so that their phases stay in step)
           mbar_wait(half_bar(seq), (seq / kDoneRing) & 1);
           if (flags & TF_SIG_HALF) {
@@ -775,6 +775,7 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
       const GTask tk_after = load_task(tasks, t_after);
       if (tk.flags & TF_ELT) {
         // ---- elementwise task: rows [256 m_blk + 128 rank, +128) of the batch, one thread per row (warps 0..3) ----
+        if (kTimeline && tl && rank == 0 && warp == 2 && lane == 0) { tl[kTL * t + 3] = gtimer(); tl[kTL * t + 5] = blockIdx.x >> 1; tl[kTL * t + 6] = t_entry; }
         if (lane == 0) {
           for (int c = 0; c < tk.wait_cnt; ++c) wait_counter(counters + tk.wait_ctr + c, (uint32_t)tk.wait_val);
           if (tk.wait2_ctr >= 0)
@@ -782,6 +783,7 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
           fence_acq_rel_gpu();               // pairs with the producers' red.release.gpu (inputs are read with ld.cg)
         }
         __syncwarp();
+        if (kTimeline && tl && rank == 0 && warp == 2 && lane == 0) tl[kTL * t + 0] = gtimer();
         if (tk.flags & TF_ELT_FINALIZE) {
           // ---- cost finalize: one warp, lanes stride the block partials, fixed-order sums (finalize_kernel's arithmetic) ----
           if (e == 0 && rank == 0) {
@@ -843,7 +845,21 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
           }
         }
         __syncwarp();
-        if (elect_one() && tk.signal_ctr >= 0) red_release_gpu_add(counters + tk.signal_ctr, 1u);
+        if (kTimeline && tl && rank == 0 && warp == 2 && lane == 0) tl[kTL * t + 8] = gtimer();
+        // published like a tile: CTA-local arrival, the signal warp fences once and adds this CTA's kEpiWarps arrivals
+        // (sixteen red.release.gpu of the warps themselves took ~3 us longer to reach the consumers)
+        if (tk.signal_ctr >= 0) {
+          if (elect_one()) {
+            if (sig_count >= (uint32_t)kDoneRing) {
+              uint32_t done;
+              do { asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(done) : "r"(sig_seq_addr) : "memory"); } while (done + kDoneRing <= sig_count);
+            }
+            asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(half_bar(sig_count)) : "memory");
+            asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(done_bar(sig_count)) : "memory");
+          }
+          ++sig_count;
+        }
+        if (kTimeline && tl && rank == 0 && warp == 2 && lane == 0) tl[kTL * t + 4] = gtimer();
         t = t_after;
         tk = tk_after;
         --tcount;
@@ -1553,7 +1569,12 @@ void group_debug_timeline(const GroupPlan* g, int site, uint32_t* queue, int res
   for (int k = 0; k < show; ++k) {
     const int i = (k < show / 2 || show == count) ? k : count - (show - k);
     const GTask& tk = g->tasks[first + i];
-    if (tk.nkb == 0) continue;
+    if (tk.nkb == 0) {
+      fprintf(stderr, "  elt  %4d flags %5d rb %2d cl %2llu | popped %6.2f inputs ready %6.2f work done %6.2f signalled %6.2f us\n", i, tk.flags,
+              tk.m_blk, h[kTL * i + 5], (h[kTL * i + 3] - t0) * 1e-3, (h[kTL * i + 0] - t0) * 1e-3, (h[kTL * i + 8] - t0) * 1e-3,
+              (h[kTL * i + 4] - t0) * 1e-3);
+      continue;
+    }
     fprintf(stderr, "  task %4d prob %2d (%2d,%2d) nkb %3d cl %2llu entry %6.2f | prod %6.2f mma %6.2f..%6.2f (%llu cyc) epi %6.2f..%6.2f us | ld0 %6.0f chunk0 %6.0f loop %6.2f | math %6.0f mask %6.0f wait %6.0f sts %6.0f\n", i,
             tk.problem, tk.m_blk, tk.n_blk, tk.nkb, h[kTL * i + 5], (h[kTL * i + 6] - t0) * 1e-3, (h[kTL * i + 0] - t0) * 1e-3,
             (h[kTL * i + 1] - t0) * 1e-3, (h[kTL * i + 2] - t0) * 1e-3, h[kTL * i + 7], (h[kTL * i + 3] - t0) * 1e-3, (h[kTL * i + 4] - t0) * 1e-3,

@@ -99,6 +99,9 @@ __device__ __forceinline__ void latent_fwd_row(const LatentArgs& a, int64_t r, f
   }
 }
 
+// (A fully vectorised n_z = 4 form of this row -- 128-bit loads and stores, all results held until the end -- measured
+// SLOWER inside the tile kernel: 6.2 against 4.0 us per task at B = 100, 0.282 against 0.276 ms per step at 8192.)
+
 // element (r, k) of the latent backward for modality m: (d mu, d log sigma^2) from d z and the stashed KL gradients
 template <typename LOAD>
 __device__ __forceinline__ void latent_bwd_elem(const LatentBwdArgs& a, int m, int64_t r, int k, float& dm, float& dl) {
