@@ -533,6 +533,10 @@ def main():
                     if top.get("bound") == "tensor" else "")
     if top.get("bound") == "tensor" and top.get("achieved") and tf32_ref:
         roofline["frac_of_tf32_cublas"] = top["achieved"] / tf32_ref
+    if top["name"] == "seg_step":
+        roofline["note"] += ("; seg_step = ONE launch of the persistent tile kernel carrying the whole gradient step (all 34 "
+                             "contractions, latent stage, reconstruction losses, cost): its fraction is the step-level figure, "
+                             "not the best segment's")
     # algorithmic FLOPs of one step = sum over the contractions of the schedule (2*M*N*K each); for the dense configs this
     # is SURVEY 8d's per-sample figure x B (7 744 400 x B at the reference arch)
     step_flops = sum(f for (_, f, _) in acc.values())

@@ -1,6 +1,7 @@
 #!/bin/bash
-# quick GPU pass: GEMM + parity tests, bench line, per-task timeline
+# quick pass: GEMM unit tests + parity tests, then the HBM-resident timing loop at 8192 / 1024 / 100 pairs under switches
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_gemm.py tests/test_gpu_parity.py -m gpu -x -q > gpurun_out/pytest_quick.log 2>&1; echo "pytest exit $?"; tail -4 gpurun_out/pytest_quick.log
-timeout 300 python bench.py --no-cpu-baseline > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; echo "bench exit $?"
-VAEASSOC_TC_TIMELINE=1 VAEASSOC_TC_TIMELINE_ALL=1 timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > /dev/null 2> gpurun_out/timeline.txt; echo "tl exit $?"
+timeout 900 python -m pytest tests/test_gpu_gemm.py tests/test_gpu_parity.py -m gpu -q -x > gpurun_out/q_pytest.log 2>&1; echo "pytest exit $?"; tail -3 gpurun_out/q_pytest.log
+run() { for B in 8192 1024 100; do echo -n "$1 B=$B "; env $1 timeout 300 python bench.py --batch $B --steps 200 --warmup 20 --no-cpu-baseline --no-parity --no-secondary --quick 2>/dev/null | tail -1; done; }
+run "X=1"
+run "${1:-VAEASSOC_RING_FIXED=1}"

@@ -3,6 +3,8 @@ loops and epilogues, mean durations; per cluster the share of time its MMA issue
 import re, sys, collections
 lines = open(sys.argv[1]).read().splitlines()
 pat = re.compile(r"task\s+(\d+) prob\s+(\d+) \(\s*(\d+),\s*(\d+)\) nkb\s+(\d+) cl\s+(\d+) entry\s+([\d.-]+) \| prod\s+([\d.-]+) mma\s+([\d.-]+)\.\.\s*([\d.-]+) \((\d+) cyc\) epi\s+([\d.-]+)\.\.\s*([\d.-]+) us")
+heads = [i for i, l in enumerate(lines) if l.startswith("[group timeline]")]
+lines = lines[heads[-1]:]          # the last dump of the file (bench.py profiles the step several times)
 T = []
 for l in lines:
     m = pat.search(l)

@@ -963,7 +963,7 @@ void build_segments(Ctx* c) {
       if (nodeps) { inT = -1; outT = -1; }
       if (in_m < 0) in_m = m;
       GemmArgs a = override_args ? *override_args : op.gargs;
-      a.bias_grad = colsum;
+      a.bias_grad = getenv("VAEASSOC_DEBUG_NO_COLSUM") ? nullptr : colsum;     // timing experiments only: no bias gradients
       const int prob = group_add_problem(g, op.kind, a, err, sizeof err);
       if (prob < 0) fail("segment plan for %s failed: %s", op.name.c_str(), err);
       const int tm = group_problem_tiles_m(g, prob), tn = group_problem_tiles_n(g, prob), kb = group_problem_kblocks(g, prob);

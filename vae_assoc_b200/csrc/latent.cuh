@@ -117,47 +117,9 @@ __device__ __forceinline__ void latent_bwd_elem(const LatentBwdArgs& a, int m, i
   a.dheads[m][r * 2 * nz + nz + k] = dl;
 }
 
-// latent dimensions [k0, k0 + kLatentRegs) of a row of modality m, every load issued before the first store.  REDUCE (tile-kernel
-// task): the warp's 32 rows are summed per (m, k) and lane 0 adds the sums into bh_grad[m] (bias gradient of the heads
-// layer: column sums of d mu | d log sigma^2); rows that are not `live` contribute zeros and store nothing
-template <typename LOAD, bool REDUCE>
-__device__ __forceinline__ void latent_bwd_row(const LatentBwdArgs& a, int m, int64_t r, int k0, bool live, float* bh_grad,
-                                               int lane) {
-  const int nz = a.n_z;
-  float e_[kLatentRegs], lv_[kLatentRegs], dz_[kLatentRegs], gm_[kLatentRegs], gl_[kLatentRegs];
-#pragma unroll
-  for (int i = 0; i < kLatentRegs; ++i) {
-    const int k = k0 + i;
-    if (k < nz && live) {
-      e_[i] = LOAD::ld(a.eps + r * nz + k);
-      lv_[i] = LOAD::ld(a.heads[m] + r * 2 * nz + nz + k);
-      dz_[i] = LOAD::ld(a.dz[m] + r * nz + k);
-      gm_[i] = LOAD::ld(a.gstat[m] + r * 2 * nz + k);
-      gl_[i] = LOAD::ld(a.gstat[m] + r * 2 * nz + nz + k);
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < kLatentRegs; ++i) {
-    const int k = k0 + i;
-    if (k >= nz) continue;                      // warp-uniform
-    float vm = 0.f, vl = 0.f;
-    if (live) {
-      const float s = sqrtf(expf(lv_[i]));                                     // d z / d lv = eps * s / 2
-      vm = dz_[i] + gm_[i];
-      vl = dz_[i] * e_[i] * 0.5f * s + gl_[i];
-      if (a.round_out) { vm = round_tf32(vm); vl = round_tf32(vl); }
-      a.dheads[m][r * 2 * nz + k] = vm;
-      a.dheads[m][r * 2 * nz + nz + k] = vl;
-    }
-    if (REDUCE && bh_grad != nullptr) {
-      vm = warp_sum(vm); vl = warp_sum(vl);
-      if (lane == 0) { atomicAdd(bh_grad + k, vm); atomicAdd(bh_grad + nz + k, vl); }
-    }
-  }
-}
-
 // n_z == 4 (the reference's latent width): every operand of the row is ONE 128-bit L1-bypassing load, so nothing of the
-// row waits behind a store; m = modality.  Same arithmetic as latent_bwd_elem.  REDUCE: see latent_bwd_row.
+// row waits behind a store; m = modality.  Same arithmetic as latent_bwd_elem.  REDUCE (tile-kernel task): the warp's 32 rows are summed per k and lane 0 adds the sums into bh_grad (bias gradient of
+// the heads layer: column sums of d mu | d log sigma^2); rows that are not `live` contribute zeros and store nothing.
 template <bool REDUCE>
 __device__ __forceinline__ void latent_bwd_row4(const LatentBwdArgs& a, int m, int64_t r, bool live, float* bh_grad, int lane) {
   float vm[4] = {0.f, 0.f, 0.f, 0.f}, vl[4] = {0.f, 0.f, 0.f, 0.f};
