@@ -429,6 +429,30 @@ def test_fused_schedules_match_four_launch(va, monkeypatch, batch):
     assert out["one"][5] <= 4, out["one"][5]        # staging, gradient memset, the tile kernel, Adam
 
 
+@pytest.mark.parametrize("which,batch", [(0, 100), (0, 2048), (1, 700)])
+def test_single_modality_one_launch(va, which, batch):
+    """ONE modality (a plain VAE, no association term: `itertools.combinations` over one element is empty, vae_assoc.py:346)
+    through the one-launch tf32 schedule -- the latent and finalize tasks then wait on one modality's counters only --
+    against the operand-rounding oracle: cost, every gradient, three training steps.  Image modality at 100 pairs (split-K
+    heads) and 2048 (half-tile hand-over), joint modality at a ragged 700."""
+    archs = [vo.reference_archs(4)[which]]
+    binary, weights = (which == 0,), (50.0 if which == 0 else 1.0,)
+    model, oracle = make_pair(va, archs, batch, "relu", "tf32", seed=21, weights=weights, binary=binary)
+    X, eps = inputs(vo.reference_archs(4), batch, 21)
+    X = [X[which]]
+    cost = float(model.compute_gradients(X, eps))
+    c_ref, g_ref, pr = oracle.loss_and_grads(X, eps)
+    assert abs(cost - c_ref) <= 5e-4 * abs(c_ref), (cost, c_ref)
+    for g, r, n in zip(model.get_grads(), [g for gs in g_ref for g in gs], model.variable_roles()):
+        assert rel_l2(g, r) < 5e-3, (n, rel_l2(g, r))        # relu mask flips at tf32 resolution: see check_step
+    assert rel(model.vae_reconstr_losses[0], pr["vae_reconstr_losses"][0]) < 5e-4
+    assert model.launch_count() > 0
+    costs = [float(model.partial_fit(X, eps)) for _ in range(3)]
+    costs_ref = [float(oracle.partial_fit(X, eps)) for _ in range(3)]
+    np.testing.assert_allclose(costs, costs_ref, rtol=2e-3)
+    model.close()
+
+
 @pytest.mark.parametrize("f", ["relu", "softplus"])
 def test_gradient_step_ragged_row_blocks(va, f):
     """B = 700 (two full 256-row blocks + a ragged one) through the two-launch tf32 schedule vs the operand-rounding
