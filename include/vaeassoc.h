@@ -111,7 +111,10 @@ int vaeassoc_step_set(vaeassoc_handle h, int64_t step);
  *               (key (eps_seed, 1), counter (global row, block, step)) replacing tf.random_normal :90
  * The step is asynchronous; the scalar cost of step t lands in a device-side history ring and is fetched with
  * vaeassoc_cost_read (which synchronises), so a training loop need not sync every step as the reference does.
- * vaeassoc_grad_step = the same without the Adam update (gradients stay readable through VAEASSOC_GRADS). */
+ * vaeassoc_grad_step = the same without the Adam update (gradients stay readable through VAEASSOC_GRADS).  After a
+ * vaeassoc_train_step the gradient buffer is unspecified: on one GPU the Adam kernel hands the accumulator back cleared
+ * (the next step then needs no memset), like the gradient tensors of the reference's `minimize` op, which no caller
+ * can fetch either (vae_assoc.py:373-374). */
 int vaeassoc_train_step(vaeassoc_handle h, const float* const* x_dev, const int64_t* ld, const float* eps_dev);
 int vaeassoc_grad_step(vaeassoc_handle h, const float* const* x_dev, const int64_t* ld, const float* eps_dev);
 int vaeassoc_adam_step(vaeassoc_handle h);                            /* ApplyAdam on the current gradients */
