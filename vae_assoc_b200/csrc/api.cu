@@ -573,14 +573,15 @@ Op make_gemm(Ctx* c, const char* name, int m, int kind, GemmArgs a, int64_t w_of
     const int kb = group_problem_kblocks(c->gplan, prob);
     if (kind == KIND_TN) {
       // split the batch contraction into row-block ranges so that every SM pair gets a task
-      const int rbs = (kb + 7) / 8;
+      const int kpr = group_problem_kb_per_rowblock(c->gplan, prob);
+      const int rbs = (kb + kpr - 1) / kpr;
       int splits = std::max(1, std::min(rbs, (kNumSMs / 2) / std::max(1, tm * tn)));
       if (a.splitk > 1) splits = std::min(a.splitk, rbs);
       const int per = (rbs + splits - 1) / splits;
       for (int r0 = 0; r0 < rbs; r0 += per)
         for (int i = 0; i < tm; ++i)
           for (int j = 0; j < tn; ++j)
-            group_add_task(c->gplan, prob, i, j, r0 * 8, std::min(per * 8, kb - r0 * 8), -1, 0, 0, -1, 0, -1);
+            group_add_task(c->gplan, prob, i, j, r0 * kpr, std::min(per * kpr, kb - r0 * kpr), -1, 0, 0, -1, 0, -1);
     } else {
       for (int i = 0; i < tm; ++i)
         for (int j = 0; j < tn; ++j) group_add_task(c->gplan, prob, i, j, 0, kb, -1, 0, 0, -1, 0, -1);
@@ -988,14 +989,15 @@ void build_segments(Ctx* c) {
       const int prob = group_add_problem(g, op.kind, a, err, sizeof err);
       if (prob < 0) fail("segment plan for %s failed: %s", op.name.c_str(), err);
       const int tm = group_problem_tiles_m(g, prob), tn = group_problem_tiles_n(g, prob), kb = group_problem_kblocks(g, prob);
-      const int rbs = (kb + 7) / 8;
+      const int kpr = group_problem_kb_per_rowblock(g, prob);
+      const int rbs = (kb + kpr - 1) / kpr;
       const int splits = std::max(1, std::min(rbs, (kNumSMs / 2) / std::max(1, tm * tn)));
       const int per = (rbs + splits - 1) / splits;
       for (int r0 = 0; r0 < rbs; r0 += per) {
         const int nrb = std::min(per, rbs - r0);
         for (int i = 0; i < tm; ++i)
           for (int j = 0; j < tn; ++j)
-            group_add_task(g, prob, i, j, r0 * 8, std::min(nrb * 8, kb - r0 * 8), dyT >= 0 ? ctr(dy_m, dyT, r0) : -1,
+            group_add_task(g, prob, i, j, r0 * kpr, std::min(nrb * kpr, kb - r0 * kpr), dyT >= 0 ? ctr(dy_m, dyT, r0) : -1,
                            dyT >= 0 ? nrb : 0, kGroupSignalsPerTile * dy_tn, -1, 0, -1);
       }
       if (external && op.gargs.bias_grad) {
@@ -2704,14 +2706,15 @@ int vaeassoc_debug_gemm(vaeassoc_handle h, int kind, int use_tc, int M, int N, i
     if (prob < 0) { group_destroy(plan); fail("tcgen05 plan failed: %s", err); }
     const int tm = group_problem_tiles_m(plan, prob), tn = group_problem_tiles_n(plan, prob);
     const int kb = group_problem_kblocks(plan, prob);
-    const int rbs = (kb + 7) / 8;
+    const int kpr = group_problem_kb_per_rowblock(plan, prob);
+    const int rbs = (kb + kpr - 1) / kpr;
     const int splits = kind == KIND_TN ? std::max(1, std::min(rbs, (kNumSMs / 2) / std::max(1, tm * tn))) : 1;
     const int per = (rbs + splits - 1) / splits;
     for (int r0 = 0; r0 < (kind == KIND_TN ? rbs : 1); r0 += per)
       for (int i = 0; i < tm; ++i)
         for (int j = 0; j < tn; ++j)
-          group_add_task(plan, prob, i, j, kind == KIND_TN ? r0 * 8 : 0,
-                         kind == KIND_TN ? std::min(per * 8, kb - r0 * 8) : kb, -1, 0, 0, -1, 0, -1);
+          group_add_task(plan, prob, i, j, kind == KIND_TN ? r0 * kpr : 0,
+                         kind == KIND_TN ? std::min(per * kpr, kb - r0 * kpr) : kb, -1, 0, 0, -1, 0, -1);
     group_set_counters(plan, h->gsync, h->n_ctr);
     if (!group_end(plan, err, sizeof err) || !group_upload(plan, err, sizeof err)) { group_destroy(plan); fail("%s", err); }
     group_launch(plan, dsite, h->gsync + h->n_ctr + 2 * (h->max_sites - 1), 0, 0, dyn_first(h), h->stream);

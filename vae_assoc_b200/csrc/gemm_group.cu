@@ -313,7 +313,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
   return d;
 }
 __device__ __forceinline__ uint64_t desc_k_major(uint32_t addr) { return make_desc(addr, 16, 1024, 2); }
-__device__ __forceinline__ uint64_t desc_mn_major(uint32_t addr) { return make_desc(addr, BK * 128, 512, 1); }
+__device__ __forceinline__ uint64_t desc_mn_major(uint32_t addr, uint32_t k_rows = BK) { return make_desc(addr, k_rows * 128, 512, 1); }
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): c_format [4,6)=1 (F32), a/b_format [7,10),[10,13)=2 (TF32),
 // a_major bit 15, b_major bit 16 (1 = MN-major), n_dim [17,23) = N>>3, m_dim [24,29) = M>>4
@@ -336,6 +336,7 @@ struct alignas(64) GProblem {
   int act, round_out, has_aux;
   int loss_binary;           // loss-fused output layer: Bernoulli cross-entropy (else Gaussian l2)
   float loss_scale;
+  int k64;                   // operand maps deliver 64-deep k-blocks (two 32-deep chunks per TMA instruction), see kDeepK
   const float* bias;
   float* colsum;             // epilogue adds the column sums of its output tile here (bias gradient), or null
   float* c_ptr;              // output matrix for the direct (non-TMA) stores of the NN / NT epilogue
@@ -375,6 +376,14 @@ enum { TF_A_MN = 1, TF_B_MN = 2, TF_REDUCE = 4, TF_AUX = 8, TF_ROUND = 16, TF_CO
        // contraction).  TF_HALF: consumer (wait2_ctr = half counter, wait2_val = k-blocks per producing tile);
        // TF_SIG_HALF: producer
        TF_HALF = kTaskHalf, TF_SIG_HALF = kTaskSigHalf };
+// Rows of a row-wise (NN / NT) tile per CTA of the pair.  A batch of at most 256 rows is ONE row block: instead of 128 rows
+// in the leader CTA and the rest (at B = 100: none) in its peer, each CTA takes half of them (rounded up to 8), so that
+// either CTA's TMA stream carries half of the A operand -- at small batches a main loop is bound by the bytes one SM
+// can pull per clock (~48), and the zero-filled rows of a 128-row box count like real ones.  The peer's rows then start
+// at rows_per_cta(M) instead of 128; TMEM lane = local row; rows at or past rows_per_cta within a CTA are dead.
+__host__ __device__ __forceinline__ int rows_per_cta(int M, bool small_rows) {
+  return (small_rows && M <= 256) ? max(8, (((M + 1) >> 1) + 7) & ~7) : 128;
+}
 // first-half chunk count of a tile with `n` chunks (both epilogue slots take the same number of first-half chunks)
 __host__ __device__ __forceinline__ int half_chunks(int n) { const int h = (((n + 1) >> 1) + 1) & ~1; return h < n ? h : n; }
 // (half_chunks() assumes two epilogue slots per TMEM lane quarter: the host only plans hand-overs when kGroupHalfOk)
@@ -500,10 +509,17 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
   // operand ring geometry of this launch (host: launch_site): the 128 KB ring holds 4 stages at the widest tile, 5 when
   // no tile of the launch is wider than 128, 6 when none is wider than 64 -- at small batches (one row block, 64-wide
   // tiles) a main loop is bound by the TMA round trip per stage, i.e. by the number of stages in flight
+  const bool small_rows = ((mode >> 24) & 1) != 0;      // rows_per_cta(): the plan's tensor maps were built with it
   const int ring_class = (mode >> 6) & 3;
-  const int nstages = ring_class == 2 ? 6 : ring_class == 1 ? 5 : kStages;
-  const uint32_t stage_bytes = ring_class == 2 ? (uint32_t)(A_BYTES + 32 * BK * 4) : ring_class == 1 ? (uint32_t)(A_BYTES + 64 * BK * 4) : (uint32_t)STAGE_BYTES;
-  const uint32_t stagger_ns = kEpiDebug ? (uint32_t)mode >> 8 : 0u;      // VAEASSOC_EPI_STAGGER_NS: the odd chunk slots start this much later
+  // ring_class 3 = 64-deep k-blocks (narrow launches at small batches): a stage is [A chunk 0 | A chunk 1] (2 x 16 KB) +
+  // [B chunk 0 | B chunk 1] (2 x 4 KB), three stages; ONE TMA instruction per operand fills both chunks.  At small batches
+  // a main loop is bound by the producer's instruction rate (~0.23 us per k-block of two TMA instructions, whatever the
+  // bytes and the ring depth), so half the instructions per k is half the main loop.
+  const bool k64 = ring_class == 3;
+  const int nstages = k64 ? 3 : ring_class == 2 ? 6 : ring_class == 1 ? 5 : kStages;
+  const uint32_t stage_bytes = k64 ? (uint32_t)(2 * A_BYTES + 2 * 32 * BK * 4) : ring_class == 2 ? (uint32_t)(A_BYTES + 32 * BK * 4) : ring_class == 1 ? (uint32_t)(A_BYTES + 64 * BK * 4) : (uint32_t)STAGE_BYTES;
+  const uint32_t b_off = k64 ? 2u * A_BYTES : (uint32_t)A_BYTES;      // B tile of a stage behind its A tile(s)
+  const uint32_t stagger_ns = kEpiDebug ? ((uint32_t)mode >> 8) & 0xfffu : 0u;      // VAEASSOC_EPI_STAGGER_NS: the odd chunk slots start this much later
   // barriers: full[s] (leader CTA only), empty[s], tmem_full[2], tmem_empty[2] (leader CTA only), aux[epilogue warp],
   // sched_full[kSched], sched_empty[kSched] (leader CTA only); then the TMEM slot and the task-index ring
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -609,9 +625,10 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
       const GProblem* p = &params.p[tk.problem];
       const int BN = tk.bn, BNH = BN >> 1;
       const bool a_mn = (tk.flags & TF_A_MN) != 0, b_mn = (tk.flags & TF_B_MN) != 0;
-      const int m0 = tk.m_blk * BM + (int)rank * BM_CTA;      // this CTA's rows of A
+      const int rpc = a_mn ? BM_CTA : rows_per_cta(tk.M, small_rows);   // (TN: M = features, always 128 per CTA)
+      const int m0 = tk.m_blk * BM + (int)rank * rpc;         // this CTA's rows of A
       const int nb0 = tk.n_blk * BN + (int)rank * BNH;        // this CTA's slice of B
-      const uint32_t stage_tx = 2u * (A_BYTES + (uint32_t)BNH * BK * 4);
+      const uint32_t stage_tx = (k64 ? 4u : 2u) * ((uint32_t)rpc * BK * 4 + (uint32_t)BNH * BK * 4);
       const bool half = (tk.flags & TF_HALF) != 0;
       const int W = half ? tk.wait2_val : tk.nkb;              // k-blocks per producing tile
       if (lane == 0) {
@@ -646,17 +663,20 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
           const int c_lo = pass == 0 ? 0 : hc, c_hi = pass == 0 ? hc : nch;
           for (int c = c_lo; c < c_hi; ++c, ++i) {
             const int s = ps;
-            const uint32_t sa = base + (uint32_t)s * stage_bytes, sb = sa + A_BYTES;
+            const uint32_t sa = base + (uint32_t)s * stage_bytes, sb = sa + b_off;
             const uint32_t full_leader = full_leader0 + 8u * s;
-            const int k0 = (tk.kb0 + j0 + c) * BK;
+            const int k0 = (tk.kb0 + j0 + c) * (k64 ? 2 * BK : BK);
             if (elect_one()) {
               mbar_wait(empty_bar(s), pphase ^ 1);
               if (kTimeline && tl && t == 0 && i < 64) tl[kTL * ntasks + (rank ? 128 : 0) + i] = gtimer();
               if (rank == 0) mbar_arrive_expect_tx(full_bar(s), stage_tx);
               // MN-major operands: one 3-D box {32 mn, 32 k, chunks} lands as [chunk][k][32 mn] (see make_map_mn)
+              // (64-deep k-blocks: K-major operands are 3-D {32 k, rows, k chunk}, box {32, rows, 2})
               if (a_mn) tma_load_3d_pair(sa, &p->map_a, full_leader, 0, k0, m0 >> 5);
+              else if (k64) tma_load_3d_pair(sa, &p->map_a, full_leader, 0, m0, k0 >> 5);
               else tma_load_2d_pair(sa, &p->map_a, full_leader, k0, m0);
               if (b_mn) tma_load_3d_pair(sb, &p->map_b, full_leader, 0, k0, nb0 >> 5);
+              else if (k64) tma_load_3d_pair(sb, &p->map_b, full_leader, 0, nb0, k0 >> 5);
               else tma_load_2d_pair(sb, &p->map_b, full_leader, k0, nb0);
               if (i == announce)               // the next task: known to every role while this one streams
                 t_after = (rank == 0) ? publish(queue_base + raw) : next_task();
@@ -690,6 +710,8 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
         const int announce = min(tk.nkb, nstages) - 1;   // the producer publishes the next task at this k-block
         const bool a_mn = (tk.flags & TF_A_MN) != 0, b_mn = (tk.flags & TF_B_MN) != 0;
         const uint32_t idesc = make_idesc(BM, tk.bn, a_mn, b_mn);
+        // 64-deep k-blocks: chunk 1 of a K-major operand starts behind the rows of chunk 0
+        const uint32_t a_chunk = (uint32_t)(a_mn ? BM_CTA : rows_per_cta(tk.M, small_rows)) * 128u, b_chunk = (uint32_t)(tk.bn >> 1) * 128u;
         const uint32_t acc = tcount & 1;
         const uint32_t tmem_d = tmem_base + acc * kAccCols;
         if (lane == 0) {
@@ -700,16 +722,25 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
         __syncwarp();
         for (int i = 0; i < tk.nkb; ++i) {
           const int s = ms;
-          const uint32_t sa = base + (uint32_t)s * stage_bytes, sb = sa + A_BYTES;
+          const uint32_t sa = base + (uint32_t)s * stage_bytes, sb = sa + b_off;
           if (elect_one()) {
             mbar_wait(full_bar(s), mphase);
             tc_fence_after();
             if (kTimeline && tl && t == 0 && i < 64) tl[kTL * ntasks + 64 + i] = gtimer();
+            if (k64) {
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-              const uint64_t da = a_mn ? desc_mn_major(sa + k * 1024) : desc_k_major(sa + k * 32);
-              const uint64_t db = b_mn ? desc_mn_major(sb + k * 1024) : desc_k_major(sb + k * 32);
-              umma_tf32_pair(tmem_d, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < 2 * BK / UMMA_K; ++k) {
+                const uint64_t da = a_mn ? desc_mn_major(sa + k * 1024, 2 * BK) : desc_k_major(sa + (k >> 2) * a_chunk + (k & 3) * 32);
+                const uint64_t db = b_mn ? desc_mn_major(sb + k * 1024, 2 * BK) : desc_k_major(sb + (k >> 2) * b_chunk + (k & 3) * 32);
+                umma_tf32_pair(tmem_d, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k) {
+                const uint64_t da = a_mn ? desc_mn_major(sa + k * 1024) : desc_k_major(sa + k * 32);
+                const uint64_t db = b_mn ? desc_mn_major(sb + k * 1024) : desc_k_major(sb + k * 32);
+                umma_tf32_pair(tmem_d, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+              }
             }
             umma_commit_pair(empty_bar(s));     // frees the smem slot in both CTAs once these MMAs have read it
             if (i == announce) t_after = next_task();
@@ -873,9 +904,11 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
       const int sig_hc = (tk.flags & TF_SIG_HALF) ? half_chunks(min(tk.bn / 32, (tk.N - tk.n_blk * tk.bn + 31) / 32)) : 0;
       float loss_acc = 0.0f;                 // this lane's row: reconstruction loss over the warp's chunks
       float* __restrict__ colsum = (tk.flags & TF_COLSUM) ? p->colsum : nullptr;
-      const int row0 = tk.m_blk * BM + (int)rank * BM_CTA + q * 32;    // first output row of this warp
+      const int rpc = (tk.flags & TF_A_MN) ? BM_CTA : rows_per_cta(tk.M, small_rows);
+      const int row0 = tk.m_blk * BM + (int)rank * rpc + q * 32;       // first output row of this warp
+      const int m_lim = min(tk.M, tk.m_blk * BM + (int)rank * rpc + rpc);   // rows of this CTA end here (warp-uniform)
       const int n0 = tk.n_blk * BN;
-      const int nchunks = (row0 < tk.M) ? min(BN / 32, (N - n0 + 31) / 32) : 0;   // warp-uniform
+      const int nchunks = (row0 < m_lim) ? min(BN / 32, (N - n0 + 31) / 32) : 0;   // warp-uniform
       const int nmine = nchunks > slot ? (nchunks - slot + kSlots - 1) / kSlots : 0;   // chunks slot, slot + kSlots, ... of this warp
       const uint32_t acc = tcount & 1;
       if (sig_hc > 0 && (nmine == 0 || slot >= sig_hc)) {      // no first-half chunk of this warp: nothing to wait for
@@ -902,7 +935,7 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
         if (3 < nmine && col + 3 * cs < N) bv3 = __ldg(bias + col + 3 * cs);
       }
       uint32_t mw0 = 0u, mw1 = 0u, mw2 = 0u, mw3 = 0u;
-      if (mask_in != nullptr && row0 + lane < tk.M) {
+      if (mask_in != nullptr && row0 + lane < m_lim) {
         const uint32_t* mrow = mask_in + (size_t)(row0 + lane) * (size_t)p->ldmask + (n0 >> 5) + slot;
         if (0 < nmine) mw0 = __ldg(mrow);
         if (1 < nmine) mw1 = __ldg(mrow + kSlots);
@@ -930,7 +963,7 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
         __syncwarp();
         red_pending = 0;
       }
-      const bool interior_rows = row0 + 32 <= tk.M;
+      const bool interior_rows = row0 + 32 <= m_lim;
       const uint32_t sts_base = ebuf + (uint32_t)lane * 128u, sts_x = (uint32_t)(lane & 7);
       const int rr = lane >> 3, jj = lane & 7;
       // read-back offsets of the transposed copy: row rr + 4k, 16-byte column jj; (rr + 4k) & 7 = rr + 4 (k & 1)
@@ -985,7 +1018,7 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
               v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + bq.w);
             }
           }
-          const int ncols = (row0 + lane < tk.M) ? min(32, N - (n0 + c * 32)) : 0;    // live columns of this lane's row
+          const int ncols = (row0 + lane < m_lim) ? min(32, N - (n0 + c * 32)) : 0;    // live columns of this lane's row
           const uint32_t xrow = ob + (uint32_t)lane * 128u, xsw = (uint32_t)(lane & 7);
           // (the four variants are separate straight-line loops: a per-element select of the loss form serialised the 32
           // independent MUFU chains of a chunk behind branches -- 18 us per tile instead of 7)
@@ -1083,10 +1116,16 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
             wl = __funnelshift_l(0u - v[j], wl, 1);
             wh = __funnelshift_l(0u - v[j + 16], wh, 1);
           }
-          if (interior_rows || row0 + lane < tk.M)
+          if (interior_rows || row0 + lane < m_lim)
             mask_out[(size_t)(row0 + lane) * (size_t)p->ldmask + (n0 >> 5) + c] = (wh << 16) | wl;
         }
         if (kTimeline && tl && rank == 0 && warp == 2 && lane == 0 && i == 0) tl[kTL * t + 12] = (unsigned long long)clock64();
+        if (rpc != BM_CTA && !interior_rows && row0 + lane >= m_lim) {
+          // split rows: A rows at or past rows_per_cta were not loaded (the stage holds an earlier task's data), so this
+          // lane's accumulator row is garbage -- the column sums and the TMA reduce-add read the staged tile
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0u;
+        }
         if (reduce || tma_store) {
           // box b was handed to a bulk store / reduce-add three chunks ago: wait until that one has read it
           if (elect_one()) bulk_wait_read<kEpiBufs - 1>();
@@ -1129,7 +1168,7 @@ gemm_group_kernel(const __grid_constant__ GParams<NP> params, const __grid_const
           } else if (col < ((N + 3) & ~3)) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-              if (row0 + rr + 4 * k < tk.M) {
+              if (row0 + rr + 4 * k < m_lim) {
                 const float4 o = lds128(ob + ((k & 1) ? rb_odd : rb_even) + (uint32_t)k * 512u);
                 asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + k * step), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
               }
@@ -1272,17 +1311,44 @@ bool make_map(CUtensorMap* map, const float* ptr, int64_t dim0, int64_t dim1, in
   return true;
 }
 
+// K-major operand [rows, K contiguous] for 64-deep k-blocks: a 3-D tensor {32 k, rows, ceil(K / 32) chunks} with strides
+// {4 B, pitch, 128 B}; ONE box {32, box_rows, 2} lands as [chunk][row][32 k] = two ordinary K-major tiles.  The last
+// chunk's k >= K - 32 c reads the pad columns of the row (pitches of the dense modalities are multiples of 32 floats; z and
+// the heads gradient, whose pitch is their width, read into the following rows / the buffer's guard region): finite
+// values, multiplied by the other operand's zeros -- its own k rows >= K are out of bounds (MN-major: zero-filled) or pad
+// columns that stay exactly 0 (weights under Adam).  Chunks past the end are zero-filled.
+bool make_map_k64(CUtensorMap* map, const float* ptr, int64_t dim_k, int64_t dim_rows, int64_t ld, int box_rows, char* err,
+                  int errlen) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { snprintf(err, errlen, "cuTensorMapEncodeTiled entry point not available"); return false; }
+  // (rows narrower than a chunk -- z: pitch n_z, the heads gradient: 2 n_z -- expose only their pitch; the box's remaining k
+  // are out of bounds and zero-filled, and no two rows of the map overlap)
+  cuuint64_t dims[3] = {(cuuint64_t)std::min<int64_t>(32, ld), (cuuint64_t)dim_rows, (cuuint64_t)((dim_k + 31) / 32)};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 4, 128u};
+  cuuint32_t box[3] = {32u, (cuuint32_t)box_rows, 2u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(err, errlen, "cuTensorMapEncodeTiled (3-D, K-major) failed (%d) ptr=%p k=%lld rows=%lld ld=%lld box_rows=%d", (int)r,
+             (const void*)ptr, (long long)dim_k, (long long)dim_rows, (long long)ld, box_rows);
+    return false;
+  }
+  return true;
+}
+
 // MN-major operand [dim_k rows, dim_mn contiguous] as a 3-D tensor {32, dim_k, ceil(dim_mn / 32)}: element (x, k, c) =
 // ptr[k * ld + 32 c + x].  The last chunk's x >= dim_mn - 32 c reads the first floats of the next row (or up to 124 B
 // past the last row: every buffer of the library carries that slack); those lanes only feed output rows / columns
 // past M / N, which the epilogue masks and the TMA store clips.  Rows k >= dim_k and chunks past the end are zero-filled.
 bool make_map_mn(CUtensorMap* map, const float* ptr, int64_t dim_mn, int64_t dim_k, int64_t ld, int chunks, char* err,
-                 int errlen) {
+                 int errlen, int box_k = 32) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) { snprintf(err, errlen, "cuTensorMapEncodeTiled entry point not available"); return false; }
   cuuint64_t dims[3] = {32u, (cuuint64_t)dim_k, (cuuint64_t)((dim_mn + 31) / 32)};
   cuuint64_t strides[2] = {(cuuint64_t)ld * 4, 128u};
-  cuuint32_t box[3] = {32u, 32u, (cuuint32_t)chunks};
+  cuuint32_t box[3] = {32u, (cuuint32_t)box_k, (cuuint32_t)chunks};
   cuuint32_t estr[3] = {1u, 1u, 1u};
   const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
@@ -1376,29 +1442,53 @@ int group_tile_width(int N, int batch_rows) {
   return std::min(max_bn, (((N + tiles_n - 1) / tiles_n) + 63) / 64 * 64);
 }
 
+bool deep_k_enabled() {
+  static const bool on = getenv("VAEASSOC_NO_DEEP_K") == nullptr && getenv("VAEASSOC_MAX_BN") == nullptr &&
+                         getenv("VAEASSOC_WIDE_TILES") == nullptr && getenv("VAEASSOC_RING_FIXED") == nullptr &&
+                         getenv("VAEASSOC_PITCH_ALIGN") == nullptr;
+  return on;
+}
+bool small_rows_enabled() {
+  static const bool on = getenv("VAEASSOC_NO_SMALL_ROWS") == nullptr;
+  return on;
+}
+
 // adds the contraction to the plan; returns its problem index or -1 (err filled)
 int group_add_problem(GroupPlan* g, int kind, const GemmArgs& a, char* err, int errlen) {
   GProblem p;
   memset(&p, 0, sizeof p);
   const int BN = getenv("VAEASSOC_WIDE_TILES") ? group_tile_width(a.N, 1 << 20) : group_tile_width(a.N, kind == 2 ? a.K : a.M);
   bool ok = true;
+  // 64-deep k-blocks where every tile of the plan is narrow, i.e. at batches of one to three row blocks (group_tile_width)
+  const int batch_rows = kind == 2 ? a.K : a.M;
+  // ... and where the K-major operands' chunk reads past K stay inside the row's zero pad (pitch a multiple of 32
+  // floats: every activation / weight of the dense modalities) or are cut by the map itself (pitch below 32: z, d heads)
+  auto k_major_ok = [](int64_t ld) { return ld % 32 == 0 || ld <= 32; };
+  const bool k64 = deep_k_enabled() && BN <= 64 && batch_rows <= 3 * BM &&
+                   (kind == 2 || (k_major_ok(a.lda) && (kind == 0 || k_major_ok(a.ldb))));
+  const int rpc = rows_per_cta(a.M, small_rows_enabled());
+  const int bk = k64 ? 64 : 32;
   switch (kind) {
     case 0:    // NN: A [M,K] K-major ; B [K,N] MN-major
-      ok = make_map(&p.map_a, a.A, a.K, a.M, a.lda, BM_CTA, false, err, errlen) &&
-           make_map_mn(&p.map_b, a.B, a.N, a.K, a.ldb, BN / 64, err, errlen);
+      ok = (k64 ? make_map_k64(&p.map_a, a.A, a.K, a.M, a.lda, rpc, err, errlen)
+                : make_map(&p.map_a, a.A, a.K, a.M, a.lda, rpc, false, err, errlen)) &&
+           make_map_mn(&p.map_b, a.B, a.N, a.K, a.ldb, BN / 64, err, errlen, bk);
       p.a_mn = 0; p.b_mn = 1;
       break;
     case 1:    // NT: A [M,K] K-major ; B [N,K] K-major
-      ok = make_map(&p.map_a, a.A, a.K, a.M, a.lda, BM_CTA, false, err, errlen) &&
-           make_map(&p.map_b, a.B, a.K, a.N, a.ldb, BN / 2, false, err, errlen);
+      ok = (k64 ? make_map_k64(&p.map_a, a.A, a.K, a.M, a.lda, rpc, err, errlen)
+                : make_map(&p.map_a, a.A, a.K, a.M, a.lda, rpc, false, err, errlen)) &&
+           (k64 ? make_map_k64(&p.map_b, a.B, a.K, a.N, a.ldb, BN / 2, err, errlen)
+                : make_map(&p.map_b, a.B, a.K, a.N, a.ldb, BN / 2, false, err, errlen));
       p.a_mn = 0; p.b_mn = 0;
       break;
     default:   // TN: A [K,M] MN-major ; B [K,N] MN-major
-      ok = make_map_mn(&p.map_a, a.A, a.M, a.K, a.lda, BM_CTA / 32, err, errlen) &&
-           make_map_mn(&p.map_b, a.B, a.N, a.K, a.ldb, BN / 64, err, errlen);
+      ok = make_map_mn(&p.map_a, a.A, a.M, a.K, a.lda, BM_CTA / 32, err, errlen, bk) &&
+           make_map_mn(&p.map_b, a.B, a.N, a.K, a.ldb, BN / 64, err, errlen, bk);
       p.a_mn = 1; p.b_mn = 1;
       break;
   }
+  p.k64 = k64 ? 1 : 0;
   ok = ok && make_map(&p.map_c, a.C, a.N, a.M, a.ldc, 32, false, err, errlen);
   const bool mask_in = kind != 2 && a.mask_in != nullptr && a.act == ACT_RELU && a.aux != nullptr;
   const bool loss = kind == 0 && a.loss_x != nullptr && a.loss_partials != nullptr;
@@ -1425,7 +1515,11 @@ int group_add_problem(GroupPlan* g, int kind, const GemmArgs& a, char* err, int 
 
 int group_problem_tiles_m(const GroupPlan* g, int prob) { return (g->problems[prob].M + BM - 1) / BM; }
 int group_problem_tiles_n(const GroupPlan* g, int prob) { const GProblem& p = g->problems[prob]; return (p.N + p.BN - 1) / p.BN; }
-int group_problem_kblocks(const GroupPlan* g, int prob) { return (g->problems[prob].K + BK - 1) / BK; }
+int group_problem_kblocks(const GroupPlan* g, int prob) {
+  const int bk = g->problems[prob].k64 ? 2 * BK : BK;
+  return (g->problems[prob].K + bk - 1) / bk;
+}
+int group_problem_kb_per_rowblock(const GroupPlan* g, int prob) { return g->problems[prob].k64 ? BM / (2 * BK) : BM / BK; }
 
 int group_add_task(GroupPlan* g, int prob, int m_blk, int n_blk, int kb0, int nkb, int wait_ctr, int wait_cnt,
                    int wait_val, int wait2_ctr, int wait2_val, int signal_ctr, int extra_flags) {
@@ -1501,12 +1595,18 @@ void launch_site(const GroupPlan* g, int site, uint32_t* queue, int reset_first,
   if (st.n_tasks <= 0) return;
   static const int env_mode = (getenv("VAEASSOC_EPI_BIAS_SHFL") ? 0 : 2) | (getenv("VAEASSOC_EPI_TMA_STORE") ? 4 : 0) |
                               (getenv("VAEASSOC_DEBUG_SKIP_MATH") ? 8 : 0) | (getenv("VAEASSOC_DEBUG_SKIP_STORE") ? 16 : 0) |
-                              (getenv("VAEASSOC_EPI_STAGGER_NS") ? (std::max(0, std::min(4000, atoi(getenv("VAEASSOC_EPI_STAGGER_NS")))) << 8) : 0);
+                              (getenv("VAEASSOC_EPI_STAGGER_NS") ? (std::max(0, std::min(4000, atoi(getenv("VAEASSOC_EPI_STAGGER_NS")))) << 8) : 0);   // bits 8..19
   int max_bn = 0;
   for (int i = 0; i < st.n_problems; ++i) max_bn = std::max(max_bn, g->problems[st.first_problem + i].BN);
   static const bool ring_fixed = getenv("VAEASSOC_RING_FIXED") != nullptr;
-  const int ring_class = ring_fixed ? 0 : (max_bn <= 64 ? 2 : (max_bn <= 128 ? 1 : 0));
-  const int mode = (dynamic_first ? 1 : 0) | env_mode | (advance ? 32 : 0) | (ring_class << 6);
+  int n_k64 = 0;
+  for (int i = 0; i < st.n_problems; ++i) n_k64 += g->problems[st.first_problem + i].k64 ? 1 : 0;
+  if (n_k64 != 0 && n_k64 != st.n_problems) {
+    fprintf(stderr, "[vaeassoc] launch site mixes 32- and 64-deep k-blocks (%d of %d problems): plan bug\n", n_k64, st.n_problems);
+    abort();
+  }
+  const int ring_class = n_k64 ? 3 : ring_fixed ? 0 : (max_bn <= 64 ? 2 : (max_bn <= 128 ? 1 : 0));
+  const int mode = (dynamic_first ? 1 : 0) | env_mode | (advance ? 32 : 0) | (ring_class << 6) | (small_rows_enabled() ? (1 << 24) : 0);
   const int clusters = std::min(st.n_tasks, kNumSMs / 2);
   if (st.n_problems <= kSiteProblemsSmall) {
     GParams<kSiteProblemsSmall> prm;

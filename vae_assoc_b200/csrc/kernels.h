@@ -68,7 +68,8 @@ void group_destroy(GroupPlan* g);
 int group_add_problem(GroupPlan* g, int kind, const GemmArgs& a, char* err, int errlen);   // problem index or -1
 int group_problem_tiles_m(const GroupPlan* g, int prob);
 int group_problem_tiles_n(const GroupPlan* g, int prob);
-int group_problem_kblocks(const GroupPlan* g, int prob);      // k-blocks of 32
+int group_problem_kblocks(const GroupPlan* g, int prob);      // k-blocks (32 deep; 64 at batches of one to three row blocks)
+int group_problem_kb_per_rowblock(const GroupPlan* g, int prob);   // k-blocks per 256 batch rows of a weight gradient (8 or 4)
 // operands ready when counters[wait_ctr .. +wait_cnt) >= wait_val (and counters[wait2_ctr] >= wait2_val); every
 // epilogue warp (16 per tile) bumps counters[signal_ctr] once the tile is globally visible; -1 / 0 = none
 // extra_flags: kTaskHalf (consumer of half-tile hand-overs: wait2_ctr = half counter, wait2_val = k-blocks per producing
