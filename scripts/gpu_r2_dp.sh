@@ -2,7 +2,7 @@
 # round 2: data-parallel pass at N ranks with the one-launch step -- the 2-GPU tests, then bench lines in peer and NCCL mode
 N=${1:-2}
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_dp.py -m gpu -q -x > gpurun_out/r2dp4_pytest.log 2>&1; echo "pytest exit $?"; tail -3 gpurun_out/r2dp4_pytest.log
+timeout 900 python -m pytest tests/test_dp.py -m gpu -q > gpurun_out/r2dp4_pytest.log 2>&1; echo "pytest exit $?"; tail -3 gpurun_out/r2dp4_pytest.log
 for mode in peer nccl; do
   case $mode in peer) E="VAEASSOC_DP_PEER=1";; nccl) E="VAEASSOC_DP_PEER=0";; esac
   env $E timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541 \
