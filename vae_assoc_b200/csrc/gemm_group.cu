@@ -6,28 +6,40 @@
 //   kind NT  C[M,N]  = (A[M,K] . B[N,K]^T) (*) act'(aux)    dgrad     (autodiff of the above, :373-374)
 //   kind TN  C[M,N] += A[K,M]^T . B[K,N]                    wgrad     (K = batch, split into tasks, TMA reduce-add)
 //
+//   elementwise tasks (no contraction): the latent stage of a row block and its backward (latent.cuh), the cost finalize
+//
 // Why: at the reference sizes one layer is 0.5-6 GFLOP, i.e. 3-8 us of tensor time; launched one kernel per layer
 // (34 GEMMs + 12 column sums per step) the fixed cost of a launch -- grid start, barrier / TMEM set-up, first
 // operand latency, epilogue drain, ~9 us -- exceeds the useful work.  Rows of the batch are independent through the
-// whole network, so the layers of a segment (encoder forward, decoder forward, decoder backward, encoder backward;
-// both modalities) become ONE launch: each task names the row-block counters it must see complete before its operands
-// may be loaded (the tiles of the producing layer over the same 256 rows) and the counter it bumps when its own
-// output is globally visible.  Tasks are listed in dependency order and handed out IN THAT ORDER from a global
-// atomic queue to whichever cluster is free, so the smallest unfinished task is always held by a running cluster
-// and is never blocked -- no deadlock, whatever share of the SMs other streams (NCCL, column sums) occupy.
+// whole network, so the WHOLE GRADIENT STEP of both modalities (round 1: each of its four segments) is ONE launch:
+// each task names the row-block counters it must see complete before its operands may be loaded (the tiles of the
+// producing layer over the same 256 rows) and the counter that is bumped when its own output is globally visible.
+// Tasks are listed in dependency order and handed out IN THAT ORDER from a global atomic queue to whichever cluster
+// is free, so the smallest unfinished task is always held by a running cluster and is never blocked -- no deadlock,
+// whatever share of the SMs other streams (NCCL) occupy.
 //
-// Tile engine (per cluster of two CTAs, `tcgen05.mma.cta_group::2`, UMMA 256 x BN x 8, kind::tf32):
+// Tile engine (per cluster of two CTAs, `tcgen05.mma.cta_group::2`, UMMA 256 x BN x 8, kind::tf32), 11 warps per CTA:
 //   warp 0     TMA producer: waits the task's counters, then streams A (its 128 rows) and B (its BN/2 columns)
-//              k-blocks of 32 into a 4-stage ring; both CTAs' loads complete on the leader's `full` barrier.
-//              The leader's producer is also the scheduler: it pops the queue two tasks ahead and publishes each
-//              task index through a 4-slot ring (shared memory of both CTAs, mbarrier full / empty) to every role
+//              k-blocks of 32 into a ring of 4 stages (5 / 6 when every tile of the launch is narrow; 3 stages of 64-deep
+//              k-blocks at small batches, see `ring_class`); both CTAs' loads complete on the leader's `full` barrier.
+//              A consumer of a half-tile hand-over (TF_HALF) streams the k-blocks of every producing tile's first half
+//              of chunks as soon as those are published, the rest after the full counters.
+//              The leader's producer is also the scheduler: it pops the queue one task ahead and publishes each task
+//              index through an 8-slot ring (shared memory of both CTAs, mbarrier full / empty) to every role
 //   warp 1     leader CTA: MMA issuer; accumulators double-buffered in TMEM (2 x 256 columns) so the epilogue of
 //              task i overlaps the main loop of task i+1; `tcgen05.commit` multicasts to both CTAs
-//   warps 2-9  epilogue: tcgen05.ld (thread = row, 32 columns) -> bias / activation / act'(aux tile via TMA, three
-//              boxes in flight per warp, processed in place) -> swizzled smem box -> coalesced 128-bit global stores
-//              (NN, NT: 8 lanes per 128-byte row segment) or TMA reduce-add (TN); then release the accumulator and
-//              bump the task's counter (red.release.gpu).  Nothing in the chunk loop waits on a fresh global / TMA
-//              round trip: bias values and aux boxes are requested before the accumulator is complete
+//   warps 2-9  epilogue: tcgen05.ld (thread = row, 32 columns) -> bias / activation / relu' from 1-bit masks / act'(aux
+//              tile via TMA, three boxes in flight per warp, processed in place) / reconstruction loss + d cost / d a
+//              against the target tile (TF_LOSS: the decoders' output layer) -> swizzled smem box -> coalesced 128-bit
+//              global stores (NN, NT: 8 lanes per 128-byte row segment) or TMA reduce-add (TN, split-K NN / NT); then
+//              release the accumulator and ARRIVE ON A CTA-LOCAL BARRIER (half-tile and full).  They also execute the
+//              elementwise tasks.  Nothing in the chunk loop waits on a fresh global / TMA round trip: bias values,
+//              mask words and aux boxes are requested before the accumulator is complete
+//   warp 10    signal warp: waits for those barriers, fences once (fence.acq_rel.gpu, cumulative over the epilogue
+//              warps' stores) and adds the CTA's eight arrivals to the row-block counter -- the MEMBAR.GPU of a release
+//              (~0.9 us) is off the epilogue warps
+// The kernel allocates 168 registers per thread (352 threads allocate like 384) and the chunk loop of the epilogue sits
+// at that limit: every variant that spilled ~150 bytes inside the loop lost 15-20 % on every configuration.
 // Operands are fp32 in HBM, rounded to tf32 by their producers.  TMA zero-fills loads past M / N / K and clips
 // stores (in 16-byte units: columns N..roundup4(N) receive zeros), so only 16-byte row pitches are required.
 //
