@@ -7,8 +7,14 @@
 // last-arriver pass in a fixed order.  Two runs of the fp32 path on the same inputs give bit-identical results
 // (tests/test_gpu_parity.py::test_fp32_path_is_bit_reproducible) -- Adam's g / (|g| + 1e-8) turns one sign flip of a
 // near-zero gradient into a different trajectory, so order noise in the fp32 path is not acceptable.
-// 64x64x16 CTA tile, 256 threads, 4x4 register micro-tile, smem tiles stored k-major so the inner loop reads
-// two float4 per k.  Any M/N/K/ld is accepted (bounds-checked loads; out-of-range elements contribute 0).
+// Two tile shapes, 256 threads each, smem tiles stored k-major so the inner loop reads float4s per k:
+//   128x128x8, 8x8 register micro-tile, 128-bit global loads where rows allow, register-prefetched and double-buffered
+//              in shared memory (one barrier per k-tile): the layers of the fp32-exact mode with M, N >= 128;
+//   64x64x16,  4x4 micro-tile, scalar loads: everything smaller.
+// Both sum over k in ascending order with fmaf, so a contraction gives the same bits whichever shape serves it (split-K
+// aside).  Any M/N/K/ld is accepted (bounds-checked loads; out-of-range elements contribute 0).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -133,6 +139,145 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(GemmArgs g, int k_per_spl
   }
 }
 
+// ---- 128 x 128 x 8 form ------------------------------------------------------------------------------------------
+constexpr int LBM = 128, LBN = 128, LBK = 8;
+
+template <int EPI>
+__device__ __forceinline__ void epi_element(const GemmArgs& g, int gm, int gn, float v) {
+  if (EPI == EPI_FWD) {
+    if (g.bias) v += g.bias[gn];
+    if (g.aux) v *= act_grad_from_output(g.act, g.aux[(int64_t)gm * g.ldaux + gn]);
+    else v = apply_act(g.act, v);
+    if (g.round_out) v = round_tf32(v);
+    g.C[(int64_t)gm * g.ldc + gn] = v;
+  } else if (EPI == EPI_DGRAD) {
+    if (g.aux) v *= act_grad_from_output(g.act, g.aux[(int64_t)gm * g.ldaux + gn]);
+    if (g.round_out) v = round_tf32(v);
+    g.C[(int64_t)gm * g.ldc + gn] = v;
+  } else {
+    if (gridDim.z > 1) g.ws[((int64_t)blockIdx.z * g.M + gm) * g.N + gn] = v;
+    else g.C[(int64_t)gm * g.ldc + gn] += v;
+  }
+}
+
+// one thread's four elements of a 128 x 8 operand tile.  CONTIG_MN: the operand is stored [K, X] (x contiguous): the
+// thread takes k = tid / 32 and four consecutive x; else [X, K] (k contiguous): x = tid / 2 and four consecutive k.
+template <bool CONTIG_MN>
+__device__ __forceinline__ void load_tile4(const float* __restrict__ P, int64_t ld, bool vec_ok, int x0, int X, int k0, int kend,
+                                           int tid, float (&r)[4]) {
+  if (CONTIG_MN) {
+    const int gk = k0 + (tid >> 5), gx = x0 + (tid & 31) * 4;
+    const float* src = P + (int64_t)gk * ld + gx;
+    if (gk < kend && gx + 3 < X && vec_ok) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src));
+      r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) r[j] = (gk < kend && gx + j < X) ? __ldg(src + j) : 0.f;
+    }
+  } else {
+    const int gx = x0 + (tid >> 1), gk = k0 + (tid & 1) * 4;
+    const float* src = P + (int64_t)gx * ld + gk;
+    if (gx < X && gk + 3 < kend && vec_ok) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src));
+      r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) r[j] = (gx < X && gk + j < kend) ? __ldg(src + j) : 0.f;
+    }
+  }
+}
+template <bool CONTIG_MN>
+__device__ __forceinline__ void store_tile4(float (*T)[LBM + 4], int tid, const float (&r)[4]) {
+  if (CONTIG_MN) {
+    *reinterpret_cast<float4*>(&T[tid >> 5][(tid & 31) * 4]) = make_float4(r[0], r[1], r[2], r[3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) T[(tid & 1) * 4 + j][tid >> 1] = r[j];
+  }
+}
+
+template <bool A_T, bool B_T, int EPI>
+__global__ void __launch_bounds__(NT, 2) gemm_simt128_kernel(GemmArgs g, int k_per_split) {
+  static_assert(LBM == LBN, "one tile-row type for both operands");
+  __shared__ __align__(16) float As[2][LBK][LBM + 4];
+  __shared__ __align__(16) float Bs[2][LBK][LBN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * LBM, n0 = blockIdx.x * LBN;
+  const int kbeg = blockIdx.z * k_per_split;
+  const int kend = min(g.K, kbeg + k_per_split);
+  // 128-bit loads need 16-byte aligned rows (the k offsets of a split are multiples of LBK, tile offsets of 128)
+  const bool vec_a = (g.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0);
+  const bool vec_b = (g.ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.B) & 15) == 0);
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const bool do_bsum = (EPI == EPI_WGRAD) && g.bias_grad != nullptr && blockIdx.y == 0 && ty == 0;
+
+  float ra[4], rb[4];
+  // A: A_T = stored [K, M] (m contiguous); B: !B_T = stored [K, N] (n contiguous)
+  load_tile4<A_T>(g.A, g.lda, vec_a, m0, g.M, kbeg, kend, tid, ra);
+  load_tile4<!B_T>(g.B, g.ldb, vec_b, n0, g.N, kbeg, kend, tid, rb);
+  store_tile4<A_T>(As[0], tid, ra);
+  store_tile4<!B_T>(Bs[0], tid, rb);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = kbeg; k0 < kend; k0 += LBK, buf ^= 1) {
+    const bool more = k0 + LBK < kend;
+    if (more) {                        // next k-tile: global -> registers while this one is consumed from shared memory
+      load_tile4<A_T>(g.A, g.lda, vec_a, m0, g.M, k0 + LBK, kend, tid, ra);
+      load_tile4<!B_T>(g.B, g.ldb, vec_b, n0, g.N, k0 + LBK, kend, tid, rb);
+    }
+#pragma unroll
+    for (int k = 0; k < LBK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      if (do_bsum) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bsum[j] += bv[j];
+      }
+    }
+    if (more) {
+      store_tile4<A_T>(As[buf ^ 1], tid, ra);
+      store_tile4<!B_T>(Bs[buf ^ 1], tid, rb);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int gm = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (gm >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int gn = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      if (gn >= g.N) continue;
+      epi_element<EPI>(g, gm, gn, acc[i][j]);
+    }
+  }
+  if (do_bsum) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int gn = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      if (gn >= g.N) continue;
+      if (gridDim.z > 1) g.ws[(int64_t)gridDim.z * g.M * g.N + (int64_t)blockIdx.z * g.N + gn] = bsum[j];
+      else g.bias_grad[gn] += bsum[j];
+    }
+  }
+}
+
 // second pass of a split contraction: C[m, n] += sum_z ws[z][m][n] and bias_grad[n] += sum_z wsb[z][n], z ascending
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, int splits, int M, int N,
                                                             float* __restrict__ C, int64_t ldc,
@@ -211,7 +356,12 @@ inline int colsum_rows_per_cta(int64_t rows) {
   return (int)rpc;
 }
 
+inline bool use_big_tiles(const GemmArgs& a) {
+  static const bool off = getenv("VAEASSOC_SIMT_SMALL_TILES") != nullptr;
+  return !off && a.M >= LBM && a.N >= LBN;
+}
 inline dim3 grid_for(const GemmArgs& a, int splits) {
+  if (use_big_tiles(a)) return dim3((a.N + LBN - 1) / LBN, (a.M + LBM - 1) / LBM, splits);
   return dim3((a.N + BN - 1) / BN, (a.M + BM - 1) / BM, splits);
 }
 
@@ -229,25 +379,29 @@ void launch_colsum(const float* X, int64_t ld, int64_t rows, int cols, float* ou
 }
 
 void launch_gemm_nn_simt(const GemmArgs& a, cudaStream_t s) {
-  gemm_simt_kernel<false, false, EPI_FWD><<<grid_for(a, 1), NT, 0, s>>>(a, a.K);
+  if (use_big_tiles(a)) gemm_simt128_kernel<false, false, EPI_FWD><<<grid_for(a, 1), NT, 0, s>>>(a, a.K);
+  else gemm_simt_kernel<false, false, EPI_FWD><<<grid_for(a, 1), NT, 0, s>>>(a, a.K);
 }
 
 void launch_gemm_nt_simt(const GemmArgs& a, cudaStream_t s) {
-  gemm_simt_kernel<false, true, EPI_DGRAD><<<grid_for(a, 1), NT, 0, s>>>(a, a.K);
+  if (use_big_tiles(a)) gemm_simt128_kernel<false, true, EPI_DGRAD><<<grid_for(a, 1), NT, 0, s>>>(a, a.K);
+  else gemm_simt_kernel<false, true, EPI_DGRAD><<<grid_for(a, 1), NT, 0, s>>>(a, a.K);
 }
 
 namespace {
 // split the batch contraction so that the grid covers the 148 SMs a few times over
 void tn_splits(const GemmArgs& a, int* splits_out, int* kps_out) {
-  const int tiles = ((a.N + BN - 1) / BN) * ((a.M + BM - 1) / BM);
+  const bool big = use_big_tiles(a);
+  const int bm = big ? LBM : BM, bn = big ? LBN : BN, bk = big ? 2 * LBK : BK;   // (k ranges in multiples of 16 either way)
+  const int tiles = ((a.N + bn - 1) / bn) * ((a.M + bm - 1) / bm);
   int splits = a.splitk > 0 ? a.splitk : 1;
   if (a.splitk <= 1) {
-    const int want = (4 * kNumSMs + tiles - 1) / tiles;
-    const int max_splits = (a.K + 4 * BK - 1) / (4 * BK);
+    const int want = ((big ? 2 : 4) * kNumSMs + tiles - 1) / tiles;
+    const int max_splits = (a.K + 4 * bk - 1) / (4 * bk);
     splits = max(1, min(want, max_splits));
   }
   int kps = (a.K + splits - 1) / splits;
-  kps = ((kps + BK - 1) / BK) * BK;
+  kps = ((kps + bk - 1) / bk) * bk;
   *splits_out = (a.K + kps - 1) / kps;
   *kps_out = kps;
 }
@@ -264,7 +418,8 @@ void launch_gemm_tn_simt(const GemmArgs& a, cudaStream_t s) {
   int splits, kps;
   tn_splits(a, &splits, &kps);
   if (splits > 1 && a.ws == nullptr) { splits = 1; kps = ((a.K + BK - 1) / BK) * BK; }   // no workspace: one ordered pass
-  gemm_simt_kernel<true, false, EPI_WGRAD><<<grid_for(a, splits), NT, 0, s>>>(a, kps);
+  if (use_big_tiles(a)) gemm_simt128_kernel<true, false, EPI_WGRAD><<<grid_for(a, splits), NT, 0, s>>>(a, kps);
+  else gemm_simt_kernel<true, false, EPI_WGRAD><<<grid_for(a, splits), NT, 0, s>>>(a, kps);
   if (splits > 1) {
     const int64_t total = (int64_t)a.M * a.N + (a.bias_grad ? a.N : 0);
     const int64_t want = (total + 255) / 256;
