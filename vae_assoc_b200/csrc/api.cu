@@ -781,6 +781,8 @@ void build_ops(Ctx* c) {
   c->free_op_ws();
   group_destroy(c->gplan);
   c->gplan = group_create();
+  // z has pitch n_z, the heads' gradient 2 n_z: 64-deep k-blocks need both to be <= 32 or multiples of 32 floats
+  group_set_deep_k(c->gplan, c->cfg.n_z <= 16 || c->cfg.n_z % 32 == 0);
   c->fused = false;
   c->ops_colsum_dec.clear(); c->ops_colsum_enc.clear();
   c->ops_fwd_enc.clear(); c->ops_latent_fwd.clear(); c->ops_fwd_dec.clear(); c->ops_loss.clear();

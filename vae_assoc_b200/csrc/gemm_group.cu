@@ -1390,6 +1390,7 @@ struct GroupPlan {
   uint32_t* d_counters = nullptr;    // row-block completion counters of the step (not owned; self-cleaning)
   int n_counters = 0;
   int half_off = 0;                  // offset of the half-tile counters (0: none)
+  bool allow_k64 = true;             // 64-deep k-blocks permitted for this plan's problems (group_set_deep_k)
   bool uploaded = false;
 };
 
@@ -1476,7 +1477,7 @@ int group_add_problem(GroupPlan* g, int kind, const GemmArgs& a, char* err, int 
   // ... and where the K-major operands' chunk reads past K stay inside the row's zero pad (pitch a multiple of 32
   // floats: every activation / weight of the dense modalities) or are cut by the map itself (pitch below 32: z, d heads)
   auto k_major_ok = [](int64_t ld) { return ld % 32 == 0 || ld <= 32; };
-  const bool k64 = deep_k_enabled() && BN <= 64 && batch_rows <= 3 * BM &&
+  const bool k64 = deep_k_enabled() && g->allow_k64 && BN <= 64 && batch_rows <= 3 * BM &&
                    (kind == 2 || (k_major_ok(a.lda) && (kind == 0 || k_major_ok(a.ldb))));
   const int rpc = rows_per_cta(a.M, small_rows_enabled());
   const int bk = k64 ? 64 : 32;
@@ -1577,6 +1578,9 @@ void group_set_counters(GroupPlan* g, uint32_t* d_counters, int n, int half_off)
   g->d_counters = d_counters; g->n_counters = n; g->half_off = half_off;
 }
 int group_problem_bn(const GroupPlan* g, int prob) { return g->problems[prob].BN; }
+// a launch site must not mix 32- and 64-deep problems: a plan whose fused sites contain K-major operands with a pitch
+// that is neither <= 32 nor a multiple of 32 floats (z / d heads at unusual latent widths) switches 64-deep k-blocks off
+void group_set_deep_k(GroupPlan* g, bool allow) { g->allow_k64 = allow; }
 
 bool group_upload(GroupPlan* g, char* err, int errlen) {
   if (g->uploaded) return true;

@@ -78,6 +78,7 @@ constexpr int kTaskHalf = 4096, kTaskSigHalf = 8192;
 int group_add_task(GroupPlan* g, int prob, int m_blk, int n_blk, int kb0, int nkb, int wait_ctr, int wait_cnt,
                    int wait_val, int wait2_ctr, int wait2_val, int signal_ctr, int extra_flags = 0);
 int group_problem_bn(const GroupPlan* g, int prob);
+void group_set_deep_k(GroupPlan* g, bool allow);   // call before adding problems
 int group_num_tasks(const GroupPlan* g);
 // elementwise task over the 256 rows of row block m_blk, executed by the epilogue warps of whichever CTA pair pops it
 // (kind 0: latent forward, 1: latent backward -- arguments from group_set_elem); waits / signals like a tile task
