@@ -453,6 +453,19 @@ def test_single_modality_one_launch(va, which, batch):
     model.close()
 
 
+@pytest.mark.parametrize("batch", [40, 200, 256])
+def test_gradient_step_rows_split_over_the_cta_pair(va, batch):
+    """Batches of at most 256 rows are one row block whose rows the two CTAs of a pair share evenly (rows_per_cta(),
+    csrc/gemm_group.cu): 24 + 16 rows at B = 40, 104 + 96 at B = 200 (the leader's last warp holds 8 live rows), 128 + 128
+    at 256 -- with 64-deep k-blocks and split-K heads on top.  Smooth activation, so every gradient is held to 5e-4 in the
+    max norm against the operand-rounding oracle."""
+    archs = vo.reference_archs(4)
+    model, oracle = make_pair(va, archs, batch, "softplus", "tf32", seed=31)
+    X, eps = inputs(archs, batch, seed=31)
+    check_step(model, oracle, X, eps, tol=5e-4)
+    model.close()
+
+
 @pytest.mark.parametrize("f", ["relu", "softplus"])
 def test_gradient_step_ragged_row_blocks(va, f):
     """B = 700 (two full 256-row blocks + a ragged one) through the two-launch tf32 schedule vs the operand-rounding
