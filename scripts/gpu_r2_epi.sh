@@ -2,6 +2,8 @@
 # round 2: where the tile epilogue's time goes -- four-segment schedule without dependency waits (pure throughput of the
 # tile engine; wrong results, timing only) with parts of the NN / NT epilogue switched off
 mkdir -p gpurun_out
+# (the SKIP / TMA-store switches live in the debug build: python -m vae_assoc_b200.build --epi-debug)
+export VAEASSOC_LIB=$PWD/vae_assoc_b200/libvaeassoc_dbg.so
 run() {
   env VAEASSOC_DEBUG_NODEPS=1 $1 timeout 300 python bench.py --batch 8192 --steps 50 --warmup 10 --no-cpu-baseline --no-parity --no-secondary 2>/dev/null | python -c "
 import sys, json
